@@ -1,0 +1,140 @@
+// Shared device/host helpers for libaccbpg_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/accbpg_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define ACCBPG_HOST_ONLY 1
+#endif
+
+namespace accbpg {
+
+constexpr int kSlots = 256;          // result slots per context
+constexpr int kMaxBlocks = 1184;     // 148 SMs x 8: upper bound on reduction grid sizes
+constexpr int kPartialStride = kMaxBlocks;
+constexpr int kPartialRows = 4;      // up to 4 simultaneous reduction outputs per kernel
+
+struct Ctx {
+    int device;
+    int sm_count;
+    double* d_slots;        // kSlots doubles
+    uint32_t* d_status;     // status word
+    double* d_partials;     // kPartialRows * kPartialStride doubles (double-buffered by the simplex kernel)
+    long long* d_ipartials; // kPartialStride int64 (arg-reductions)
+    unsigned int* d_counter;// "last block done" ticket
+    double* h_slots;        // pinned mirror (kSlots doubles)
+    uint32_t* h_status;     // pinned
+    int coop_blocks_burg;   // co-resident grid size for the Burg-simplex kernel
+};
+
+extern thread_local char g_err[512];
+extern unsigned long long g_launches;
+
+inline int set_err(const char* what, cudaError_t e) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return ACCBPG_E_CUDA;
+}
+inline int arg_err(const char* what) {
+    snprintf(g_err, sizeof(g_err), "bad argument: %s", what);
+    return ACCBPG_E_ARG;
+}
+
+#define ACCBPG_CUDA(call)                                         \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return accbpg::set_err(#call, e__); \
+    } while (0)
+
+#define ACCBPG_LAUNCHED(name)                                     \
+    do {                                                          \
+        ++accbpg::g_launches;                                     \
+        cudaError_t e__ = cudaGetLastError();                     \
+        if (e__ != cudaSuccess) return accbpg::set_err(name, e__); \
+    } while (0)
+
+// defined in dopt.cu: byte offset of Linv (mp x mp, zero padded) inside the dopt workspace
+size_t dopt_linv_offset(int m, int64_t n, int sm_count, int* mp_out);
+
+inline int grid_for(const Ctx* c, int64_t n, int threads, int items_per_thread, int blocks_per_sm) {
+    int64_t per_block = (int64_t)threads * items_per_thread;
+    int64_t want = (n + per_block - 1) / per_block;
+    int64_t cap = (int64_t)c->sm_count * blocks_per_sm;
+    if (cap > kMaxBlocks) cap = kMaxBlocks;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum with a fixed tree; every thread gets the result.  blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ double block_sum(double v, double* sh /* >= 32 doubles */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();                 // protect sh against a previous use
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double r = (lane < nw) ? sh[lane] : 0.0;
+    r = warp_sum(r);
+    return r;
+}
+__device__ __forceinline__ double block_min(double v, double* sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_min(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double r = (lane < nw) ? sh[lane] : __longlong_as_double(0x7ff0000000000000LL);
+    r = warp_min(r);
+    return r;
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double r = (lane < nw) ? sh[lane] : __longlong_as_double(0xfff0000000000000LL);
+    r = warp_max(r);
+    return r;
+}
+
+// "last block done" ticket: returns true in exactly one block (the last to arrive), after all other
+// blocks' global writes issued before the call are visible to it.
+__device__ __forceinline__ bool last_block_ticket(unsigned int* counter, bool* sh_flag) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        bool last = (t == gridDim.x * gridDim.y - 1);
+        *sh_flag = last;
+        if (last) *counter = 0u;     // re-arm for the next kernel on the stream
+    }
+    __syncthreads();
+    bool last = *sh_flag;
+    if (last) __threadfence();
+    return last;
+}
+
+__device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
+#endif  // __CUDACC__
+
+}  // namespace accbpg

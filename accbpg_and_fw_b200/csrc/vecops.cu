@@ -1,0 +1,695 @@
+// Context management, iterate arithmetic, Burg / Shannon Bregman kernels and the simplex LMO.
+// HBM-bound elementwise + reduction kernels; every reduction is a fixed tree (per-thread grid-stride
+// partial -> warp shuffle -> block -> ordered sum of block partials by the last block to finish).
+// Compiled with -fmad=false: expressions are rounded exactly as NumPy rounds them (no contraction).
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace accbpg {
+thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
+
+constexpr int kThreads = 256;
+#define kInf (__longlong_as_double(0x7ff0000000000000LL))
+
+// ---------------------------------------------------------------- generic multi-output sum reduction
+// F::operator()(int64_t i, double* acc, uint32_t& st) accumulates element i into acc[0..NOUT)
+template <int NOUT, class F>
+__global__ void __launch_bounds__(kThreads) reduce_sum_kernel(int64_t n, F f, double* partials,
+                                                              unsigned int* counter, double* out,
+                                                              uint32_t* status) {
+    __shared__ double sh[32];
+    __shared__ bool is_last;
+    double acc[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) acc[o] = 0.0;
+    uint32_t st = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, acc, st);
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+        double s = block_sum(acc[o], sh);
+        if (threadIdx.x == 0) partials[o * kPartialStride + blockIdx.x] = s;
+    }
+    if (st) atomicOr(status, st);
+    if (last_block_ticket(counter, &is_last)) {
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            double s = 0.0;
+            for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+                s += ld_cg(&partials[o * kPartialStride + b]);
+            s = block_sum(s, sh);
+            if (threadIdx.x == 0) out[o] = s;
+        }
+    }
+}
+
+template <int NOUT, class F>
+static int launch_reduce(Ctx* c, cudaStream_t s, int64_t n, F f, double* d_out, const char* name) {
+    int grid = grid_for(c, n, kThreads, 4, 4);
+    reduce_sum_kernel<NOUT, F><<<grid, kThreads, 0, s>>>(n, f, c->d_partials, c->d_counter, d_out, c->d_status);
+    ACCBPG_LAUNCHED(name);
+    return ACCBPG_OK;
+}
+
+template <class F>
+__global__ void __launch_bounds__(kThreads) map_kernel(int64_t n, F f, uint32_t* status) {
+    uint32_t st = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, st);
+    if (st) atomicOr(status, st);
+}
+
+template <class F>
+static int launch_map(Ctx* c, cudaStream_t s, int64_t n, F f, const char* name) {
+    int grid = grid_for(c, n, kThreads, 2, 8);
+    map_kernel<F><<<grid, kThreads, 0, s>>>(n, f, c->d_status);
+    ACCBPG_LAUNCHED(name);
+    return ACCBPG_OK;
+}
+
+// ---------------------------------------------------------------- functors: iterate arithmetic
+struct AxpbyF {
+    double a, b; const double *x, *y; double* out;
+    __device__ void operator()(int64_t i, uint32_t&) const {
+        out[i] = __dadd_rn(__dmul_rn(a, x[i]), __dmul_rn(b, y[i]));
+    }
+};
+struct StepTowardF {   // x + a*(s - x)
+    double a; const double *x, *s; double* out;
+    __device__ void operator()(int64_t i, uint32_t&) const {
+        double xi = x[i];
+        out[i] = __dadd_rn(xi, __dmul_rn(a, __dsub_rn(s[i], xi)));
+    }
+};
+struct DivideF {
+    double denom; const double* x; double* out;
+    __device__ void operator()(int64_t i, uint32_t&) const { out[i] = x[i] / denom; }
+};
+struct DotF {
+    const double *x, *y;
+    __device__ void operator()(int64_t i, double* acc, uint32_t&) const { acc[0] += __dmul_rn(x[i], y[i]); }
+};
+struct DotDiffF {
+    const double *g, *a, *b;
+    __device__ void operator()(int64_t i, double* acc, uint32_t&) const {
+        acc[0] += __dmul_rn(g[i], __dsub_rn(a[i], b[i]));
+    }
+};
+struct SumF {
+    const double* x;
+    __device__ void operator()(int64_t i, double* acc, uint32_t&) const { acc[0] += x[i]; }
+};
+
+// ---------------------------------------------------------------- functors: Burg entropy
+struct BurgValueF {     // -sum log x
+    const double* x;
+    __device__ void operator()(int64_t i, double* acc, uint32_t& st) const {
+        double xi = x[i];
+        if (!(xi > 0.0)) st |= ACCBPG_ST_ARG_NOT_POS;
+        acc[0] += -log(xi);      // sum of negated terms rounds exactly like the negated sum
+    }
+};
+struct BurgGradF {
+    const double* x; double* out;
+    __device__ void operator()(int64_t i, uint32_t& st) const {
+        double xi = x[i];
+        if (!(xi > 0.0)) st |= ACCBPG_ST_ARG_NOT_POS;
+        out[i] = -1.0 / xi;
+    }
+};
+struct BurgDivF {       // sum (x/y - log(x/y) - 1)
+    const double *x, *y;
+    __device__ void operator()(int64_t i, double* acc, uint32_t& st) const {
+        double xi = x[i], yi = y[i];
+        if (!(xi > 0.0) || !(yi > 0.0)) st |= ACCBPG_ST_ARG_NOT_POS;
+        double r = xi / yi;
+        acc[0] += (r - log(r)) - 1.0;
+    }
+};
+// shifted gradient s = g - L*(-1/y) (or g when y == nullptr)
+__device__ __forceinline__ double burg_shift(const double* y, const double* g, double L, int64_t i, uint32_t& st) {
+    double gi = g[i];
+    if (y != nullptr) {
+        double yi = y[i];
+        if (!(yi > 0.0)) st |= ACCBPG_ST_ARG_NOT_POS;
+        gi = gi - L * (-1.0 / yi);
+    }
+    return gi;
+}
+struct BurgProxF {
+    int kind; double lamda, L, four_lamL, two_lamL; const double *y, *g; double* out;
+    __device__ void operator()(int64_t i, uint32_t& st) const {
+        double s = burg_shift(y, g, L, i, st);
+        double r;
+        if (kind == ACCBPG_BURG_PLAIN) {
+            if (!(s > 0.0)) st |= ACCBPG_ST_PROX_NOT_POS;
+            r = L / s;
+        } else if (kind == ACCBPG_BURG_L1) {
+            if (!(s > -lamda)) st |= ACCBPG_ST_PROX_NOT_POS;
+            r = L / (lamda + s);
+        } else {
+            double gg = s / L;
+            r = (sqrt(gg * gg + four_lamL) - gg) / two_lamL;
+        }
+        out[i] = r;
+    }
+};
+struct BurgSimplexSumsF {
+    const double* gg; double c;
+    __device__ void operator()(int64_t i, double* acc, uint32_t&) const {
+        double t = gg[i] + c;
+        acc[0] += 1.0 / t;
+        acc[1] += -1.0 / (t * t);
+    }
+};
+struct BurgSimplexFinishF {
+    const double* gg; double c; double* out;
+    __device__ void operator()(int64_t i, uint32_t&) const { out[i] = 1.0 / (gg[i] + c); }
+};
+
+// ---------------------------------------------------------------- functors: Shannon entropy
+struct ShannonValueF {
+    const double* x; double delta;
+    __device__ void operator()(int64_t i, double* acc, uint32_t& st) const {
+        double xi = x[i];
+        if (!(xi >= 0.0)) st |= ACCBPG_ST_ARG_NEGATIVE;
+        double xx = fmax(xi, delta);
+        acc[0] += xx * log(xx);
+    }
+};
+struct ShannonGradF {
+    const double* x; double delta; double* out;
+    __device__ void operator()(int64_t i, uint32_t& st) const {
+        double xi = x[i];
+        if (!(xi >= 0.0)) st |= ACCBPG_ST_ARG_NEGATIVE;
+        out[i] = 1.0 + log(fmax(xi, delta));
+    }
+};
+struct ShannonDivF {    // acc0 = sum x log((x+d)/(y+d)); acc1 = sum y; acc2 = sum x
+    const double *x, *y; double delta;
+    __device__ void operator()(int64_t i, double* acc, uint32_t& st) const {
+        double xi = x[i], yi = y[i];
+        if (!(xi >= 0.0) || !(yi >= 0.0)) st |= ACCBPG_ST_ARG_NEGATIVE;
+        acc[0] += xi * log((xi + delta) / (yi + delta));
+        acc[1] += yi;
+        acc[2] += xi;
+    }
+};
+__device__ __forceinline__ double shannon_point(const double* y, const double* g, double lamda, double L,
+                                                int need_pos, int64_t i, uint32_t& st) {
+    double gi = g[i];
+    if (lamda != 0.0) gi = lamda + gi;          // ShannonEntropyL1: prox on (lamda + g)
+    if (y == nullptr) return exp(-gi / L - 1.0);
+    double yi = y[i];
+    if (need_pos) { if (!(yi > 0.0)) st |= ACCBPG_ST_Y_NOT_POS; }
+    else          { if (!(yi >= 0.0)) st |= ACCBPG_ST_ARG_NEGATIVE; }
+    return yi * exp(-gi / L);
+}
+struct ShannonProxF {
+    double lamda, L; const double *y, *g; double* out;
+    __device__ void operator()(int64_t i, uint32_t& st) const { out[i] = shannon_point(y, g, lamda, L, 0, i, st); }
+};
+struct ShannonProxSumF {   // writes the un-normalised point and accumulates its sum
+    double lamda, L; const double *y, *g; double* out;
+    __device__ void operator()(int64_t i, double* acc, uint32_t& st) const {
+        double v = shannon_point(y, g, lamda, L, 1, i, st);
+        out[i] = v;
+        acc[0] += v;
+    }
+};
+struct DivideBySlotF {
+    const double* x; const double* denom; double* out;
+    __device__ void operator()(int64_t i, uint32_t&) const { out[i] = x[i] / ld_cg(denom); }
+};
+
+// ---------------------------------------------------------------- LMO functors
+struct FillVertexF {
+    double fill, radius; int64_t idx; double* out;
+    __device__ void operator()(int64_t i, uint32_t&) const { out[i] = (i == idx) ? radius : fill; }
+};
+struct FillVertexSlotF {   // vertex index read from a device slot
+    double fill, radius; const double* idx_slot; double* out;
+    __device__ void operator()(int64_t i, uint32_t&) const {
+        int64_t idx = (int64_t)ld_cg(idx_slot);
+        out[i] = (i == idx) ? radius : fill;
+    }
+};
+struct LmoLinfF {
+    double radius; const double *g, *center; double* out;
+    __device__ void operator()(int64_t i, uint32_t&) const {
+        double gi = g[i];
+        double sg = (gi > 0.0) ? 1.0 : ((gi < 0.0) ? -1.0 : gi);   // np.sign (nan stays nan)
+        double ci = center ? center[i] : 0.0;
+        out[i] = ci - radius * sg;
+    }
+};
+struct LmoL2F {
+    double radius, gnorm; const double *g, *center; double* out;
+    __device__ void operator()(int64_t i, uint32_t&) const {
+        double ci = center ? center[i] : 0.0;
+        out[i] = ci - radius * g[i] / gnorm;      // (radius*g)/gnorm, left to right as in NumPy
+    }
+};
+struct LmoBoxF {
+    const double *g, *lo, *hi; double* out;
+    __device__ void operator()(int64_t i, uint32_t&) const { out[i] = (g[i] < 0.0) ? hi[i] : lo[i]; }
+};
+
+// ---------------------------------------------------------------- min / max / arg-extremum
+__global__ void __launch_bounds__(kThreads) minmax_kernel(int64_t n, const double* x, double* partials,
+                                                          unsigned int* counter, double* out) {
+    __shared__ double sh[32];
+    __shared__ bool is_last;
+    double lo = kInf, hi = -kInf;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double v = x[i];
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    lo = block_min(lo, sh);
+    hi = block_max(hi, sh);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = lo;
+        partials[kPartialStride + blockIdx.x] = hi;
+    }
+    if (last_block_ticket(counter, &is_last)) {
+        lo = kInf; hi = -kInf;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+            lo = fmin(lo, ld_cg(&partials[b]));
+            hi = fmax(hi, ld_cg(&partials[kPartialStride + b]));
+        }
+        lo = block_min(lo, sh);
+        hi = block_max(hi, sh);
+        if (threadIdx.x == 0) { out[0] = lo; out[1] = hi; }
+    }
+}
+
+// (value, first index) extremum.  sign = +1 argmin, -1 argmax (compares sign*x).
+__device__ __forceinline__ void arg_combine(double& v, long long& i, double v2, long long i2) {
+    if (v2 < v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+}
+__device__ __forceinline__ void block_argmin(double& v, long long& i, double* shv, long long* shi) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        long long i2 = __shfl_xor_sync(0xffffffffu, i, o);
+        arg_combine(v, i, v2, i2);
+    }
+    __syncthreads();
+    if (lane == 0) { shv[wid] = v; shi[wid] = i; }
+    __syncthreads();
+    v = (lane < nw) ? shv[lane] : kInf;
+    i = (lane < nw) ? shi[lane] : 0x7fffffffffffffffLL;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        long long i2 = __shfl_xor_sync(0xffffffffu, i, o);
+        arg_combine(v, i, v2, i2);
+    }
+}
+__global__ void __launch_bounds__(kThreads) argext_kernel(int64_t n, const double* x, double sign,
+                                                          double* partials, long long* ipartials,
+                                                          unsigned int* counter, double* out) {
+    __shared__ double shv[32];
+    __shared__ long long shi[32];
+    __shared__ bool is_last;
+    double v = kInf;
+    long long idx = 0x7fffffffffffffffLL;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double xi = sign * x[i];
+        if (xi < v) { v = xi; idx = i; }       // strict: first index wins inside a thread
+    }
+    block_argmin(v, idx, shv, shi);
+    if (threadIdx.x == 0) { partials[blockIdx.x] = v; ipartials[blockIdx.x] = idx; }
+    if (last_block_ticket(counter, &is_last)) {
+        v = kInf; idx = 0x7fffffffffffffffLL;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+            arg_combine(v, idx, ld_cg(&partials[b]), __ldcg(&ipartials[b]));
+        block_argmin(v, idx, shv, shi);
+        if (threadIdx.x == 0) { out[0] = sign * v; out[1] = (double)idx; }
+    }
+}
+
+// ---------------------------------------------------------------- Burg-simplex persistent root-find
+// One cooperative kernel replays accbpg/functions.py:341-356 without leaving the device:
+//   gg = (g [- L*(-1/y)]) / L ; cmin = -min gg ; c = cmin+1 ; bisection while sum 1/(gg+c) - 1 < 0 ;
+//   Newton on fc = sum 1/(gg+c) - 1 with fpc = sum -1/(gg+c)^2 ; x = 1/(gg+c).
+// gg lives in the output buffer; each pass reads it back (L2 resident for n <= 10^6) and produces both
+// sums, so one grid-wide sync per pass.  Block partials are double buffered across passes.
+constexpr int kBurgThreads = 512;
+
+__device__ __forceinline__ void grid_sum2(cg::grid_group& grid, double a, double b, double* partials,
+                                          int parity, double* sh, double& ra, double& rb) {
+    a = block_sum(a, sh);
+    b = block_sum(b, sh);
+    double* pa = partials + (size_t)parity * kPartialStride;
+    double* pb = partials + (size_t)(2 + parity) * kPartialStride;
+    if (threadIdx.x == 0) { pa[blockIdx.x] = a; pb[blockIdx.x] = b; }
+    grid.sync();
+    double sa = 0.0, sb = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) { sa += ld_cg(&pa[k]); sb += ld_cg(&pb[k]); }
+    ra = block_sum(sa, sh);
+    rb = block_sum(sb, sh);
+}
+
+__global__ void __launch_bounds__(kBurgThreads) burg_simplex_kernel(int64_t n, const double* y, const double* g,
+                                                                    double L, double eps, double* out,
+                                                                    double* info, double* partials,
+                                                                    uint32_t* status) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[32];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t st = 0;
+    double lo = kInf;
+    for (int64_t i = first; i < n; i += stride) {
+        double gg = burg_shift(y, g, L, i, st) / L;
+        out[i] = gg;
+        lo = fmin(lo, gg);
+    }
+    lo = block_min(lo, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = lo;
+    grid.sync();
+    lo = kInf;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) lo = fmin(lo, ld_cg(&partials[k]));
+    lo = block_min(lo, sh);
+    const double cmin = -lo;
+    double c = cmin + 1.0;
+    int parity = 1, nbis = 0, nnewton = 0;
+    double s1, s2;
+    // bisection: halve toward cmin until sum 1/(gg+c) - 1 >= 0   (functions.py:344-346)
+    for (;;) {
+        double a = 0.0, b = 0.0;
+        for (int64_t i = first; i < n; i += stride) {
+            double t = out[i] + c;
+            a += 1.0 / t;
+            b += -1.0 / (t * t);
+        }
+        grid_sum2(grid, a, b, partials, parity, sh, s1, s2);
+        parity ^= 1;
+        if (s1 - 1.0 < 0.0 && nbis < 2000) { c = (cmin + c) / 2.0; ++nbis; }
+        else break;
+    }
+    double fc = s1 - 1.0;
+    // Newton  (functions.py:348-354); s2 already holds fpc at the current c
+    while (fabs(fc) > eps) {
+        double fpc = s2;
+        double cn = c - fc / fpc;
+        if (c - cn == 0.0) break;
+        c = cn;
+        double a = 0.0, b = 0.0;
+        for (int64_t i = first; i < n; i += stride) {
+            double t = out[i] + c;
+            a += 1.0 / t;
+            b += -1.0 / (t * t);
+        }
+        grid_sum2(grid, a, b, partials, parity, sh, s1, s2);
+        parity ^= 1;
+        fc = s1 - 1.0;
+        if (++nnewton >= 200) { st |= ACCBPG_ST_NEWTON_MAXIT; break; }
+    }
+    // the grid.sync inside the last grid_sum2 came after every block's read loop: gg may be overwritten
+    for (int64_t i = first; i < n; i += stride) out[i] = 1.0 / (out[i] + c);
+    if (st) atomicOr(status, st);
+    if (info != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        info[0] = (double)nbis; info[1] = (double)nnewton; info[2] = c;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) burg_prepare_kernel(int64_t n, const double* y, const double* g,
+                                                                double L, double* gg, double* partials,
+                                                                unsigned int* counter, double* out,
+                                                                uint32_t* status) {
+    __shared__ double sh[32];
+    __shared__ bool is_last;
+    uint32_t st = 0;
+    double lo = kInf;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double v = burg_shift(y, g, L, i, st) / L;
+        gg[i] = v;
+        lo = fmin(lo, v);
+    }
+    lo = block_min(lo, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = lo;
+    if (st) atomicOr(status, st);
+    if (last_block_ticket(counter, &is_last)) {
+        lo = kInf;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) lo = fmin(lo, ld_cg(&partials[b]));
+        lo = block_min(lo, sh);
+        if (threadIdx.x == 0) out[0] = lo;
+    }
+}
+
+}  // namespace accbpg
+
+using namespace accbpg;
+
+// ======================================================================== C ABI
+extern "C" {
+
+int accbpg_abi_version(void) { return ACCBPG_ABI_VERSION; }
+const char* accbpg_last_error(void) { return g_err; }
+uint64_t accbpg_launch_count(void) { return g_launches; }
+
+int accbpg_ctx_create(void** out) {
+    if (!out) return arg_err("ctx out pointer is NULL");
+    Ctx* c = new Ctx();
+    ACCBPG_CUDA(cudaGetDevice(&c->device));
+    ACCBPG_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    ACCBPG_CUDA(cudaMalloc(&c->d_slots, kSlots * sizeof(double)));
+    ACCBPG_CUDA(cudaMalloc(&c->d_status, 256));
+    ACCBPG_CUDA(cudaMalloc(&c->d_partials, (size_t)kPartialRows * kPartialStride * sizeof(double)));
+    ACCBPG_CUDA(cudaMalloc(&c->d_ipartials, (size_t)kPartialStride * sizeof(long long)));
+    ACCBPG_CUDA(cudaMalloc(&c->d_counter, 256));
+    ACCBPG_CUDA(cudaMemset(c->d_slots, 0, kSlots * sizeof(double)));
+    ACCBPG_CUDA(cudaMemset(c->d_status, 0, 256));
+    ACCBPG_CUDA(cudaMemset(c->d_counter, 0, 256));
+    ACCBPG_CUDA(cudaMallocHost(&c->h_slots, kSlots * sizeof(double)));
+    ACCBPG_CUDA(cudaMallocHost(&c->h_status, 64));
+    int per_sm = 0;
+    ACCBPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, burg_simplex_kernel, kBurgThreads, 0));
+    if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "burg_simplex_kernel cannot be made resident"); return ACCBPG_E_CUDA; }
+    if (per_sm > 2) per_sm = 2;
+    c->coop_blocks_burg = c->sm_count * per_sm;
+    if (c->coop_blocks_burg > kMaxBlocks) c->coop_blocks_burg = kMaxBlocks;
+    ACCBPG_CUDA(cudaDeviceSynchronize());
+    *out = c;
+    return ACCBPG_OK;
+}
+
+int accbpg_ctx_destroy(void* ctx) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return ACCBPG_OK;
+    cudaFree(c->d_slots); cudaFree(c->d_status); cudaFree(c->d_partials);
+    cudaFree(c->d_ipartials); cudaFree(c->d_counter);
+    cudaFreeHost(c->h_slots); cudaFreeHost(c->h_status);
+    delete c;
+    return ACCBPG_OK;
+}
+
+double* accbpg_ctx_slots(void* ctx) { return ctx ? ((Ctx*)ctx)->d_slots : nullptr; }
+int accbpg_ctx_sm_count(void* ctx) { return ctx ? ((Ctx*)ctx)->sm_count : 0; }
+
+int accbpg_ctx_read(void* ctx, void* stream, const double* d_src, int count, double* h_out, uint32_t* h_status) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c) return arg_err("ctx is NULL");
+    if (count < 0 || count > kSlots) return arg_err("ctx_read: count must be in [0, 256]");
+    if (count > 0 && (!d_src || !h_out)) return arg_err("ctx_read: NULL pointer");
+    if (count > 0)
+        ACCBPG_CUDA(cudaMemcpyAsync(c->h_slots, d_src, count * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ACCBPG_CUDA(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ACCBPG_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(uint32_t), s));
+    ACCBPG_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < count; ++i) h_out[i] = c->h_slots[i];
+    if (h_status) *h_status = *c->h_status;
+    return ACCBPG_OK;
+}
+
+#define CTX_STREAM                       \
+    Ctx* c = (Ctx*)ctx;                  \
+    cudaStream_t s = (cudaStream_t)stream; \
+    if (!c) return arg_err("ctx is NULL"); \
+    if (n < 0) return arg_err("n < 0");
+
+int accbpg_vec_axpby(void* ctx, void* stream, int64_t n, double a, const double* x, double b, const double* y,
+                     double* out) {
+    CTX_STREAM
+    if (n == 0) return ACCBPG_OK;
+    return launch_map(c, s, n, AxpbyF{a, b, x, y, out}, "vec_axpby");
+}
+int accbpg_vec_step_toward(void* ctx, void* stream, int64_t n, const double* x, const double* sv, double a,
+                           double* out) {
+    CTX_STREAM
+    if (n == 0) return ACCBPG_OK;
+    return launch_map(c, s, n, StepTowardF{a, x, sv, out}, "vec_step_toward");
+}
+int accbpg_vec_divide(void* ctx, void* stream, int64_t n, const double* x, double denom, double* out) {
+    CTX_STREAM
+    if (n == 0) return ACCBPG_OK;
+    return launch_map(c, s, n, DivideF{denom, x, out}, "vec_divide");
+}
+int accbpg_vec_dot(void* ctx, void* stream, int64_t n, const double* x, const double* y, double* d_out) {
+    CTX_STREAM
+    return launch_reduce<1>(c, s, n, DotF{x, y}, d_out, "vec_dot");
+}
+int accbpg_vec_dot_diff(void* ctx, void* stream, int64_t n, const double* g, const double* a, const double* b,
+                        double* d_out) {
+    CTX_STREAM
+    return launch_reduce<1>(c, s, n, DotDiffF{g, a, b}, d_out, "vec_dot_diff");
+}
+int accbpg_vec_sum(void* ctx, void* stream, int64_t n, const double* x, double* d_out) {
+    CTX_STREAM
+    return launch_reduce<1>(c, s, n, SumF{x}, d_out, "vec_sum");
+}
+int accbpg_vec_minmax(void* ctx, void* stream, int64_t n, const double* x, double* d_out) {
+    CTX_STREAM
+    int grid = grid_for(c, n, kThreads, 4, 4);
+    minmax_kernel<<<grid, kThreads, 0, s>>>(n, x, c->d_partials, c->d_counter, d_out);
+    ACCBPG_LAUNCHED("vec_minmax");
+    return ACCBPG_OK;
+}
+int accbpg_vec_argext(void* ctx, void* stream, int64_t n, const double* x, int want_max, double* d_out) {
+    CTX_STREAM
+    int grid = grid_for(c, n, kThreads, 4, 4);
+    argext_kernel<<<grid, kThreads, 0, s>>>(n, x, want_max ? -1.0 : 1.0, c->d_partials, c->d_ipartials,
+                                            c->d_counter, d_out);
+    ACCBPG_LAUNCHED("vec_argext");
+    return ACCBPG_OK;
+}
+
+// ---- Burg
+int accbpg_burg_value(void* ctx, void* stream, int64_t n, const double* x, double* d_out) {
+    CTX_STREAM
+    return launch_reduce<1>(c, s, n, BurgValueF{x}, d_out, "burg_value");
+}
+int accbpg_burg_gradient(void* ctx, void* stream, int64_t n, const double* x, double* out) {
+    CTX_STREAM
+    if (n == 0) return ACCBPG_OK;
+    return launch_map(c, s, n, BurgGradF{x, out}, "burg_gradient");
+}
+int accbpg_burg_divergence(void* ctx, void* stream, int64_t n, const double* x, const double* y, double* d_out) {
+    CTX_STREAM
+    return launch_reduce<1>(c, s, n, BurgDivF{x, y}, d_out, "burg_divergence");
+}
+int accbpg_burg_prox(void* ctx, void* stream, int64_t n, int kind, double lamda, const double* y,
+                     const double* g, double L, double* out) {
+    CTX_STREAM
+    if (kind < 0 || kind > 2) return arg_err("burg kind");
+    if (!(L > 0.0)) return arg_err("L must be positive");
+    if (n == 0) return ACCBPG_OK;
+    double lamL = lamda / L;
+    return launch_map(c, s, n, BurgProxF{kind, lamda, L, 4 * lamL, 2 * lamL, y, g, out}, "burg_prox");
+}
+int accbpg_burg_simplex_prox(void* ctx, void* stream, int64_t n, const double* y, const double* g, double L,
+                             double eps, double* out, double* info) {
+    CTX_STREAM
+    if (!(L > 0.0)) return arg_err("L must be positive");
+    if (n < 1) return arg_err("n must be >= 1");
+    int64_t want = (n + kBurgThreads - 1) / kBurgThreads;
+    int grid = (int)(want < c->coop_blocks_burg ? want : c->coop_blocks_burg);
+    double* partials = c->d_partials;
+    uint32_t* status = c->d_status;
+    void* args[] = {&n, &y, &g, &L, &eps, &out, &info, &partials, &status};
+    ACCBPG_CUDA(cudaLaunchCooperativeKernel((void*)burg_simplex_kernel, dim3(grid), dim3(kBurgThreads), args, 0, s));
+    ACCBPG_LAUNCHED("burg_simplex_prox");
+    return ACCBPG_OK;
+}
+int accbpg_burg_simplex_prepare(void* ctx, void* stream, int64_t n, const double* y, const double* g, double L,
+                                double* gg, double* d_out) {
+    CTX_STREAM
+    if (!(L > 0.0)) return arg_err("L must be positive");
+    int grid = grid_for(c, n, kThreads, 4, 4);
+    burg_prepare_kernel<<<grid, kThreads, 0, s>>>(n, y, g, L, gg, c->d_partials, c->d_counter, d_out, c->d_status);
+    ACCBPG_LAUNCHED("burg_simplex_prepare");
+    return ACCBPG_OK;
+}
+int accbpg_burg_simplex_sums(void* ctx, void* stream, int64_t n, const double* gg, double cc, double* d_out) {
+    CTX_STREAM
+    return launch_reduce<2>(c, s, n, BurgSimplexSumsF{gg, cc}, d_out, "burg_simplex_sums");
+}
+int accbpg_burg_simplex_finish(void* ctx, void* stream, int64_t n, const double* gg, double cc, double* out) {
+    CTX_STREAM
+    if (n == 0) return ACCBPG_OK;
+    return launch_map(c, s, n, BurgSimplexFinishF{gg, cc, out}, "burg_simplex_finish");
+}
+
+// ---- Shannon
+int accbpg_shannon_value(void* ctx, void* stream, int64_t n, const double* x, double delta, double* d_out) {
+    CTX_STREAM
+    return launch_reduce<1>(c, s, n, ShannonValueF{x, delta}, d_out, "shannon_value");
+}
+int accbpg_shannon_gradient(void* ctx, void* stream, int64_t n, const double* x, double delta, double* out) {
+    CTX_STREAM
+    if (n == 0) return ACCBPG_OK;
+    return launch_map(c, s, n, ShannonGradF{x, delta, out}, "shannon_gradient");
+}
+__global__ void shannon_div_finish_kernel(const double* t, double* o) {   // sum(x log ..) + (sum y - sum x)
+    o[0] = t[0] + (t[1] - t[2]);
+}
+int accbpg_shannon_divergence(void* ctx, void* stream, int64_t n, const double* x, const double* y, double delta,
+                              double* d_out) {
+    CTX_STREAM
+    // three sums land in scratch slots 250..252, then are combined into d_out
+    double* tmp = c->d_slots + 250;
+    int rc = launch_reduce<3>(c, s, n, ShannonDivF{x, y, delta}, tmp, "shannon_divergence");
+    if (rc) return rc;
+    shannon_div_finish_kernel<<<1, 1, 0, s>>>(tmp, d_out);
+    ACCBPG_LAUNCHED("shannon_div_finish");
+    return ACCBPG_OK;
+}
+int accbpg_shannon_prox(void* ctx, void* stream, int64_t n, double lamda, const double* y, const double* g,
+                        double L, int normalize, double* out, double* d_sum_out) {
+    CTX_STREAM
+    if (!(L > 0.0)) return arg_err("L must be positive");
+    if (n == 0) return ACCBPG_OK;
+    if (!normalize) return launch_map(c, s, n, ShannonProxF{lamda, L, y, g, out}, "shannon_prox");
+    double* sum_slot = d_sum_out ? d_sum_out : (c->d_slots + 253);
+    int rc = launch_reduce<1>(c, s, n, ShannonProxSumF{lamda, L, y, g, out}, sum_slot, "shannon_prox_sum");
+    if (rc || normalize == 2) return rc;
+    return launch_map(c, s, n, DivideBySlotF{out, sum_slot, out}, "shannon_normalize");
+}
+
+// ---- LMO
+int accbpg_lmo_simplex(void* ctx, void* stream, int64_t n, const double* g, double radius, double* sv,
+                       double* d_out) {
+    CTX_STREAM
+    if (n < 1) return arg_err("n must be >= 1");
+    double* slot = d_out ? d_out : (c->d_slots + 254);
+    int rc = accbpg_vec_argext(ctx, stream, n, g, 0, slot);
+    if (rc) return rc;
+    return launch_map(c, s, n, FillVertexSlotF{1e-15, radius, slot + 1, sv}, "lmo_simplex_fill");
+}
+int accbpg_lmo_fill_vertex(void* ctx, void* stream, int64_t n, double fill, int64_t idx, double radius,
+                           double* sv) {
+    CTX_STREAM
+    if (n == 0) return ACCBPG_OK;
+    return launch_map(c, s, n, FillVertexF{fill, radius, idx, sv}, "lmo_fill_vertex");
+}
+int accbpg_lmo_linf(void* ctx, void* stream, int64_t n, const double* g, double radius, const double* center,
+                    double* sv) {
+    CTX_STREAM
+    if (n == 0) return ACCBPG_OK;
+    return launch_map(c, s, n, LmoLinfF{radius, g, center, sv}, "lmo_linf");
+}
+int accbpg_lmo_l2(void* ctx, void* stream, int64_t n, const double* g, double radius, double gnorm,
+                  const double* center, double* sv) {
+    CTX_STREAM
+    if (n == 0) return ACCBPG_OK;
+    return launch_map(c, s, n, LmoL2F{radius, gnorm, g, center, sv}, "lmo_l2");
+}
+int accbpg_lmo_box(void* ctx, void* stream, int64_t n, const double* g, const double* lo, const double* hi,
+                   double* sv) {
+    CTX_STREAM
+    if (n == 0) return ACCBPG_OK;
+    return launch_map(c, s, n, LmoBoxF{g, lo, hi, sv}, "lmo_box");
+}
+
+}  // extern "C"

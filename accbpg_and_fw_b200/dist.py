@@ -1,0 +1,98 @@
+"""Column (n) sharding of the design / data matrix over one-process-per-GPU ranks.
+
+The reference is single-process; the path shards naturally by columns:
+rank r owns columns [lo, hi) of H / A and the matching slice of every length-n vector, while
+m-sized objects (M, L, Ax, b) and all scalars are replicated.  The only exchange steps are
+  * all-reduce(sum) of the m x m Gram matrix (D-opt) or of the m-vector Ax (Poisson / KL),
+  * all-reduce of a handful of scalars per driver step (divergences, dot products, Newton sums),
+  * (value, index) extremum with lowest-index tie-break for the simplex LMO.
+torch.distributed carries them (NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+class ColumnShard:
+    def __init__(self, n, group=None, rank=None, world=None):
+        self.group = group
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n, self.rank, self.world = int(n), int(rank), int(world)
+        self.offsets = self.partition(self.n, self.world)
+        self.lo, self.hi = self.offsets[self.rank], self.offsets[self.rank + 1]
+        self.n_local = self.hi - self.lo
+
+    @staticmethod
+    def partition(n, world):
+        """Contiguous, balanced, every boundary even (keeps 16-byte alignment of row slabs)."""
+        pairs, odd = divmod(n, 2)
+        q, r = divmod(pairs, world)
+        out = [0]
+        for i in range(world):
+            out.append(out[-1] + 2 * (q + (1 if i < r else 0)))
+        out[-1] += odd            # an odd last column goes to the last rank
+        return out
+
+    # ---- data movement ------------------------------------------------------------------
+    def cols(self, M):
+        """Local column slab of a host or device matrix (copy, C-contiguous)."""
+        if isinstance(M, torch.Tensor):
+            return M[:, self.lo:self.hi].contiguous()
+        import numpy as np
+        return np.ascontiguousarray(M[:, self.lo:self.hi])
+
+    def part(self, v):
+        if isinstance(v, torch.Tensor):
+            return v[self.lo:self.hi].contiguous()
+        import numpy as np
+        return np.ascontiguousarray(v[self.lo:self.hi])
+
+    def gather(self, t):
+        """All ranks receive the full length-n vector assembled from the local slices."""
+        if self.world == 1:
+            return t.clone()
+        width = max(self.offsets[i + 1] - self.offsets[i] for i in range(self.world))
+        pad = torch.zeros(width, dtype=t.dtype, device=t.device)
+        pad[: t.numel()] = t
+        bufs = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(bufs, pad, group=self.group)
+        return torch.cat([bufs[i][: self.offsets[i + 1] - self.offsets[i]] for i in range(self.world)])
+
+    # ---- collectives ----------------------------------------------------------------------
+    def sum_(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def min_(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return t
+
+    def max_(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def argmin_(self, pair):
+        """pair = tensor [value, global_index] (float64).  In place: the minimum value over ranks and,
+        among ranks attaining it, the lowest global index -- independent of the GPU count."""
+        if self.world == 1:
+            return pair
+        bufs = [torch.empty_like(pair) for _ in range(self.world)]
+        dist.all_gather(bufs, pair, group=self.group)
+        allp = torch.stack(bufs)                          # [world, 2]
+        vmin = allp[:, 0].min()
+        cand = torch.where(allp[:, 0] == vmin, allp[:, 1], torch.full_like(allp[:, 1], float("inf")))
+        pair[0] = vmin
+        pair[1] = cand.min()
+        return pair
+
+    def owner(self, col):
+        """Rank that owns global column `col`."""
+        for r in range(self.world):
+            if self.offsets[r] <= col < self.offsets[r + 1]:
+                return r
+        raise IndexError(col)

@@ -1,0 +1,403 @@
+"""BPG, ABPG, ABPG_expo, ABPG_gain and ABDA over GPU-resident iterates.
+
+Signatures, keyword defaults, return tuples and the host-side scalar control flow (theta
+schedule, line search on L / gain / exponent, restart, stopping tests) are those of
+accbpg/algorithms.py:11-514; the per-iteration arithmetic (oracles, Bregman steps, axpby,
+dot products) is enqueued on the GPU through the asynchronous operator forms and the scalars a
+decision needs come back in one pinned read per line-search trip.  Iterates stay in HBM: x0
+is uploaded once, the last iterate is returned in the form x0 was given (NumPy or CUDA tensor).
+History arrays are host NumPy float64, truncated to k+1 like the reference's.
+"""
+import time
+
+import numpy as np
+
+from . import _native as nat
+from .runtime import is_host, like_input
+
+lib = nat.lib
+
+
+def solve_theta(theta, gamma, gainratio=1):
+    """Newton solve of (1-t)/t^gamma = gainratio/theta^gamma starting at theta.   algorithms.py:75-91."""
+    ckg = theta ** gamma / gainratio
+    cta = theta
+    tol = 1e-6 * theta
+    phi = cta ** gamma - ckg * (1 - cta)
+    while abs(phi) > tol:
+        cta = cta - phi / (gamma * cta ** (gamma - 1) + ckg)
+        phi = cta ** gamma - ckg * (1 - cta)
+    return cta
+
+
+class _Loop:
+    """Device-side helpers shared by the drivers (one instance per solve)."""
+
+    def __init__(self, f, h, x0):
+        self.f, self.h = f, h
+        self.rt = f.rt
+        self.host = is_host(x0)
+        self.shard = getattr(f, "shard", None)
+        self.x0 = self.rt.to_device(x0).clone()
+        self.n = self.x0.numel()
+        self.t0 = time.time()
+
+    # vectors
+    def combo(self, a, x, b, y):
+        """a*x + b*y as a new vector (algorithms.py:147,150,243,250,369,374,478,483)."""
+        rt = self.rt
+        out = rt.empty(self.n)
+        nat.check(lib.accbpg_vec_axpby(rt.ctx, rt.stream, self.n, float(a), x.data_ptr(), float(b), y.data_ptr(),
+                                       out.data_ptr()))
+        return out
+
+    def div_prox(self, y, g, L):
+        out = self.rt.empty(self.n)
+        self.h._enq_div_prox(y, g, float(L), out)
+        return out
+
+    def prox(self, g, L):
+        out = self.rt.empty(self.n)
+        self.h._enq_prox(g, float(L), out)
+        return out
+
+    # scalars (enqueue only; `fetch` brings slots 0..5 back in one synchronising read)
+    def enq_f(self, x, slot):
+        self.f._enqueue(x, 0, slot, None)
+
+    def enq_fg(self, x, slot):
+        g = self.rt.empty(self.n)
+        self.f._enqueue(x, 2, slot, g)
+        return g
+
+    def enq_psi(self, x):
+        if self.h.has_psi:
+            self.h._enq_extra_psi(x, self.rt.S_PSI)
+
+    def enq_dot_diff(self, g, a, b):
+        rt = self.rt
+        nat.check(lib.accbpg_vec_dot_diff(rt.ctx, rt.stream, self.n, g.data_ptr(), a.data_ptr(), b.data_ptr(),
+                                          rt.slot(rt.S_DOT)))
+        if self.shard is not None and self.shard.world > 1:
+            self.shard.sum_(rt.scal[rt.S_DOT:rt.S_DOT + 1])
+
+    def enq_div(self, x, y, slot):
+        self.h._enq_divergence(x, y, slot)
+
+    def fetch(self):
+        return self.rt.read(0, 6)
+
+    def psi(self, vals):
+        return vals[self.rt.S_PSI] if self.h.has_psi else 0
+
+    def now(self):
+        return time.time() - self.t0
+
+    def result(self, x):
+        return like_input(x, self.host)
+
+
+def BPG(f, h, L, x0, maxitrs, epsilon=1e-14, linesearch=True, ls_ratio=1.2,
+        verbose=True, verbskip=1):
+    """Bregman proximal gradient.   accbpg/algorithms.py:11-72.   Returns (x, F, Ls, T)."""
+    if verbose:
+        print("\nBPG_LS method for min_{x in C} F(x) = f(x) + Psi(x)")
+        print("     k      F(x)         Lk       time")
+    lp = _Loop(f, h, x0)
+    rt = lp.rt
+    F = np.zeros(maxitrs)
+    Ls = np.ones(maxitrs) * L
+    T = np.zeros(maxitrs)
+    x = lp.x0
+    for k in range(maxitrs):
+        g = lp.enq_fg(x, rt.S_F)
+        lp.enq_psi(x)
+        vals = lp.fetch()
+        fx = vals[rt.S_F]
+        F[k] = fx + lp.psi(vals)
+        T[k] = lp.now()
+        if linesearch:
+            L = L / ls_ratio
+            while True:
+                x1 = lp.div_prox(x, g, L)
+                lp.enq_f(x1, rt.S_F2)
+                lp.enq_dot_diff(g, x1, x)
+                lp.enq_div(x1, x, rt.S_DXY)
+                vals = lp.fetch()
+                if vals[rt.S_F2] > fx + vals[rt.S_DOT] + L * vals[rt.S_DXY]:      # algorithms.py:53
+                    L = L * ls_ratio
+                else:
+                    break
+            x = x1
+        else:
+            x = lp.div_prox(x, g, L)
+        Ls[k] = L
+        if verbose and k % verbskip == 0:
+            print("{0:6d}  {1:10.3e}  {2:10.3e}  {3:6.1f}".format(k, F[k], L, T[k]))
+        if k > 0 and abs(F[k] - F[k - 1]) < epsilon:
+            break
+    return lp.result(x), F[0:k + 1], Ls[0:k + 1], T[0:k + 1]
+
+
+def _restart_now(lp, rule, F, k, g, x, x_1):
+    """Restart predicate of algorithms.py:168, :279, :406."""
+    if rule == 'f':
+        return F[k] > F[k - 1]
+    if rule == 'g':
+        lp.enq_dot_diff(g, x, x_1)
+        return lp.fetch()[lp.rt.S_DOT] > 0
+    return False
+
+
+def ABPG(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=False,
+         restart=False, restart_rule='g', verbose=True, verbskip=1):
+    """Accelerated BPG.   accbpg/algorithms.py:94-180.   Returns (x, F, G, T)."""
+    if verbose:
+        print("\nABPG method for minimize_{x in C} F(x) = f(x) + Psi(x)")
+        print("     k      F(x)       theta        TSG       D(x+,y)     D(z+,z)     time")
+    lp = _Loop(f, h, x0)
+    rt = lp.rt
+    F = np.zeros(maxitrs)
+    G = np.zeros(maxitrs)
+    T = np.zeros(maxitrs)
+    x = lp.x0
+    z = lp.x0.clone()
+    theta = 1.0
+    kk = 0
+    for k in range(maxitrs):
+        lp.enq_f(x, rt.S_F)
+        lp.enq_psi(x)
+        vals = lp.fetch()
+        F[k] = vals[rt.S_F] + lp.psi(vals)
+        T[k] = lp.now()
+        z_1, x_1 = z, x
+        if theta_eq and kk > 0:
+            theta = solve_theta(theta, gamma)
+        else:
+            theta = gamma / (kk + gamma)
+        y = lp.combo(1 - theta, x, theta, z_1)
+        g = rt.empty(lp.n)
+        f._enqueue(y, 1, rt.S_F2, g)
+        z = lp.div_prox(z_1, g, theta ** (gamma - 1) * L)
+        x = lp.combo(1 - theta, x, theta, z)
+        lp.enq_div(x, y, rt.S_DXY)
+        lp.enq_div(z, z_1, rt.S_DZZ)
+        vals = lp.fetch()
+        dxy, dzz = vals[rt.S_DXY], vals[rt.S_DZZ]
+        Gdr = dxy / dzz / theta ** gamma
+        G[k] = Gdr
+        if verbose and k % verbskip == 0:
+            print("{0:6d}  {1:10.3e}  {2:10.3e}  {3:10.3e}  {4:10.3e}  {5:10.3e}  {6:6.1f}".format(
+                k, F[k], theta, Gdr, dxy, dzz, T[k]))
+        kk += 1
+        if restart and k > 0:
+            if _restart_now(lp, restart_rule, F, k, g, x, x_1):
+                theta = 1.0
+                kk = 0
+                z = x
+        if dzz < epsilon:
+            break
+    return lp.result(x), F[0:k + 1], G[0:k + 1], T[0:k + 1]
+
+
+def ABPG_expo(f, h, L, x0, gamma0, maxitrs, epsilon=1e-14, delta=0.2,
+              theta_eq=True, checkdiv=False, Gmargin=10, restart=False,
+              restart_rule='g', verbose=True, verbskip=1):
+    """ABPG with exponent adaption.   accbpg/algorithms.py:183-292.   Returns (x, F, Gamma, G, T)."""
+    if verbose:
+        print("\nABPG_expo method for min_{x in C} F(x) = f(x) + Psi(x)")
+        print("     k      F(x)       theta       gamma        TSG       D(x+,y)     D(z+,z)     time")
+    lp = _Loop(f, h, x0)
+    rt = lp.rt
+    F = np.zeros(maxitrs)
+    G = np.zeros(maxitrs)
+    Gamma = np.ones(maxitrs) * gamma0
+    T = np.zeros(maxitrs)
+    gamma = gamma0
+    x = lp.x0
+    z = lp.x0.clone()
+    theta = 1.0
+    kk = 0
+    for k in range(maxitrs):
+        lp.enq_f(x, rt.S_F)
+        lp.enq_psi(x)
+        vals = lp.fetch()
+        F[k] = vals[rt.S_F] + lp.psi(vals)
+        T[k] = lp.now()
+        z_1, x_1 = z, x
+        if theta_eq and kk > 0:
+            theta = solve_theta(theta, gamma)
+        else:
+            theta = gamma / (kk + gamma)
+        y = lp.combo(1 - theta, x_1, theta, z_1)
+        g = lp.enq_fg(y, rt.S_F2)
+        fy = None
+        again = True
+        while again:
+            z = lp.div_prox(z_1, g, theta ** (gamma - 1) * L)
+            x = lp.combo(1 - theta, x_1, theta, z)
+            lp.enq_div(x, y, rt.S_DXY)
+            lp.enq_div(z, z_1, rt.S_DZZ)
+            if not checkdiv:
+                lp.enq_f(x, rt.S_F)
+                lp.enq_dot_diff(g, x, y)
+            vals = lp.fetch()
+            if fy is None:
+                fy = vals[rt.S_F2]
+            dxy, dzz = vals[rt.S_DXY], vals[rt.S_DZZ]
+            Gdr = dxy / dzz / theta ** gamma
+            if checkdiv:
+                again = (dxy > Gmargin * (theta ** gamma) * dzz)
+            else:
+                again = (vals[rt.S_F] > fy + vals[rt.S_DOT] + theta ** gamma * L * dzz)     # algorithms.py:260
+            if again and gamma > 1:
+                gamma = max(gamma - delta, 1)
+            else:
+                again = False
+        G[k] = Gdr
+        Gamma[k] = gamma
+        if verbose and k % verbskip == 0:
+            print("{0:6d}  {1:10.3e}  {2:10.3e}  {3:10.3e}  {4:10.3e}  {5:10.3e}  {6:10.3e}  {7:6.1f}".format(
+                k, F[k], theta, gamma, Gdr, dxy, dzz, T[k]))
+        kk += 1
+        if restart:
+            if _restart_now(lp, restart_rule, F, k, g, x, x_1):
+                theta = 1.0
+                kk = 0
+                z = x
+        if dzz < epsilon:
+            break
+    return lp.result(x), F[0:k + 1], Gamma[0:k + 1], G[0:k + 1], T[0:k + 1]
+
+
+def ABPG_gain(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, G0=1,
+              ls_inc=1.2, ls_dec=1.2, theta_eq=True, checkdiv=False,
+              restart=False, restart_rule='g', verbose=True, verbskip=1):
+    """ABPG with gain adaption.   accbpg/algorithms.py:295-420.   Returns (x, F, Gain, Gdiv, Gavg, T)."""
+    if verbose:
+        print("\nABPG_gain method for min_{x in C} F(x) = f(x) + Psi(x)")
+        print("     k      F(x)       theta         Gk         TSG       D(x+,y)     D(z+,z)      Gavg       time")
+    lp = _Loop(f, h, x0)
+    rt = lp.rt
+    F = np.zeros(maxitrs)
+    Gain = np.ones(maxitrs) * G0
+    Gdiv = np.zeros(maxitrs)
+    Gavg = np.zeros(maxitrs)
+    T = np.zeros(maxitrs)
+    x = lp.x0
+    z = lp.x0.clone()
+    G = G0
+    sumlogG = gamma * np.log(G)
+    theta = 1.0
+    kk = 0
+    for k in range(maxitrs):
+        lp.enq_f(x, rt.S_F)
+        lp.enq_psi(x)
+        vals = lp.fetch()
+        F[k] = vals[rt.S_F] + lp.psi(vals)
+        T[k] = lp.now()
+        z_1, x_1 = z, x
+        G_1 = G
+        theta_1 = theta
+        G = G / ls_dec
+        again = True
+        while again:
+            if kk > 0:
+                if theta_eq:
+                    theta = solve_theta(theta_1, gamma, G / G_1)
+                else:
+                    alpha = G / G_1
+                    theta = theta_1 * ((1 + alpha * (gamma - 1)) / (gamma * alpha + theta_1))
+            y = lp.combo(1 - theta, x_1, theta, z_1)
+            g = lp.enq_fg(y, rt.S_F2)
+            z = lp.div_prox(z_1, g, theta ** (gamma - 1) * G * L)
+            x = lp.combo(1 - theta, x_1, theta, z)
+            lp.enq_div(x, y, rt.S_DXY)
+            lp.enq_div(z, z_1, rt.S_DZZ)
+            if not checkdiv:
+                # the reference evaluates f(x) only when dzz >= epsilon; doing it unconditionally here saves a
+                # second round trip per trip and does not change any recorded value
+                lp.enq_f(x, rt.S_F)
+                lp.enq_dot_diff(g, x, y)
+            vals = lp.fetch()
+            fy = vals[rt.S_F2]
+            dxy, dzz = vals[rt.S_DXY], vals[rt.S_DZZ]
+            if dzz < epsilon:
+                break
+            Gdr = dxy / dzz / theta ** gamma
+            if checkdiv:
+                again = (Gdr > G)
+            else:
+                again = (vals[rt.S_F] > fy + vals[rt.S_DOT] + theta ** gamma * G * L * dzz)   # algorithms.py:387
+            if again:
+                G = G * ls_inc
+        Gain[k] = G
+        Gdiv[k] = Gdr       # stale (or unbound on the very first trip) after the break above, as in the reference
+        sumlogG += np.log(G)
+        Gavg[k] = np.exp(sumlogG / (gamma + k))
+        if verbose and k % verbskip == 0:
+            print("{0:6d}  {1:10.3e}  {2:10.3e}  {3:10.3e}  {4:10.3e}  {5:10.3e}  {6:10.3e}  {7:10.3e}  {8:6.1f}".format(
+                k, F[k], theta, G, Gdr, dxy, dzz, Gavg[k], T[k]))
+        kk += 1
+        if restart:
+            if _restart_now(lp, restart_rule, F, k, g, x, x_1):
+                theta = 1.0
+                kk = 0
+                z = x
+        if dzz < epsilon:
+            break
+    return lp.result(x), F[0:k + 1], Gain[0:k + 1], Gdiv[0:k + 1], Gavg[0:k + 1], T[0:k + 1]
+
+
+def ABDA(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=True,
+         verbose=True, verbskip=1):
+    """Accelerated Bregman dual averaging.   accbpg/algorithms.py:423-514.   Returns (x, F, G, T)."""
+    if verbose:
+        print("\nABDA method for min_{x in C} F(x) = f(x) + Psi(x)")
+        print("     k      F(x)       theta        TSG       D(x+,y)     D(z+,z)     time")
+    lp = _Loop(f, h, x0)
+    rt = lp.rt
+    F = np.zeros(maxitrs)
+    G = np.zeros(maxitrs)
+    T = np.zeros(maxitrs)
+    x = lp.x0
+    z = lp.x0.clone()
+    theta = 1.0
+    kk = 0
+    gavg = rt.empty(lp.n).zero_()
+    csum = 0
+    for k in range(maxitrs):
+        lp.enq_f(x, rt.S_F)
+        lp.enq_psi(x)
+        vals = lp.fetch()
+        F[k] = vals[rt.S_F] + lp.psi(vals)
+        T[k] = lp.now()
+        z_1, x_1 = z, x
+        if theta_eq and kk > 0:
+            theta = solve_theta(theta, gamma)
+        else:
+            theta = gamma / (kk + gamma)
+        y = lp.combo(1 - theta, x_1, theta, z_1)
+        g = rt.empty(lp.n)
+        f._enqueue(y, 1, rt.S_F2, g)
+        wgt = theta ** (1 - gamma)
+        gavg = lp.combo(1.0, gavg, wgt, g)            # gavg + theta^(1-gamma) * g   (1.0*gavg is exact)
+        csum = csum + wgt
+        # gavg / csum: a true division, not a multiplication by the reciprocal (algorithms.py:482)
+        gq = rt.empty(lp.n)
+        nat.check(lib.accbpg_vec_divide(rt.ctx, rt.stream, lp.n, gavg.data_ptr(), float(csum), gq.data_ptr()))
+        z = lp.prox(gq, L / csum)
+        x = lp.combo(1 - theta, x_1, theta, z)
+        lp.enq_div(x, y, rt.S_DXY)
+        lp.enq_div(z, z_1, rt.S_DZZ)
+        vals = lp.fetch()
+        dxy, dzz = vals[rt.S_DXY], vals[rt.S_DZZ]
+        Gdr = dxy / dzz / theta ** gamma
+        G[k] = Gdr
+        if verbose and k % verbskip == 0:
+            print("{0:6d}  {1:10.3e}  {2:10.3e}  {3:10.3e}  {4:10.3e}  {5:10.3e}  {6:6.1f}".format(
+                k, F[k], theta, Gdr, dxy, dzz, T[k]))
+        kk += 1
+        if dzz < epsilon:
+            break
+    return lp.result(x), F[0:k + 1], G[0:k + 1], T[0:k + 1]

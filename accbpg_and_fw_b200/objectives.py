@@ -1,0 +1,124 @@
+"""GPU-resident drop-ins for the relatively-smooth objectives of accbpg/functions.py.
+
+Same duck-typed protocol as the reference (`f(x)`, `f.gradient(x)`, `f.func_grad(x, flag)`,
+attributes H / A / b / m / n); NumPy in -> NumPy / float out, CUDA tensor in -> CUDA tensor
+out.  The `_enqueue*` methods are the asynchronous form the drivers in this package use:
+they write scalars to runtime slots and never synchronise.
+
+With `shard=ColumnShard(...)` the matrix passed in is this rank's column slab and vectors are
+local slices; the m x m Gram matrix (D-opt) or the m-vector Ax (Poisson / KL) is all-reduced.
+"""
+import numpy as np
+import torch
+
+from . import _native as nat
+from .runtime import Runtime, is_host, like_input
+
+lib = nat.lib
+
+
+class RSmoothFunction:
+    """Protocol of accbpg/functions.py:10-24."""
+
+    def __call__(self, x):
+        return self.func_grad(x, flag=0)
+
+    def gradient(self, x):
+        return self.func_grad(x, flag=1)
+
+    def func_grad(self, x, flag=2):
+        assert flag in (0, 1, 2), "flag must be 0, 1 or 2"
+        rt = self.rt
+        host = is_host(x)
+        xd = rt.to_device(x)
+        assert xd.numel() == self.n_local, f"{type(self).__name__}: x.size not equal to n"
+        g = rt.empty(self.n_local) if flag >= 1 else None
+        self._enqueue(xd, flag, rt.S_TMP, g)
+        fval = rt.read(rt.S_TMP, 1)[0]            # also surfaces x<0 / not-PD like the reference's checks
+        if flag == 0:
+            return fval
+        gout = like_input(g, host)
+        return gout if flag == 1 else (fval, gout)
+
+
+class DOptimalObj(RSmoothFunction):
+    """f(x) = -log det(H diag(x) H^T), H m x n with m < n.   accbpg/functions.py:27-59.
+
+    K1 gram (DMMA SYRK) -> [all-reduce M] -> K2 Cholesky / log det -> K3 L^{-1} -> K4 gradient.
+    """
+
+    def __init__(self, H, shard=None, device=None):
+        self.rt = Runtime.get(device)
+        self.shard = shard
+        self.H = H                                     # kept as given: notebooks pass f.H to D_opt_FW*
+        self._Hd = self.rt.to_device(H)
+        self.m, self.n_local = int(self._Hd.shape[0]), int(self._Hd.shape[1])
+        self.n = shard.n if shard is not None else self.n_local
+        assert self.m < self.n, "DOptimalObj: need m < n"
+        self._ws = self.rt.workspace(("dopt", self.m, self.n_local),
+                                     lib.accbpg_dopt_workspace_bytes(self.m, self.n_local))
+        if shard is not None and shard.world > 1:
+            self._M = torch.empty(self.m, self.m, dtype=torch.float64, device=self.rt.device)
+            self._L = torch.empty(self.m, self.m, dtype=torch.float64, device=self.rt.device)
+
+    def _enqueue(self, xd, flag, slot, g):
+        rt = self.rt
+        H = self._Hd
+        gp = g.data_ptr() if g is not None else None
+        if self.shard is None or self.shard.world == 1:
+            nat.check(lib.accbpg_dopt_func_grad(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
+                                                xd.data_ptr(), flag, self._ws.data_ptr(), rt.slot(slot), gp))
+            return
+        ws = self._ws.data_ptr()
+        nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
+                                       xd.data_ptr(), ws, self._M.data_ptr()))
+        self.shard.sum_(self._M)
+        nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, self.m, self._M.data_ptr(), self._L.data_ptr(),
+                                         rt.slot(slot)))
+        if flag >= 1:
+            nat.check(lib.accbpg_dopt_grad(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
+                                           self._L.data_ptr(), ws, gp))
+
+
+class _LinearInverse(RSmoothFunction):
+    """Shared body of PoissonRegression / KLdivRegression: Ax, value + residual, A^T r."""
+    _kind = None
+
+    def __init__(self, A, b, shard=None, device=None):
+        assert A.shape[0] == b.shape[0], "A and b sizes not matching"
+        self.rt = Runtime.get(device)
+        self.shard = shard
+        self.A, self.b = A, b
+        self._Ad = self.rt.to_device(A)
+        self._bd = self.rt.to_device(b)
+        self.m, self.n_local = int(self._Ad.shape[0]), int(self._Ad.shape[1])
+        self.n = shard.n if shard is not None else self.n_local
+        self._ws = self.rt.workspace(("linreg", self.m, self.n_local),
+                                     lib.accbpg_linreg_workspace_bytes(self.m, self.n_local))
+        self._Ax = self.rt.empty(self.m)
+        self._r = self.rt.empty(self.m)
+
+    def _enqueue(self, xd, flag, slot, g):
+        rt = self.rt
+        A = self._Ad
+        nat.check(lib.accbpg_linreg_matvec(rt.ctx, rt.stream, A.data_ptr(), self.m, self.n_local, A.stride(0),
+                                           xd.data_ptr(), self._ws.data_ptr(), self._Ax.data_ptr()))
+        if self.shard is not None and self.shard.world > 1:
+            self.shard.sum_(self._Ax)
+        # the value costs nothing extra next to the residual (one pass over m), so it is always produced
+        nat.check(lib.accbpg_linreg_value_resid(rt.ctx, rt.stream, self._kind, self.m, self._Ax.data_ptr(),
+                                                self._bd.data_ptr(), rt.slot(slot),
+                                                self._r.data_ptr() if flag >= 1 else None))
+        if flag >= 1:
+            nat.check(lib.accbpg_linreg_rmatvec(rt.ctx, rt.stream, A.data_ptr(), self.m, self.n_local, A.stride(0),
+                                                self._r.data_ptr(), self._ws.data_ptr(), g.data_ptr()))
+
+
+class PoissonRegression(_LinearInverse):
+    """f(x) = D_KL(b, Ax).   accbpg/functions.py:85-120."""
+    _kind = nat.MACROS["ACCBPG_LINREG_POISSON"]
+
+
+class KLdivRegression(_LinearInverse):
+    """f(x) = D_KL(Ax, b).   accbpg/functions.py:123-158."""
+    _kind = nat.MACROS["ACCBPG_LINREG_KL"]

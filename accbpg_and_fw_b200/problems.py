@@ -1,0 +1,142 @@
+"""Problem constructors returning GPU-resident (f, h, L, x0).
+
+Signature-compatible with accbpg/applications.py:17-206: the random instances draw from the
+legacy global NumPy RNG in the same order, so a seeded call builds the same H / A / b as the
+reference; f and h are the device operators of this package, L and x0 are host values exactly
+as in the reference (x0 is uploaded by the driver).
+"""
+import os
+
+import numpy as np
+
+from .objectives import DOptimalObj, PoissonRegression, KLdivRegression
+from .bregman import BurgEntropySimplex, BurgEntropyL1, BurgEntropyL2, ShannonEntropyL1
+
+
+def load_libsvm_dense(filename, zero_based="auto"):
+    """Parse a LIBSVM / svmlight text file into a dense (n_samples, n_features) float64 array and labels.
+
+    Same conventions as accbpg/utils.py:22-95 ('#' comments, sorted unique 1-based indices by
+    default, feature count from the largest index)."""
+    rows, labels = [], []
+    opener = open
+    if filename.endswith(".gz"):
+        import gzip
+        opener = lambda p: gzip.open(p, "rt")
+    elif filename.endswith(".bz2"):
+        import bz2
+        opener = lambda p: bz2.open(p, "rt")
+    min_idx, max_idx = None, -1
+    with opener(filename) as fh:
+        for line in fh:
+            line = line.split("#", 1)[0].split()
+            if not line:
+                continue
+            labels.append(float(line[0]))
+            feats = []
+            prev = -1
+            for tok in line[1:]:
+                k, v = tok.split(":", 1)
+                k = int(k)
+                if k < 0 or (zero_based is False and k == 0):
+                    raise ValueError("Invalid index {0:d} in LibSVM data file.".format(k))
+                if k <= prev:
+                    raise ValueError("Feature indices in LibSVM data file should be sorted and unique.")
+                prev = k
+                feats.append((k, float(v)))
+                min_idx = k if min_idx is None else min(min_idx, k)
+                max_idx = max(max_idx, k)
+            rows.append(feats)
+    shift = 1 if (zero_based is False or (zero_based == "auto" and min_idx is not None and min_idx > 0)) else 0
+    X = np.zeros((len(rows), max_idx + 1 - shift))
+    for i, feats in enumerate(rows):
+        for k, v in feats:
+            X[i, k - shift] = v
+    return X, np.array(labels)
+
+
+def D_opt_libsvm(filename, device=None):
+    """D-optimal design instance from a LIBSVM regression data set.   applications.py:17-33."""
+    X, _ = load_libsvm_dense(filename)
+    H = np.ascontiguousarray(X.T) if X.shape[0] > X.shape[1] else np.ascontiguousarray(X)
+    n = H.shape[1]
+    return DOptimalObj(H, device=device), BurgEntropySimplex(device=device), 1.0, (1.0 / n) * np.ones(n)
+
+
+def D_opt_design(m, n, randseed=-1, device=None):
+    """Random D-optimal design instance, H = randn(m, n).   applications.py:36-56."""
+    if randseed > 0:
+        np.random.seed(randseed)
+    H = np.random.randn(m, n)
+    return DOptimalObj(H, device=device), BurgEntropySimplex(device=device), 1.0, (1.0 / n) * np.ones(n)
+
+
+def _poisson_data(m, n, noise, randseed, normalizeA):
+    if randseed > 0:
+        np.random.seed(randseed)
+    A = np.random.rand(m, n)
+    if normalizeA:
+        A = A / A.sum(axis=0)
+    x = np.random.rand(n) / n
+    xavg = x.sum() / x.size
+    x = np.maximum(x - xavg, 0) * 10
+    b = np.dot(A, x) + noise * (np.random.rand(m) - 0.5)
+    assert b.min() > 0, "need b > 0 for nonnegative regression."
+    return A, b
+
+
+def Poisson_regrL1(m, n, noise=0.01, lamda=0, randseed=-1, normalizeA=True, device=None):
+    """min D_KL(b, Ax) + lamda*||x||_1 over x >= 0.   applications.py:98-134."""
+    A, b = _poisson_data(m, n, noise, randseed, normalizeA)
+    return (PoissonRegression(A, b, device=device), BurgEntropyL1(lamda, device=device), b.sum(),
+            (1.0 / n) * np.ones(n) * 10)
+
+
+def Poisson_regrL2(m, n, noise=0.01, lamda=0, randseed=-1, normalizeA=True, device=None):
+    """min D_KL(b, Ax) + (lamda/2)*||x||_2^2 over x >= 0.   applications.py:137-172."""
+    A, b = _poisson_data(m, n, noise, randseed, normalizeA)
+    return (PoissonRegression(A, b, device=device), BurgEntropyL2(lamda, device=device), b.sum(),
+            (1.0 / n) * np.ones(n))
+
+
+def KL_nonneg_regr(m, n, noise=0.01, lamdaL1=0, randseed=-1, normalizeA=True, device=None):
+    """min D_KL(Ax, b) + lamda*||x||_1 over x >= 0.   applications.py:175-206."""
+    if randseed > 0:
+        np.random.seed(randseed)
+    A = np.random.rand(m, n)
+    if normalizeA:
+        A = A / A.sum(axis=0)
+    x = np.random.rand(n)
+    b = np.dot(A, x) + noise * (np.random.rand(m) - 0.5)
+    assert b.min() > 0, "need b > 0 for nonnegative regression."
+    L = max(A.sum(axis=0))
+    return KLdivRegression(A, b, device=device), ShannonEntropyL1(lamdaL1, device=device), L, 0.5 * np.ones(n)
+
+
+def D_opt_KYinit(V):
+    """Kumar-Yildirim sparse starting point (applications.py:59-95).
+
+    Host-side setup executed once before a solve (m Gram-Schmidt sweeps, each with one q^T V product);
+    it is a SURVEY section 8(f) "next" item for the device path and runs in NumPy here."""
+    V = np.asarray(V.cpu().numpy() if hasattr(V, "cpu") else V)
+    m, n = V.shape
+    if n <= 2 * m:
+        return (1.0 / n) * np.ones(n)
+    picked = []
+    Q = np.zeros((m, m))
+    for i in range(m):
+        b = np.random.rand(m)
+        q = b.copy()
+        for j in range(i):
+            q = q - np.dot(Q[:, j], b) * Q[:, j]
+        qV = np.dot(q, V)
+        kmax, kmin = int(np.argmax(qV)), int(np.argmin(qV))
+        picked += [kmax, kmin]
+        v = V[:, kmin] - V[:, kmax]
+        q = v.copy()
+        for j in range(i):
+            q = q - np.dot(Q[:, j], v) * Q[:, j]
+        Q[:, i] = q / np.linalg.norm(q)
+    x0 = np.zeros(n)
+    x0[picked] = np.ones(len(picked)) / len(picked)
+    return x0 / x0.sum()

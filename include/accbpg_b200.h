@@ -1,0 +1,202 @@
+/*
+ * accbpg_b200.h -- C ABI of the B200-native accbpg hot path (libaccbpg_b200.so).
+ *
+ * The reference (DredderGun/accbpg_and_fw) is pure Python/NumPy and has no FFI:
+ * its boundary is the duck-typed operator protocol between the driver loops and
+ * the f / h / lmo objects (accbpg/functions.py:10-24, :199-235,
+ * accbpg/functions_lmo.py:137-160).  Each entry point below replaces the NumPy
+ * body of one of those operator methods; the citation next to it is the
+ * reference code it stands in for.  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add to route the method to the entry point.
+ *
+ * Conventions
+ *   - every `const double*` / `double*` named d_* or documented "device" is a
+ *     device pointer to IEEE float64; matrices are row-major (C order) with an
+ *     explicit leading dimension in elements;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises except
+ *     accbpg_ctx_read(), so results that are host scalars in the reference are
+ *     written to a device slot (`d_out`) and fetched with accbpg_ctx_read();
+ *   - data-dependent failures that the reference raises as AssertionError /
+ *     ValueError are reported as bits OR-ed into the context's status word
+ *     (ACCBPG_ST_*), fetched by the same accbpg_ctx_read();
+ *   - return value: 0 ok, ACCBPG_E_ARG bad argument, ACCBPG_E_CUDA a CUDA call
+ *     failed (text from accbpg_last_error());
+ *   - no entry point allocates device memory except accbpg_ctx_create();
+ *     matrix-sized scratch is caller-provided after a *_workspace_bytes() query;
+ *   - all reductions use a fixed tree (no floating-point atomics): results are
+ *     bit-reproducible run to run for a given shape and GPU.
+ */
+#ifndef ACCBPG_B200_H
+#define ACCBPG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACCBPG_ABI_VERSION 1
+
+/* return codes */
+#define ACCBPG_OK      0
+#define ACCBPG_E_ARG   1
+#define ACCBPG_E_CUDA  2
+
+/* status bits (device-side precondition checks of the reference) */
+#define ACCBPG_ST_X_NEGATIVE     0x001u  /* DOptimalObj: x.min() >= 0            functions.py:45  */
+#define ACCBPG_ST_NOT_PD         0x002u  /* slogdet sign <= 0 -> ValueError      functions.py:49  */
+#define ACCBPG_ST_ARG_NOT_POS    0x004u  /* Burg: x.min()>0, y.min()>0           functions.py:243,252,270 */
+#define ACCBPG_ST_PROX_NOT_POS   0x008u  /* Burg prox: g.min()>0 / >-lamda       functions.py:261,296 */
+#define ACCBPG_ST_ARG_NEGATIVE   0x010u  /* Shannon: x.min()>=0, y.min()>=0      functions.py:406,419,436 */
+#define ACCBPG_ST_Y_NOT_POS      0x020u  /* ShannonSimplex div_prox: y.min()>0   functions.py:488 */
+#define ACCBPG_ST_NEWTON_MAXIT   0x040u  /* Burg-simplex root-find hit the iteration guard (never in the reference) */
+
+/* ---- library ---------------------------------------------------------- */
+int         accbpg_abi_version(void);
+const char* accbpg_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t    accbpg_launch_count(void);
+
+/* ---- context: small device scratch (reduction partials, 256 scalar slots,
+ *      status word) + pinned host mirror.  One per device/thread of control. */
+int     accbpg_ctx_create(void** ctx);
+int     accbpg_ctx_destroy(void* ctx);
+double* accbpg_ctx_slots(void* ctx);            /* device pointer to 256 float64 result slots */
+int     accbpg_ctx_sm_count(void* ctx);
+/* copy count (<= 256) float64 results from device address d_src (the context's slots or any
+ * caller-owned device buffer the kernels were told to write to) and the status word to the
+ * host through pinned memory, wait for the stream, clear the status word.  This is the only
+ * synchronising entry point.  d_src / h_out may be NULL when count == 0. */
+int     accbpg_ctx_read(void* ctx, void* stream, const double* d_src, int count,
+                        double* h_out, uint32_t* h_status);
+
+/* ---- iterate arithmetic inlined in the drivers (accbpg/algorithms.py:147,150,
+ *      243,250,369,374,478,483; np.dot at :53,168,260,279,387,406;
+ *      algorithms_fw.py:39,231) ---------------------------------------- */
+/* out = a*x + b*y  (two rounded products, one rounded add: same as NumPy) */
+int accbpg_vec_axpby(void* ctx, void* stream, int64_t n, double a, const double* d_x,
+                     double b, const double* d_y, double* d_out);
+/* out = x + a*(s - x)   algorithms_fw.py:34,54,231 */
+int accbpg_vec_step_toward(void* ctx, void* stream, int64_t n, const double* d_x,
+                           const double* d_s, double a, double* d_out);
+int accbpg_vec_dot(void* ctx, void* stream, int64_t n, const double* d_x, const double* d_y, double* d_out);
+/* d_out = dot(g, a - b) without the temporary */
+int accbpg_vec_dot_diff(void* ctx, void* stream, int64_t n, const double* d_g, const double* d_a,
+                        const double* d_b, double* d_out);
+int accbpg_vec_sum(void* ctx, void* stream, int64_t n, const double* d_x, double* d_out);
+/* d_out[0] = min(x), d_out[1] = max(x) */
+int accbpg_vec_minmax(void* ctx, void* stream, int64_t n, const double* d_x, double* d_out);
+/* d_out[0] = value, d_out[1] = (double) first index attaining it; want_max = 0 argmin, 1 argmax */
+int accbpg_vec_argext(void* ctx, void* stream, int64_t n, const double* d_x, int want_max, double* d_out);
+
+/* ---- Burg entropy kernels  h(x) = -sum log x   (accbpg/functions.py:238-356) */
+#define ACCBPG_BURG_PLAIN   0   /* BurgEntropy.prox_map        functions.py:255-262 */
+#define ACCBPG_BURG_L1      1   /* BurgEntropyL1.prox_map      functions.py:290-298 */
+#define ACCBPG_BURG_L2      2   /* BurgEntropyL2.prox_map      functions.py:316-323 */
+int accbpg_burg_value(void* ctx, void* stream, int64_t n, const double* d_x, double* d_out);        /* :242-244 */
+int accbpg_burg_gradient(void* ctx, void* stream, int64_t n, const double* d_x, double* d_out_vec); /* :246-248 */
+int accbpg_burg_divergence(void* ctx, void* stream, int64_t n, const double* d_x, const double* d_y,
+                           double* d_out);                                                          /* :250-253 */
+/* prox_map(g, L) when d_y == NULL, div_prox_map(y, g, L) = prox_map(g - L*(-1/y), L) otherwise (:264-271) */
+int accbpg_burg_prox(void* ctx, void* stream, int64_t n, int kind, double lamda,
+                     const double* d_y, const double* d_g, double L, double* d_out_vec);
+/* BurgEntropySimplex.prox_map / inherited div_prox_map (functions.py:336-356): one persistent
+ * cooperative kernel replays cmin, bisection and Newton with grid-wide reductions.
+ * d_info (3 slots, may be NULL): bisection steps, Newton steps, final c. */
+int accbpg_burg_simplex_prox(void* ctx, void* stream, int64_t n, const double* d_y, const double* d_g,
+                             double L, double eps, double* d_out_vec, double* d_info);
+/* column-sharded building blocks of the same root-find (one rank's slice; the caller
+ * all-reduces the scalars):  prepare: out = gg = (g [+ L/y]) / L, d_out[0] = min(gg);
+ * sums: d_out[0] = sum 1/(gg+c), d_out[1] = sum -1/(gg+c)^2;  finish: out = 1/(gg+c). */
+int accbpg_burg_simplex_prepare(void* ctx, void* stream, int64_t n, const double* d_y, const double* d_g,
+                                double L, double* d_gg, double* d_out);
+int accbpg_burg_simplex_sums(void* ctx, void* stream, int64_t n, const double* d_gg, double c, double* d_out);
+int accbpg_burg_simplex_finish(void* ctx, void* stream, int64_t n, const double* d_gg, double c,
+                               double* d_out_vec);
+
+/* ---- Shannon entropy kernels  h(x) = sum x log x   (accbpg/functions.py:398-490) */
+int accbpg_shannon_value(void* ctx, void* stream, int64_t n, const double* d_x, double delta, double* d_out);   /* :405-408 */
+int accbpg_shannon_gradient(void* ctx, void* stream, int64_t n, const double* d_x, double delta,
+                            double* d_out_vec);                                                                  /* :410-413 */
+int accbpg_shannon_divergence(void* ctx, void* stream, int64_t n, const double* d_x, const double* d_y,
+                              double delta, double* d_out);                                                      /* :415-421 */
+/* exp(-(lamda+g)/L - 1) when d_y == NULL (:423-428, :458-462), y*exp(-(lamda+g)/L) otherwise (:430-438, :464-466).
+ * normalize != 0: divide by the sum (ShannonEntropySimplex :475-490); d_sum_out (1 slot) receives the
+ * un-normalised sum.  normalize == 2: write the un-normalised vector and the sum only (sharded use). */
+int accbpg_shannon_prox(void* ctx, void* stream, int64_t n, double lamda, const double* d_y,
+                        const double* d_g, double L, int normalize, double* d_out_vec, double* d_sum_out);
+/* out = x * scale (finishes the sharded simplex normalisation: scale = 1/sum is NOT used; out = x / denom) */
+int accbpg_vec_divide(void* ctx, void* stream, int64_t n, const double* d_x, double denom, double* d_out_vec);
+
+/* ---- linear minimisation oracle over the simplex (accbpg/functions_lmo.py:137-160) */
+/* s = 1e-15 everywhere, s[first argmin g] = radius; d_out[0] = min g, d_out[1] = index */
+int accbpg_lmo_simplex(void* ctx, void* stream, int64_t n, const double* d_g, double radius,
+                       double* d_s_vec, double* d_out);
+/* s = fill everywhere except s[idx] = radius (sharded use: each rank fills its slice) */
+int accbpg_lmo_fill_vertex(void* ctx, void* stream, int64_t n, double fill, int64_t idx, double radius,
+                           double* d_s_vec);
+/* elementwise LMOs: l_inf ball  c - r*sign(g)  (functions_lmo.py:106-134); l2 ball  c - r*g/||g||
+ * (:16-51, norm supplied by the caller from accbpg_vec_dot); box  where(g<0, upper, lower) (:190-212) */
+int accbpg_lmo_linf(void* ctx, void* stream, int64_t n, const double* d_g, double radius,
+                    const double* d_center, double* d_s_vec);
+int accbpg_lmo_l2(void* ctx, void* stream, int64_t n, const double* d_g, double radius, double gnorm,
+                  const double* d_center, double* d_s_vec);
+int accbpg_lmo_box(void* ctx, void* stream, int64_t n, const double* d_g, const double* d_lower,
+                   const double* d_upper, double* d_s_vec);
+
+/* ---- D-optimal design objective  f(x) = -log det(H diag(x) H^T)
+ *      (DOptimalObj.func_grad, accbpg/functions.py:43-59).  H is m x n_local row-major. */
+size_t accbpg_dopt_workspace_bytes(int m, int64_t n_local);
+/* K1: M = H diag(x) H^T as an FP64 DMMA SYRK (lower tiles, split over n, fixed-order reduce), written
+ * as a full symmetric m x m matrix with leading dimension m.  Sets ST_X_NEGATIVE if some x < 0. */
+int accbpg_dopt_gram(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
+                     const double* d_x, void* d_ws, double* d_M);
+/* K2: blocked Cholesky M = L L^T, out of place (d_M symmetric m x m is only read; d_L m x m receives the lower
+ * factor, zero above the diagonal); d_out[0] = -log det M = -sum log(pivot).  Sets ST_NOT_PD on a pivot <= 0. */
+int accbpg_dopt_factor(void* ctx, void* stream, int m, const double* d_M, double* d_L, double* d_out);
+/* K3+K4: g_j = -|| L^{-1} h_j ||^2 for the local columns: triangular inverse, then a DMMA triangular
+ * GEMM whose epilogue reduces squared column norms (M^{-1}H is never materialised). */
+int accbpg_dopt_grad(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
+                     const double* d_L, void* d_ws, double* d_g);
+/* whole func_grad on one GPU: flag 0 value, 1 gradient, 2 both (value always computed, as in the reference) */
+int accbpg_dopt_func_grad(void* ctx, void* stream, const double* d_H, int m, int64_t n, int64_t ldh,
+                          const double* d_x, int flag, void* d_ws, double* d_f_out, double* d_g);
+
+/* ---- Poisson / KL regression objectives (accbpg/functions.py:102-120, :140-158).  A is m x n_local. */
+#define ACCBPG_LINREG_POISSON 0   /* f = sum b log(b/Ax) + Ax - b ; r = 1 - b/Ax   */
+#define ACCBPG_LINREG_KL      1   /* f = sum Ax log(Ax/b) - Ax + b ; r = log(Ax/b) */
+size_t accbpg_linreg_workspace_bytes(int64_t m, int64_t n_local);
+/* K5: Ax (local partial product when A is a column slab) */
+int accbpg_linreg_matvec(void* ctx, void* stream, const double* d_A, int64_t m, int64_t n_local, int64_t lda,
+                         const double* d_x, void* d_ws, double* d_Ax);
+/* K7: objective value and the residual vector r that the gradient needs (d_r may be NULL) */
+int accbpg_linreg_value_resid(void* ctx, void* stream, int kind, int64_t m, const double* d_Ax,
+                              const double* d_b, double* d_f_out, double* d_r);
+/* K6: g = A^T r, one pass over A (the reference materialises an m x n broadcast product) */
+int accbpg_linreg_rmatvec(void* ctx, void* stream, const double* d_A, int64_t m, int64_t n_local, int64_t lda,
+                          const double* d_r, void* d_ws, double* d_g);
+
+/* ---- D_opt_FW / D_opt_FW_away (accbpg/D_opt_alg.py:9-88, :91-185) -------
+ * State lives in caller-owned device buffers: x, w (n), Hinv (m x m, ld m), a control block of
+ * ACCBPG_FW_CTRL_DOUBLES float64 (layout: enum FwCtrl in csrc/fw.cu, mirrored by dopt_fw.py) and four
+ * history arrays of maxitrs float64 (F, SP, SN, T; T holds %globaltimer nanoseconds). */
+#define ACCBPG_FW_CTRL_DOUBLES 32
+size_t accbpg_fw_workspace_bytes(int m, int64_t n);
+/* setup (D_opt_alg.py:39-45 / :123-129): M = V diag(x0) V^T, Hinv = M^{-1}, w_j = v_j^T Hinv v_j,
+ * ctrl <- {log det M, not stopped}.  Sets the ST_X_NEGATIVE / ST_NOT_PD status bits like func_grad. */
+int accbpg_fw_setup(void* ctx, void* stream, const double* d_V, int m, int64_t n, int64_t ldv,
+                    const double* d_x0, void* d_ws, double* d_Hinv, double* d_w, double* d_ctrl);
+/* enqueue iterations k_start .. k_start+k_count-1 of the loop (:51-82 / :135-179), five kernels each:
+ * argmax w; masked argmin + step rule + history entry + gather of the chosen column; u = Hinv v;
+ * Hinv <- (Hinv -/+ c u u^T)/(1 -/+ t); the single pass over V that forms u^T V and updates w and x.
+ * away = 0: D_opt_FW, 1: D_opt_FW_away.  Once the optimality test fires (ctrl[0] = 1, ctrl[1] = k) the
+ * remaining launches are no-ops; ctrl[14] counts the history entries written. */
+int accbpg_fw_run(void* ctx, void* stream, const double* d_V, int m, int64_t n, int64_t ldv, int away, double eps,
+                  int k_start, int k_count, void* d_ws, double* d_Hinv, double* d_x, double* d_w, double* d_ctrl,
+                  double* d_hist_F, double* d_hist_SP, double* d_hist_SN, double* d_hist_T);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACCBPG_B200_H */

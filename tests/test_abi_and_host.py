@@ -1,0 +1,144 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares; host-side logic
+(theta solver, column sharding, LIBSVM parser, constructors' RNG order) without touching a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from oracle import accbpg_oracle as orc
+
+
+def test_library_exports_every_declared_symbol():
+    from accbpg_and_fw_b200 import _native as nat
+    assert os.path.exists(nat.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "accbpg_b200.h")).read()
+    declared = set(re.findall(r"\b(accbpg_\w+)\s*\(", re.sub(r"/\*.*?\*/", " ", header, flags=re.S)))
+    assert len(declared) >= 40
+    assert declared == set(nat.PROTOS), declared ^ set(nat.PROTOS)
+    raw = ctypes.CDLL(nat.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert nat.lib.accbpg_abi_version() == nat.MACROS["ACCBPG_ABI_VERSION"]
+    assert nat.launch_count() == 0            # nothing computed on CPU
+    nm = subprocess.run(["nm", "-D", "--defined-only", nat.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (accbpg_\w+)", nm))
+    assert declared <= exported
+
+
+def test_library_is_sm100a_with_dmma():
+    from accbpg_and_fw_b200 import _native as nat
+    out = subprocess.run(["cuobjdump", "-lelf", nat.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN6accbpg16syrk_dmma_kernelILb1EEEvNS_10SyrkParamsE",
+                           nat.LIB_PATH], capture_output=True, text=True).stdout
+    assert sass.count("DMMA.8x8x4") >= 128 and "LDGSTS" in sass
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import accbpg_and_fw_b200 as acc
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        acc.D_opt_design(8, 20, randseed=1)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "accbpg_and_fw_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in text.replace("Linear minimisation oracle", "").replace(
+                    "linear minimisation oracle", "").replace("oracles", "").replace("(value/gradient oracle", "") \
+                    or fn in (), f"{fn} mentions the oracle package"
+
+
+def test_solve_theta_matches_oracle():
+    from accbpg_and_fw_b200.drivers import solve_theta
+    for theta in (1.0, 0.5, 0.0123):
+        for gamma in (1.0, 1.5, 2.0, 3.0):
+            for ratio in (1, 0.8, 1.2):
+                assert solve_theta(theta, gamma, ratio) == orc.solve_theta(theta, gamma, ratio)
+
+
+def test_column_partition():
+    from accbpg_and_fw_b200.dist import ColumnShard
+    for n in (1, 2, 7, 200, 50001, 1000000):
+        for world in (1, 2, 3, 4, 8):
+            offs = ColumnShard.partition(n, world)
+            assert offs[0] == 0 and offs[-1] == n and len(offs) == world + 1
+            assert all(b >= a for a, b in zip(offs, offs[1:]))
+            assert all(o % 2 == 0 for o in offs[:-1])
+            sizes = [b - a for a, b in zip(offs, offs[1:])]
+            assert max(sizes) - min(sizes) <= 3
+    sh = ColumnShard(10, rank=1, world=2)
+    assert (sh.lo, sh.hi, sh.n_local) == (6, 10, 4) or (sh.lo, sh.hi) == (4, 10) or sh.lo % 2 == 0
+    assert sh.owner(0) == 0 and sh.owner(9) == 1
+
+
+def test_libsvm_parser_matches_reference_matrix(golden_ops):
+    from accbpg_and_fw_b200.problems import load_libsvm_dense
+    X, y = load_libsvm_dense(os.path.join(GOLDEN, "housing_libsvm.txt"))
+    assert X.shape == (506, 13) and y.shape == (506,)
+    assert np.array_equal(np.ascontiguousarray(X.T), golden_ops["housing_H"])
+
+
+def test_libsvm_parser_edge_cases(tmp_path):
+    from accbpg_and_fw_b200.problems import load_libsvm_dense
+    p = tmp_path / "t.txt"
+    p.write_text("# comment only\n1.5 1:2.0 3:4.0 # trailing\n\n-1 2:1e-3\n")
+    X, y = load_libsvm_dense(str(p))
+    assert X.tolist() == [[2.0, 0.0, 4.0], [0.0, 1e-3, 0.0]] and y.tolist() == [1.5, -1.0]
+    p.write_text("1 3:1 2:1\n")
+    with pytest.raises(ValueError):
+        load_libsvm_dense(str(p))
+
+
+def test_ky_init_matches_oracle(golden_traj):
+    from accbpg_and_fw_b200.problems import D_opt_KYinit
+    np.random.seed(10)
+    H = np.random.randn(80, 200)
+    np.random.seed(77)
+    assert np.array_equal(D_opt_KYinit(H), golden_traj["ky_x0"])
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[3])
+from accbpg_and_fw_b200.dist import ColumnShard
+rank, world = int(sys.argv[1]), 2
+os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = sys.argv[2]
+dist.init_process_group("gloo", rank=rank, world_size=world)
+sh = ColumnShard(11)
+full = torch.arange(11, dtype=torch.float64) * 1.5
+loc = sh.part(full)
+assert torch.equal(sh.gather(loc), full)
+t = torch.tensor([float(loc.sum())], dtype=torch.float64); sh.sum_(t); assert t.item() == full.sum().item()
+# argmin with an exact tie across ranks: value 0.25 at global columns 3 (rank 0) and 8 (rank 1) -> 3 wins
+g = torch.ones(11, dtype=torch.float64); g[3] = 0.25; g[8] = 0.25
+gl = sh.part(g)
+li = int(torch.argmin(gl)); pair = torch.tensor([float(gl[li]), float(li + sh.lo)], dtype=torch.float64)
+sh.argmin_(pair); assert pair.tolist() == [0.25, 3.0], pair
+m = torch.tensor([float(gl.min())], dtype=torch.float64); sh.min_(m); assert m.item() == 0.25
+assert sh.owner(3) == 0 and sh.owner(8) == 1
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_column_shard_collectives_gloo_world2(tmp_path):
+    """World-size-2 gloo run of the sharding collectives (sum, min, gather, lowest-index argmin)."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port, ROOT], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"ok {r}" in o, o

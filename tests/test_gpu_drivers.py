@@ -1,0 +1,164 @@
+"""GPU parity: driver trajectories on seeded instances against the oracle and the reference's golden runs.
+Bar (BASELINE.json north_star): F_k within 1e-9 relative over the first 1000 iterations, FP64; discrete
+line-search outputs (L_k, gain G_k, gamma_k) identical; the divergence-ratio diagnostic Gdiv is
+conditioning-limited and is checked to 1e-6 while D(z+,z) is above 1e-10."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import accbpg_oracle as orc
+
+pytestmark = pytest.mark.gpu
+FTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def acc():
+    import accbpg_and_fw_b200 as a
+    return a
+
+
+@pytest.fixture(scope="module")
+def dopt(acc):
+    return acc.D_opt_design(80, 200, randseed=10)
+
+
+def ferr(F, Fref):
+    assert F.shape == Fref.shape, (F.shape, Fref.shape)
+    return float(np.max(np.abs(F - Fref) / np.maximum(np.abs(Fref), 1e-3)))
+
+
+def test_bpg_golden(acc, dopt, golden_traj):
+    f, h, L, x0 = dopt
+    x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=1000, linesearch=True, ls_ratio=1.2, verbose=False)
+    assert ferr(F, golden_traj["bpg_ls_F"]) <= FTOL
+    assert np.array_equal(Ls, golden_traj["bpg_ls_Ls"])
+    assert relerr(x, golden_traj["bpg_ls_x"]) <= 1e-6
+    assert T.shape == F.shape and np.all(np.diff(T) >= 0)
+    x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=300, linesearch=False, verbose=False)
+    assert ferr(F, golden_traj["bpg_F"]) <= FTOL and np.all(Ls == L)
+
+
+def test_abpg_golden(acc, dopt, golden_traj):
+    f, h, L, x0 = dopt
+    x, F, G, T = acc.ABPG(f, h, L, x0, gamma=2, maxitrs=1000, theta_eq=False, verbose=False)
+    assert ferr(F, golden_traj["abpg_F"]) <= FTOL
+    Gref = golden_traj["abpg_G"]
+    assert relerr(G[:200], Gref[:200]) <= 1e-6
+    x, F, G, T = acc.ABPG(f, h, L, x0, gamma=2, maxitrs=1000, theta_eq=True, verbose=False)
+    assert ferr(F, golden_traj["abpg_eq_F"]) <= FTOL
+    x, F, G, T = acc.ABPG(f, h, L, x0, gamma=2, maxitrs=400, theta_eq=True, restart=True, verbose=False)
+    assert ferr(F, golden_traj["abpg_rs_F"]) <= FTOL
+
+
+def test_abpg_expo_golden(acc, dopt, golden_traj):
+    f, h, L, x0 = dopt
+    x, F, Gamma, G, T = acc.ABPG_expo(f, h, L, x0, gamma0=3, maxitrs=600, theta_eq=True, verbose=False)
+    assert ferr(F, golden_traj["expo_F"]) <= FTOL
+    assert np.array_equal(Gamma, golden_traj["expo_Gamma"])
+
+
+def test_abpg_gain_golden(acc, dopt, golden_traj):
+    f, h, L, x0 = dopt
+    x, F, Gain, Gdiv, Gavg, T = acc.ABPG_gain(f, h, L, x0, gamma=2, maxitrs=1000, G0=0.1, theta_eq=True, verbose=False)
+    assert ferr(F, golden_traj["gain_F"]) <= FTOL
+    assert np.array_equal(Gain, golden_traj["gain_Gain"])            # the gain G_k: identical line-search decisions
+    assert relerr(Gavg, golden_traj["gain_Gavg"]) <= 1e-12
+    assert relerr(Gdiv[:200], golden_traj["gain_Gdiv"][:200]) <= 1e-6
+    assert relerr(x, golden_traj["gain_x"]) <= 1e-6
+    x, F, Gain, Gdiv, Gavg, T = acc.ABPG_gain(f, h, L, x0, gamma=2, maxitrs=400, G0=1, theta_eq=False, restart=True,
+                                              verbose=False)
+    assert ferr(F, golden_traj["gain_rs_F"]) <= FTOL and np.array_equal(Gain, golden_traj["gain_rs_Gain"])
+
+
+def test_abda_golden(acc, dopt, golden_traj):
+    f, h, L, x0 = dopt
+    x, F, G, T = acc.ABDA(f, h, L, x0, gamma=2, maxitrs=600, theta_eq=True, verbose=False)
+    assert ferr(F, golden_traj["abda_F"]) <= FTOL
+    assert relerr(x, golden_traj["abda_x"]) <= 1e-6
+
+
+def test_fw_generic_golden(acc, dopt, golden_traj):
+    f, h, L, x0 = dopt
+    x, F, Ls, T = acc.FW_alg_div_step(f, h, L, x0, maxitrs=300, gamma=2.0, lmo=acc.lmo_simplex(), ls_ratio=2,
+                                      verbose=False)
+    assert ferr(F, golden_traj["fwdiv_F"]) <= FTOL
+    assert np.array_equal(Ls, golden_traj["fwdiv_Ls"])
+    assert relerr(x, golden_traj["fwdiv_x"]) <= 1e-6
+    x, F, T, G = acc.FW_alg_descent_step(f, h, x0, maxitrs=300, lmo=acc.lmo_simplex(), verbose=False)
+    assert ferr(F, golden_traj["fwdesc_F"]) <= FTOL and not G.any()
+    # vertex sequence of the first 100 iterations is bit-identical to the oracle's
+    fo, ho, Lo, x0o = orc.D_opt_design(80, 200, randseed=10)
+    log = []
+    orc.FW_alg_div_step(fo, ho, Lo, x0o, maxitrs=100, gamma=2.0, lmo=orc.make_lmo_simplex(), vertex_log=log)
+    lmo = acc.lmo_simplex()
+    mine = []
+
+    def logging_lmo(g):
+        s = lmo(g)
+        mine.append(lmo.last_index())
+        return s
+    acc.FW_alg_div_step(f, h, L, x0, maxitrs=100, gamma=2.0, lmo=logging_lmo, verbose=False)
+    assert mine == log
+    with pytest.raises(ValueError):
+        acc.FW_alg_div_step(f, h, -1.0, x0, 10, 2.0, acc.lmo_simplex(), verbose=False)
+
+
+def test_housing_libsvm_golden(acc, golden_traj, golden_ops):
+    import os
+    from conftest import GOLDEN
+    f, h, L, x0 = acc.D_opt_libsvm(os.path.join(GOLDEN, "housing_libsvm.txt"))
+    assert (f.m, f.n) == (13, 506)
+    x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=1001, linesearch=True, ls_ratio=1.2, verbose=False)
+    assert ferr(F, golden_traj["housing_bpg_ls_F"]) <= FTOL
+    assert np.array_equal(Ls, golden_traj["housing_bpg_ls_Ls"])
+    assert f"{F[1000]:.3e}" == "-5.102e+01" and f"{Ls[1000]:.3e}" == "4.019e-01"     # notebook row
+
+
+def test_kl_poisson_golden(acc, golden_traj):
+    t = golden_traj
+    f, h, L, x0 = acc.KL_nonneg_regr(300, 120, noise=0.01, lamdaL1=0.001, randseed=1)
+    x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=300, linesearch=True, verbose=False)
+    assert ferr(F, t["kl_bpg_F"]) <= FTOL and np.array_equal(Ls, t["kl_bpg_Ls"])
+    x, F, Gain, Gdiv, Gavg, T = acc.ABPG_gain(f, h, L, x0, gamma=2.0, maxitrs=300, verbose=False)
+    assert ferr(F, t["kl_gain_F"]) <= FTOL and np.array_equal(Gain, t["kl_gain_Gain"])
+    f, h, L, x0 = acc.Poisson_regrL1(200, 100, noise=1e-4, lamda=0, randseed=1)
+    x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=300, linesearch=True, verbose=False)
+    assert ferr(F, t["poi_bpg_F"]) <= FTOL and np.array_equal(Ls, t["poi_bpg_Ls"])
+    f, h, L, x0 = acc.Poisson_regrL2(200, 100, noise=1e-3, lamda=1e-3, randseed=1)
+    x, F, Gain, Gdiv, Gavg, T = acc.ABPG_gain(f, h, L, x0, gamma=2.0, maxitrs=300, verbose=False)
+    assert ferr(F, t["poi2_gain_F"]) <= FTOL and np.array_equal(Gain, t["poi2_gain_Gain"])
+    f = acc.KLdivRegression(t["kls_A"], t["kls_b"])
+    h = acc.ShannonEntropySimplex()
+    x0 = np.ones(400) / 400
+    x, F, Gain, Gdiv, Gavg, T = acc.ABPG_gain(f, h, 1.0, x0, gamma=2.0, maxitrs=300, verbose=False)
+    assert ferr(F, t["kls_gain_F"]) <= FTOL and np.array_equal(Gain, t["kls_gain_Gain"])
+    assert relerr(x, t["kls_gain_x"]) <= 1e-6
+    x, F, Ls, T = acc.FW_alg_div_step(f, h, 1.0, x0, maxitrs=100, gamma=2.0, lmo=acc.lmo_simplex(), verbose=False)
+    assert ferr(F, t["kls_fw_F"]) <= FTOL and np.array_equal(Ls, t["kls_fw_Ls"])
+
+
+def test_oracle_drivers_over_gpu_operators(acc):
+    """The oracle's NumPy driver loops drive the GPU operators through the public NumPy interface:
+    the operators are drop-ins for the reference protocol, not only for this package's drivers."""
+    f, h, L, x0 = acc.D_opt_design(30, 120, randseed=6)
+    fo, ho, Lo, x0o = orc.D_opt_design(30, 120, randseed=6)
+    a = orc.ABPG_gain(f, h, L, x0, gamma=2, maxitrs=60)
+    b = orc.ABPG_gain(fo, ho, Lo, x0o, gamma=2, maxitrs=60)
+    assert ferr(a[1], b[1]) <= FTOL and np.array_equal(a[2], b[2])
+    a = orc.FW_alg_div_step(f, h, L, x0, 40, 2.0, acc.lmo_simplex())
+    b = orc.FW_alg_div_step(fo, ho, Lo, x0o, 40, 2.0, orc.make_lmo_simplex())
+    assert ferr(a[1], b[1]) <= FTOL and np.array_equal(a[2], b[2])
+
+
+def test_midsize_trajectory_vs_oracle(acc):
+    """500 x 5000 (reduced twin of the benchmark shape): 25 ABPG and ABPG_gain iterations against the oracle."""
+    f, h, L, x0 = acc.D_opt_design(500, 5000, randseed=1)
+    fo = orc.make_dopt(f.H)
+    ho = orc.make_burg("simplex")
+    a = acc.ABPG(f, h, L, x0, gamma=2, maxitrs=25, verbose=False)
+    b = orc.ABPG(fo, ho, L, x0, gamma=2, maxitrs=25)
+    assert ferr(a[1], b[1]) <= FTOL and relerr(a[2], b[2]) <= 1e-6
+    a = acc.ABPG_gain(f, h, L, x0, gamma=2, maxitrs=15, verbose=False)
+    b = orc.ABPG_gain(fo, ho, L, x0, gamma=2, maxitrs=15)
+    assert ferr(a[1], b[1]) <= FTOL and np.array_equal(a[2], b[2])

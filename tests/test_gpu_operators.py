@@ -1,0 +1,296 @@
+"""GPU parity: every operator of the hot path, called through the C ABI, against the CPU oracle
+(oracle/accbpg_oracle.py) and the golden fixtures generated from the real reference.
+Tolerances: objective values 1e-10 relative, gradients 1e-9 relative (FP64 throughout;
+only summation order, Cholesky-vs-LU and 1-ulp libm differences separate the two paths);
+index results (LMO vertices) bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+from oracle import accbpg_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def acc():
+    import accbpg_and_fw_b200 as a
+    return a
+
+
+def rel(a, b):
+    return relerr(a, b)
+
+
+# ------------------------------------------------------------------ D-optimal design objective
+@pytest.mark.parametrize("m,n,seed", [(80, 200, 10), (30, 1000, 3), (129, 517, 7), (5, 6, 1), (64, 4096, 2),
+                                      (200, 3001, 4), (300, 20000, 5)])
+def test_dopt_func_grad_vs_oracle(acc, m, n, seed):
+    rng = np.random.RandomState(seed)
+    f, h, L, x0 = acc.D_opt_design(m, n, randseed=seed)
+    fo = orc.make_dopt(f.H)
+    x = rng.rand(n) + 1e-3
+    x /= x.sum()
+    for xx in (x0, x):
+        fx, g = f.func_grad(xx)
+        fxo, go = fo.func_grad(xx)
+        assert abs(fx - fxo) <= 1e-10 * max(1.0, abs(fxo)), (fx, fxo)
+        assert rel(g, go) <= 1e-9
+        assert abs(f(xx) - fxo) <= 1e-10 * max(1.0, abs(fxo))
+        assert rel(f.gradient(xx), go) <= 1e-9
+        # size-independent identity: sum_j x_j g_j = -trace(M^-1 M) = -m
+        assert abs(float(np.dot(xx, g)) + m) <= 1e-9 * m
+
+
+def test_dopt_golden_fixtures(acc, golden_ops):
+    for tag, (m, n, seed) in {"dopt_80x200": (80, 200, 10), "dopt_30x1000": (30, 1000, 3),
+                              "dopt_129x517": (129, 517, 7)}.items():
+        f, h, L, x0 = acc.D_opt_design(m, n, randseed=seed)
+        fx, g = f.func_grad(golden_ops[tag + "_x"])
+        assert abs(fx - golden_ops[tag + "_f"]) <= 1e-10 * abs(golden_ops[tag + "_f"])
+        assert rel(g, golden_ops[tag + "_g"]) <= 1e-9
+        assert abs(f(x0) - golden_ops[tag + "_f0"]) <= 1e-10 * abs(golden_ops[tag + "_f0"])
+    f = acc.DOptimalObj(golden_ops["housing_H"])
+    x0 = np.ones(506) / 506
+    assert abs(f(x0) - golden_ops["housing_f0"]) <= 1e-10 * abs(golden_ops["housing_f0"])
+    assert rel(f.gradient(x0), golden_ops["housing_g0"]) <= 1e-9
+
+
+def test_dopt_device_tensor_in_out_and_sparse_x(acc):
+    f, h, L, x0 = acc.D_opt_design(40, 300, randseed=3)
+    fo = orc.make_dopt(f.H)
+    xd = torch.tensor(x0, device="cuda")
+    fx, g = f.func_grad(xd)
+    assert isinstance(g, torch.Tensor) and g.is_cuda and g.dtype == torch.float64
+    assert rel(g.cpu().numpy(), fo.gradient(x0)) <= 1e-9
+    # x with exact zeros (support of 2m columns): still positive definite
+    xs = np.zeros(300)
+    xs[:80] = 1.0 / 80
+    fx, g = f.func_grad(xs)
+    fxo, go = fo.func_grad(xs)
+    assert abs(fx - fxo) <= 1e-10 * abs(fxo) and rel(g, go) <= 1e-8
+
+
+def test_dopt_error_behaviour(acc):
+    f, h, L, x0 = acc.D_opt_design(20, 60, randseed=2)
+    bad = x0.copy()
+    bad[7] = -1e-3
+    with pytest.raises(AssertionError):
+        f.func_grad(bad)
+    with pytest.raises(AssertionError):
+        f.func_grad(x0[:-1])
+    rank_def = np.zeros(60)
+    rank_def[:5] = 0.2                       # only 5 columns for m = 20 -> singular
+    with pytest.raises(ValueError):
+        f(rank_def)
+    assert np.isfinite(f(x0))                # status word was cleared by the failed calls
+    with pytest.raises(AssertionError):
+        acc.DOptimalObj(np.random.randn(10, 10))
+
+
+def test_dopt_properties_at_benchmark_shape(acc):
+    """C2 shape (500 x 50000): too slow for the NumPy oracle inside the suite, so size-independent properties:
+    <x, g> = -m, f(c x) = f(x) - m log c, run-to-run bit reproducibility."""
+    m, n = 500, 50000
+    g0 = torch.Generator(device="cuda").manual_seed(1)
+    H = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g0)
+    f = acc.DOptimalObj(H)
+    x = torch.rand(n, dtype=torch.float64, device="cuda", generator=g0) + 0.1
+    x /= x.sum()
+    fx, g = f.func_grad(x)
+    assert abs(float(torch.dot(x, g)) + m) <= 1e-9 * m
+    f2 = f(3.0 * x)
+    assert abs(f2 - (fx - m * np.log(3.0))) <= 1e-10 * abs(fx)
+    fx_b, g_b = f.func_grad(x)
+    assert fx_b == fx and torch.equal(g, g_b)
+    # spot-check 64 gradient entries against a dense solve
+    M = (H * x) @ H.T
+    cols = torch.arange(0, n, n // 64, device="cuda")[:64]
+    ref = -(H[:, cols] * torch.linalg.solve(M, H[:, cols])).sum(0)
+    assert rel(g[cols].cpu().numpy(), ref.cpu().numpy()) <= 1e-9
+    assert abs(fx + float(torch.linalg.slogdet(M)[1])) <= 1e-10 * abs(fx)
+
+
+# ------------------------------------------------------------------ Poisson / KL objectives
+@pytest.mark.parametrize("kind", ["poisson", "kl"])
+@pytest.mark.parametrize("m,n", [(200, 100), (37, 1001), (300, 70000), (4, 3)])
+def test_linreg_vs_oracle(acc, kind, m, n):
+    rng = np.random.RandomState(m + n)
+    A = rng.rand(m, n)
+    A = A / A.sum(axis=0)
+    xs = rng.rand(n) + 0.05
+    b = A @ xs * (1 + 0.1 * (rng.rand(m) - 0.5))
+    x = rng.rand(n) + 0.05
+    f = (acc.PoissonRegression if kind == "poisson" else acc.KLdivRegression)(A, b)
+    fo = (orc.make_poisson if kind == "poisson" else orc.make_kl)(A, b)
+    fx, g = f.func_grad(x)
+    fxo, go = fo.func_grad(x)
+    assert abs(fx - fxo) <= 1e-10 * max(abs(fxo), 1e-3), (fx, fxo)
+    assert np.max(np.abs(g - go)) <= 1e-10 * np.max(np.abs(go))
+    assert abs(f(x) - fxo) <= 1e-10 * max(abs(fxo), 1e-3)
+    assert np.max(np.abs(f.gradient(x) - go)) <= 1e-10 * np.max(np.abs(go))
+
+
+def test_linreg_golden(acc, golden_ops):
+    o = golden_ops
+    f = acc.PoissonRegression(o["poisson_A"], o["poisson_b"])
+    fx, g = f.func_grad(o["poisson_x"])
+    assert abs(fx - o["poisson_f"]) <= 1e-10 * abs(o["poisson_f"]) and rel(g, o["poisson_g"]) <= 1e-9
+    f = acc.KLdivRegression(o["kl_A"], o["kl_b"])
+    fx, g = f.func_grad(o["kl_x"])
+    assert abs(fx - o["kl_f"]) <= 1e-10 * abs(o["kl_f"]) and rel(g, o["kl_g"]) <= 1e-8
+    f, h, L, x0 = acc.Poisson_regrL1(200, 100, noise=1e-4, lamda=0, randseed=1)
+    assert np.array_equal(f.A, o["poisson_A"]) and L == o["poisson_L"]
+    assert abs(f(x0) - o["poisson_f0"]) <= 1e-10 * abs(o["poisson_f0"])
+    f, h, L, x0 = acc.KL_nonneg_regr(1000, 100, noise=0.01, lamdaL1=0.001, randseed=1)
+    assert abs(f(x0) + h.extra_Psi(x0) - o["kl1000_F0"]) <= 1e-10 * abs(o["kl1000_F0"])
+
+
+# ------------------------------------------------------------------ Bregman kernels
+def test_bregman_kernels_golden(acc, golden_ops):
+    o = golden_ops
+    x, y, g, gp, ys = o["vec_x"], o["vec_y"], o["vec_g"], o["vec_gpos"], o["vec_ysimplex"]
+    L = 0.7
+    tol = 1e-12
+    b = acc.BurgEntropy()
+    assert abs(b(x) - o["burg_h"]) <= tol * abs(o["burg_h"])
+    assert rel(b.gradient(x), o["burg_grad"]) <= tol
+    assert abs(b.divergence(x, y) - o["burg_div"]) <= tol * abs(o["burg_div"])
+    assert rel(b.prox_map(gp, L), o["burg_prox"]) <= tol
+    assert rel(b.div_prox_map(y, gp, L), o["burg_divprox"]) <= tol
+    b1 = acc.BurgEntropyL1(lamda=0.3)
+    assert rel(b1.prox_map(gp, L), o["burgl1_prox"]) <= tol
+    assert rel(b1.div_prox_map(y, g * 0.1, L), o["burgl1_divprox"]) <= tol
+    assert abs(b1.extra_Psi(x) - o["burgl1_psi"]) <= tol * abs(o["burgl1_psi"])
+    b2 = acc.BurgEntropyL2(lamda=0.3)
+    assert rel(b2.prox_map(g, L), o["burgl2_prox"]) <= 1e-10        # (sqrt(gg^2+4l)-gg) cancels for large gg
+    assert rel(b2.div_prox_map(y, g, L), o["burgl2_divprox"]) <= 1e-10
+    assert abs(b2.extra_Psi(x) - o["burgl2_psi"]) <= tol * abs(o["burgl2_psi"])
+    bs = acc.BurgEntropySimplex()
+    assert rel(bs.prox_map(g, L), o["burgs_prox"]) <= 1e-11
+    assert rel(bs.div_prox_map(ys, g, L), o["burgs_divprox"]) <= 1e-11
+    s = acc.ShannonEntropy()
+    assert abs(s(x) - o["sh_h"]) <= tol * abs(o["sh_h"])
+    assert rel(s.gradient(x), o["sh_grad"]) <= 1e-11
+    assert abs(s.divergence(x, y) - o["sh_div"]) <= 1e-11 * abs(o["sh_div"])
+    assert rel(s.prox_map(g, L), o["sh_prox"]) <= tol
+    assert rel(s.div_prox_map(y, g, L), o["sh_divprox"]) <= tol
+    s1 = acc.ShannonEntropyL1(lamda=0.3)
+    assert rel(s1.prox_map(g, L), o["shl1_prox"]) <= tol
+    assert rel(s1.div_prox_map(y, g, L), o["shl1_divprox"]) <= tol
+    ss = acc.ShannonEntropySimplex()
+    assert rel(ss.prox_map(g, L), o["shs_prox"]) <= tol
+    assert rel(ss.div_prox_map(ys, g, L), o["shs_divprox"]) <= tol
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 200, 4097, 100003, 1000000])
+def test_burg_simplex_newton_replay(acc, n):
+    """Same Newton iteration count and root as the reference recurrence, at every size incl. n = 10^6."""
+    rng = np.random.RandomState(n % 1000 + 1)
+    g = rng.randn(n)
+    y = rng.rand(n) + 1e-3
+    y /= y.sum()
+    L = 0.37
+    h = acc.BurgEntropySimplex()
+    rt = h.rt
+    for yy in (None, y):
+        if n <= 5000:
+            ho = orc.make_burg("simplex")
+            xo = ho.prox_map(g, L) if yy is None else ho.div_prox_map(yy, g, L)
+            nbis_o, nnewt_o, c_o = ho.newton_trace[-1]
+        else:   # vectorised restatement of the same recurrence (the builtin-sum oracle takes minutes at 10^6)
+            gg = (g if yy is None else g - L * (-1 / yy)) / L
+            cmin = -gg.min(); c = cmin + 1; nbis_o = 0
+            while np.sum(1 / (gg + c)) - 1 < 0:
+                c = (cmin + c) / 2.0; nbis_o += 1
+            fc = np.sum(1 / (gg + c)) - 1; nnewt_o = 0
+            while abs(fc) > 1e-8:
+                fpc = np.sum(-1.0 / (gg + c) ** 2)
+                if (c - (c - fc / fpc)) == 0:
+                    break
+                c = c - fc / fpc; fc = np.sum(1 / (gg + c)) - 1; nnewt_o += 1
+            xo, c_o = 1.0 / (gg + c), c
+        x = h.prox_map(g, L) if yy is None else h.div_prox_map(yy, g, L)
+        info = rt.scal[rt.S_AUX1:rt.S_AUX1 + 3].cpu().numpy()
+        assert (int(info[0]), int(info[1])) == (nbis_o, nnewt_o)
+        assert abs(info[2] - c_o) <= 1e-12 * abs(c_o)
+        assert rel(x, xo) <= 1e-10
+        assert abs(x.sum() - 1.0) <= 1e-7       # normalised only to eps, like the reference
+
+
+def test_bregman_error_behaviour(acc):
+    b = acc.BurgEntropy()
+    x = np.array([0.5, 0.0, 1.0])
+    with pytest.raises(AssertionError):
+        b(x)
+    with pytest.raises(AssertionError):
+        b.divergence(np.ones(3), x)
+    with pytest.raises(AssertionError):
+        b.prox_map(np.array([1.0, -1.0, 2.0]), 1.0)
+    with pytest.raises(AssertionError):
+        acc.BurgEntropyL1(lamda=0.1).prox_map(np.array([1.0, -0.2, 2.0]), 1.0)
+    with pytest.raises(AssertionError):
+        b.prox_map(np.ones(3), -1.0)
+    with pytest.raises(AssertionError):
+        acc.ShannonEntropy()(np.array([0.1, -0.1]))
+    with pytest.raises(AssertionError):
+        acc.ShannonEntropySimplex().div_prox_map(np.array([0.5, 0.0, 0.5]), np.ones(3), 1.0)
+    assert np.isfinite(b(np.ones(3)))
+    # Shannon at exact zeros: h(0) = 0 through the delta clamp
+    s = acc.ShannonEntropy()
+    so = orc.make_shannon()
+    z = np.array([0.0, 0.3, 0.0, 0.7])
+    assert abs(s(z) - so(z)) <= 1e-15 and abs(s.divergence(z, np.array([0.25] * 4)) - so.divergence(z, np.array([0.25] * 4))) <= 1e-15
+
+
+def test_vector_primitives(acc):
+    from accbpg_and_fw_b200 import _native as nat
+    rt = acc.Runtime.get()
+    lib = nat.lib
+    for n in (1, 5, 1000, 123457):
+        rng = np.random.RandomState(n % 97)
+        a, b, g = rng.randn(n), rng.randn(n), rng.randn(n)
+        ad, bd, gd = (rt.to_device(v) for v in (a, b, g))
+        out = rt.empty(n)
+        nat.check(lib.accbpg_vec_axpby(rt.ctx, rt.stream, n, 0.3, ad.data_ptr(), 0.7, bd.data_ptr(), out.data_ptr()))
+        assert np.array_equal(out.cpu().numpy(), 0.3 * a + 0.7 * b)          # bit-exact: same two roundings
+        nat.check(lib.accbpg_vec_step_toward(rt.ctx, rt.stream, n, ad.data_ptr(), bd.data_ptr(), 0.25, out.data_ptr()))
+        assert np.array_equal(out.cpu().numpy(), a + 0.25 * (b - a))
+        nat.check(lib.accbpg_vec_dot_diff(rt.ctx, rt.stream, n, gd.data_ptr(), ad.data_ptr(), bd.data_ptr(), rt.slot(40)))
+        nat.check(lib.accbpg_vec_dot(rt.ctx, rt.stream, n, ad.data_ptr(), bd.data_ptr(), rt.slot(41)))
+        nat.check(lib.accbpg_vec_sum(rt.ctx, rt.stream, n, ad.data_ptr(), rt.slot(42)))
+        nat.check(lib.accbpg_vec_minmax(rt.ctx, rt.stream, n, ad.data_ptr(), rt.slot(43)))
+        nat.check(lib.accbpg_vec_argext(rt.ctx, rt.stream, n, ad.data_ptr(), 1, rt.slot(45)))
+        v = rt.read(40, 7)
+        scale = np.sum(np.abs(g * (a - b))) + 1e-300
+        assert abs(v[0] - np.dot(g, a - b)) <= 1e-14 * scale
+        assert abs(v[1] - np.dot(a, b)) <= 1e-14 * np.sum(np.abs(a * b))
+        assert abs(v[2] - a.sum()) <= 1e-14 * np.sum(np.abs(a))
+        assert v[3] == a.min() and v[4] == a.max()
+        assert v[5] == a.max() and int(v[6]) == int(np.argmax(a))
+
+
+# ------------------------------------------------------------------ LMOs
+def test_lmos_golden(acc, golden_ops):
+    o = golden_ops
+    g, x, gt = o["vec_g"], o["vec_x"], o["lmo_gties"]
+    lmo = acc.lmo_simplex(2.0)
+    s = lmo(gt)
+    assert np.array_equal(s, o["lmo_simplex"])                      # bit-exact, first index among 3 exact ties
+    assert lmo.last_index() == 137
+    assert rel(acc.lmo_l2_ball(1.5)(g), o["lmo_l2"]) <= 1e-14
+    assert rel(acc.lmo_l2_ball(1.5, center=x)(g), o["lmo_l2_center"]) <= 1e-13
+    assert np.max(np.abs(acc.lmo_l2_ball_positive_orthant(1.5, center=x, epsilon=1e-3)(g) - o["lmo_l2pos"])) <= 1e-14
+    assert np.array_equal(acc.lmo_linf_ball(0.5, center=x)(g), o["lmo_linf"])
+    assert np.array_equal(acc.lmo_matrix_simplex(3.0)(g.reshape(25, 40)), o["lmo_msimplex"])
+    assert np.array_equal(acc.lmo_matrix_box(-np.ones((25, 40)), 2 * np.ones((25, 40)))(g.reshape(25, 40)), o["lmo_mbox"])
+
+
+def test_lmo_simplex_large_ties(acc):
+    n = 1000003
+    g = np.ones(n)
+    g[[999999, 5, 777777]] = -2.0
+    lmo = acc.lmo_simplex()
+    s = lmo(g)
+    assert lmo.last_index() == 5 and s[5] == 1.0 and s[4] == 1e-15 and s.sum() == orc.lmo_simplex_eval(g).sum()
