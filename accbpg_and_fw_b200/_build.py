@@ -1,6 +1,7 @@
 """Build recipe for libaccbpg_b200.so (sm_100a only, in-tree, no torch linkage).
 
-    python -m accbpg_and_fw_b200._build          # or  __graft_entry__.build()
+    python accbpg_and_fw_b200/_build.py          # or  __graft_entry__.build()
+    (run it by path: importing the package requires an up-to-date library)
 
 nvcc cross-compiles without a GPU.  The shared object is written next to this file so
 it travels with the repo snapshot to the GPU box; it links cudart statically and has
@@ -23,6 +24,7 @@ SOURCES = {
     "linreg.cu": ["-fmad=false"],
     "fw.cu": ["-fmad=false"],
     "dopt.cu": [],
+    "prof.cu": [],
 }
 
 

@@ -21,6 +21,7 @@ _CTYPES = {
     "uint32_t*": ctypes.POINTER(ctypes.c_uint32),
     "int": ctypes.c_int,
     "int64_t": ctypes.c_int64,
+    "int64_t*": ctypes.POINTER(ctypes.c_int64),
     "uint64_t": ctypes.c_uint64,
     "size_t": ctypes.c_size_t,
     "double": ctypes.c_double,
@@ -62,7 +63,7 @@ class NativeError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m accbpg_and_fw_b200._build` "
+            f"{LIB_PATH} is missing: build it with `python accbpg_and_fw_b200/_build.py` "
             "(nvcc, sm_100a).  This package has no CPU fallback.")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (ret, args) in PROTOS.items():

@@ -54,6 +54,15 @@ inline int arg_err(const char* what) {
         if (e__ != cudaSuccess) return accbpg::set_err(name, e__); \
     } while (0)
 
+// optional cudaEvent bracketing of selected launches (prof.cu); a no-op unless accbpg_prof_enable(1)
+enum ProfId { P_SYRK = 0, P_SYRK_REDUCE, P_CHOL, P_TRINV, P_TRMM, P_GRAD_FIN, P_BURG_SIMPLEX, P_MATVEC, P_RMATVEC,
+              P_FW_PASS, P_FW_ITER, P_COUNT };
+struct ProfScope {
+    ProfScope(int id, cudaStream_t s);
+    ~ProfScope();
+    int id_; cudaStream_t s_; bool active_;
+};
+
 // defined in dopt.cu: byte offset of Linv (mp x mp, zero padded) inside the dopt workspace
 size_t dopt_linv_offset(int m, int64_t n, int sm_count, int* mp_out);
 

@@ -639,11 +639,17 @@ int accbpg_dopt_gram(void* ctx, void* stream, const double* H, int m, int64_t n,
     p.status = c->d_status;
     dim3 grid(pl.ntri, pl.splits);
     bool al = aligned16(H) && aligned16(x) && (ldh % 2 == 0);
-    if (al) syrk_dmma_kernel<true><<<grid, GEMM_THREADS, SYRK_SMEM, s>>>(p);
-    else    syrk_dmma_kernel<false><<<grid, GEMM_THREADS, SYRK_SMEM, s>>>(p);
+    {
+        ProfScope ps(P_SYRK, s);
+        if (al) syrk_dmma_kernel<true><<<grid, GEMM_THREADS, SYRK_SMEM, s>>>(p);
+        else    syrk_dmma_kernel<false><<<grid, GEMM_THREADS, SYRK_SMEM, s>>>(p);
+    }
     ACCBPG_LAUNCHED("syrk_dmma_kernel");
     dim3 rg((m + 31) / 32, (m + 7) / 8);
-    syrk_reduce_kernel<<<rg, 256, 0, s>>>(p.P, pl.splits, m, pl.mp, M);
+    {
+        ProfScope ps(P_SYRK_REDUCE, s);
+        syrk_reduce_kernel<<<rg, 256, 0, s>>>(p.P, pl.splits, m, pl.mp, M);
+    }
     ACCBPG_LAUNCHED("syrk_reduce_kernel");
     return ACCBPG_OK;
 }
@@ -657,11 +663,14 @@ int accbpg_dopt_factor(void* ctx, void* stream, int m, const double* M, double* 
     double* acc = c->d_slots + 248;                  // running sum of log pivots
     ACCBPG_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), s));
     ACCBPG_CUDA(cudaMemsetAsync(L, 0, (size_t)m * m * sizeof(double), s));
-    for (int j0 = 0; j0 < m; j0 += CH_NB) {
-        int below = m - j0 - CH_NB;
-        int grid = below > 0 ? (below + CH_ROWS - 1) / CH_ROWS : 1;
-        chol_panel_kernel<<<grid, 256, 0, s>>>(M, L, m, j0, acc, c->d_status);
-        ACCBPG_LAUNCHED("chol_panel_kernel");
+    {
+        ProfScope ps(P_CHOL, s);
+        for (int j0 = 0; j0 < m; j0 += CH_NB) {
+            int below = m - j0 - CH_NB;
+            int grid = below > 0 ? (below + CH_ROWS - 1) / CH_ROWS : 1;
+            chol_panel_kernel<<<grid, 256, 0, s>>>(M, L, m, j0, acc, c->d_status);
+            ACCBPG_LAUNCHED("chol_panel_kernel");
+        }
     }
     store_neg_kernel<<<1, 1, 0, s>>>(acc, d_out);
     ACCBPG_LAUNCHED("store_neg_kernel");
@@ -681,11 +690,14 @@ int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n,
     double* part = (double*)((char*)ws + pl.off_part);
     ACCBPG_CUDA(cudaMemsetAsync(Linv, 0, (size_t)pl.mp * pl.mp * 8, s));
     int nblk = (m + CH_NB - 1) / CH_NB;
-    trinv_diag_kernel<<<nblk, 32, 0, s>>>(L, m, Linv, pl.mp);
-    ACCBPG_LAUNCHED("trinv_diag_kernel");
-    if (nblk > 1) {
-        trinv_cols_kernel<<<nblk - 1, 256, 0, s>>>(L, m, Linv, pl.mp);
-        ACCBPG_LAUNCHED("trinv_cols_kernel");
+    {
+        ProfScope ps(P_TRINV, s);
+        trinv_diag_kernel<<<nblk, 32, 0, s>>>(L, m, Linv, pl.mp);
+        ACCBPG_LAUNCHED("trinv_diag_kernel");
+        if (nblk > 1) {
+            trinv_cols_kernel<<<nblk - 1, 256, 0, s>>>(L, m, Linv, pl.mp);
+            ACCBPG_LAUNCHED("trinv_cols_kernel");
+        }
     }
     TrmmParams p;
     p.Linv = Linv; p.H = H; p.part = part; p.m = m; p.mp = pl.mp; p.nib = pl.nib;
@@ -694,11 +706,17 @@ int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n,
     if (npanels > 65535) return arg_err("dopt_grad: n_local too large for one launch (max 65535*128 columns)");
     dim3 grid(pl.nib, (unsigned)npanels);
     bool al = aligned16(H) && (ldh % 2 == 0);
-    if (al) trmm_colnorm_kernel<true><<<grid, GEMM_THREADS, TRMM_SMEM, s>>>(p);
-    else    trmm_colnorm_kernel<false><<<grid, GEMM_THREADS, TRMM_SMEM, s>>>(p);
+    {
+        ProfScope ps(P_TRMM, s);
+        if (al) trmm_colnorm_kernel<true><<<grid, GEMM_THREADS, TRMM_SMEM, s>>>(p);
+        else    trmm_colnorm_kernel<false><<<grid, GEMM_THREADS, TRMM_SMEM, s>>>(p);
+    }
     ACCBPG_LAUNCHED("trmm_colnorm_kernel");
     int fg = grid_for(c, n, 256, 2, 8);
-    grad_finalize_kernel<<<fg, 256, 0, s>>>(part, pl.nib, pl.npad, n, g);
+    {
+        ProfScope ps(P_GRAD_FIN, s);
+        grad_finalize_kernel<<<fg, 256, 0, s>>>(part, pl.nib, pl.npad, n, g);
+    }
     ACCBPG_LAUNCHED("grad_finalize_kernel");
     return ACCBPG_OK;
 }

@@ -353,6 +353,7 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
     p.ctrl = ctrl; p.v = v; p.hist_F = hist_F; p.hist_SP = hist_SP; p.hist_SN = hist_SN; p.hist_T = hist_T;
     p.partials = c->d_partials; p.ipartials = c->d_ipartials; p.counter = c->d_counter;
     for (int k = k_start; k < k_start + k_count; ++k) {
+        ProfScope ps_iter(P_FW_ITER, s);
         fw_argmax_kernel<<<sel_grid, FW_THREADS, 0, s>>>(n, w, c->d_partials, c->d_ipartials, c->d_counter, ctrl);
         ACCBPG_LAUNCHED("fw_argmax_kernel");
         p.k = k;
@@ -362,7 +363,10 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
         ACCBPG_LAUNCHED("fw_hv_kernel");
         fw_rank1_kernel<<<r1_grid, 256, 0, s>>>(Hinv, m, u, ctrl);
         ACCBPG_LAUNCHED("fw_rank1_kernel");
-        fw_pass_kernel<<<(unsigned)pass_grid, FWP_THREADS, pass_smem, s>>>(V, m, n, ldv, u, x, w, ctrl);
+        {
+            ProfScope ps(P_FW_PASS, s);
+            fw_pass_kernel<<<(unsigned)pass_grid, FWP_THREADS, pass_smem, s>>>(V, m, n, ldv, u, x, w, ctrl);
+        }
         ACCBPG_LAUNCHED("fw_pass_kernel");
     }
     return ACCBPG_OK;

@@ -250,8 +250,11 @@ int accbpg_linreg_matvec(void* ctx, void* stream, const double* A, int64_t m, in
     dim3 grid((unsigned)rowblocks, (unsigned)pl.nseg);
     bool vec = al16(A) && al16(x) && (lda % 2 == 0);
     double* out = (pl.nseg > 1) ? (double*)((char*)ws + pl.off_mv) : Ax;
-    if (vec) matvec_kernel<true><<<grid, MV_THREADS, 0, s>>>(A, m, n, lda, x, out, pl.pstride_mv);
-    else     matvec_kernel<false><<<grid, MV_THREADS, 0, s>>>(A, m, n, lda, x, out, pl.pstride_mv);
+    {
+        ProfScope ps(P_MATVEC, s);
+        if (vec) matvec_kernel<true><<<grid, MV_THREADS, 0, s>>>(A, m, n, lda, x, out, pl.pstride_mv);
+        else     matvec_kernel<false><<<grid, MV_THREADS, 0, s>>>(A, m, n, lda, x, out, pl.pstride_mv);
+    }
     ACCBPG_LAUNCHED("matvec_kernel");
     if (pl.nseg > 1) {
         int g = grid_for(c, m, 256, 2, 8);
@@ -286,8 +289,11 @@ int accbpg_linreg_rmatvec(void* ctx, void* stream, const double* A, int64_t m, i
     if (colblocks > 2147483647LL) return arg_err("linreg_rmatvec: n too large");
     dim3 grid((unsigned)colblocks, (unsigned)pl.nchunk);
     bool vec = al16(A) && (lda % 2 == 0);
-    if (vec) rmatvec_kernel<true><<<grid, RMV_THREADS, 0, s>>>(A, m, n, lda, r, pl.rows_per_chunk, partial, pl.pstride_rmv);
-    else     rmatvec_kernel<false><<<grid, RMV_THREADS, 0, s>>>(A, m, n, lda, r, pl.rows_per_chunk, partial, pl.pstride_rmv);
+    {
+        ProfScope ps(P_RMATVEC, s);
+        if (vec) rmatvec_kernel<true><<<grid, RMV_THREADS, 0, s>>>(A, m, n, lda, r, pl.rows_per_chunk, partial, pl.pstride_rmv);
+        else     rmatvec_kernel<false><<<grid, RMV_THREADS, 0, s>>>(A, m, n, lda, r, pl.rows_per_chunk, partial, pl.pstride_rmv);
+    }
     ACCBPG_LAUNCHED("rmatvec_kernel");
     int fg = grid_for(c, n, 256, 2, 8);
     seg_reduce_kernel<<<fg, 256, 0, s>>>(partial, pl.nchunk, pl.pstride_rmv, n, g, 1.0);

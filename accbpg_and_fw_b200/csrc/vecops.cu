@@ -598,6 +598,7 @@ int accbpg_burg_simplex_prox(void* ctx, void* stream, int64_t n, const double* y
     double* partials = c->d_partials;
     uint32_t* status = c->d_status;
     void* args[] = {&n, &y, &g, &L, &eps, &out, &info, &partials, &status};
+    ProfScope ps(P_BURG_SIMPLEX, s);
     ACCBPG_CUDA(cudaLaunchCooperativeKernel((void*)burg_simplex_kernel, dim3(grid), dim3(kBurgThreads), args, 0, s));
     ACCBPG_LAUNCHED("burg_simplex_prox");
     return ACCBPG_OK;

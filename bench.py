@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the accbpg hot path on B200 (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): D-optimal design, H = randn(500, 50000) per GPU
+(D_opt_design(500, 50000, randseed=1) at N=1), solved by ABPG with gamma=2.  One *step* is one ABPG outer
+iteration: f(x) [SYRK + Cholesky], grad f(y) [SYRK + Cholesky + L^-1 + triangular GEMM with column-norm
+epilogue], the Burg-simplex Bregman step, two axpby and two Burg divergences.  N > 1 is weak scaling:
+every rank owns a 500 x 50000 column slab of a 500 x (50000 N) design, the Gram matrix is all-reduced.
+
+Printed JSON (one line, rank 0):
+  value     ABPG iterations/s with H and the iterates resident in HBM (x N slabs under weak scaling)
+  e2e       the same iteration driven through the public operator protocol with HOST vectors
+            (NumPy in / NumPy out on every call, H resident in the operator as in the reference)
+  roofline  the dominant kernel (FP64 DMMA SYRK) against the FP64 GEMM rate measured in this run
+  cpu_baseline  the NumPy oracle port of the reference on this box's host cores (bounded sample)
+`--impl reference` times only that CPU path, on the same metric and config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_ROWS = 500
+N_PER_GPU = 50000
+GAMMA = 2
+
+
+def make_slab(rank, n_local):
+    """Legacy-RNG Gaussian slab; rank 0 at N=1 is exactly D_opt_design(500, 50000, randseed=1)'s H."""
+    np.random.seed(1 + rank)
+    return np.random.randn(M_ROWS, n_local)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference (test infrastructure; only ever the thing *compared against*)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_cpu_abpg(H, iters):
+    """ABPG(gamma=2) of the oracle on H; returns seconds per iteration measured from its own T array."""
+    from oracle import accbpg_oracle as orc
+    f = orc.make_dopt(H)
+    h = orc.make_burg("simplex")
+    n = H.shape[1]
+    x0 = (1.0 / n) * np.ones(n)
+    t0 = time.time()
+    x, F, G, T = orc.ABPG(f, h, 1.0, x0, gamma=GAMMA, maxitrs=iters + 1, theta_eq=False)
+    wall = time.time() - t0
+    per_it = (T[-1] - T[0]) / (len(T) - 1) if len(T) > 1 else wall
+    return per_it, F
+
+
+def reference_arm(args, world):
+    n = N_PER_GPU * world
+    H = np.concatenate([make_slab(r, N_PER_GPU) for r in range(world)], axis=1) if world > 1 else make_slab(0, n)
+    if args.warmup > 0:
+        run_cpu_abpg(H, max(1, min(args.warmup, 2)))
+    per_it, F = run_cpu_abpg(H, args.steps)
+    cores = cpu_threads()
+    value = world / per_it
+    line = {
+        "impl": "reference", "metric": "abpg_gamma2_iterations_per_sec", "value": value,
+        "unit": "it/s (x N slabs of 500x50000 under weak scaling)", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_it * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"D-opt {M_ROWS}x{n} (H=randn, seed 1+rank per slab), ABPG gamma=2, x0=1/n, L=1",
+                   "timing": "reference's own T array (time.time() at the top of each iteration)"},
+        "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} ABPG iterations of the NumPy oracle port (oracle/accbpg_oracle.py) "
+                                   f"on the full {M_ROWS}x{n} instance, os.cpu_count()={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measure_fp64_peak(torch):
+    """cuBLAS DGEMM 8192^3 burst rate: the FP64 roof MEASURED_PEAKS.json does not record."""
+    N = 8192
+    A = torch.randn(N, N, dtype=torch.float64, device="cuda")
+    B = torch.randn(N, N, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        torch.matmul(A, B)
+    best = 1e30
+    for _ in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); torch.matmul(A, B); b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    del A, B
+    torch.cuda.empty_cache()
+    return 2 * N ** 3 / best / 1e9
+
+
+def host_vector_abpg(f, h, L, x0, gamma, iters):
+    """ABPG (algorithms.py:94-180 call sequence) with HOST vectors through the public operator protocol:
+    every call uploads its NumPy arguments and downloads its result.  Returns (F, h2d_bytes, d2h_bytes)."""
+    n8 = x0.size * 8
+    x, z = x0.copy(), x0.copy()
+    F = np.zeros(iters)
+    up = down = 0
+    for k in range(iters):
+        F[k] = f(x) + h.extra_Psi(x); up += n8; down += 8
+        theta = gamma / (k + gamma)
+        y = (1 - theta) * x + theta * z
+        g = f.gradient(y); up += n8; down += n8
+        z1 = h.div_prox_map(z, g, theta ** (gamma - 1) * L); up += 2 * n8; down += n8
+        x = (1 - theta) * x + theta * z1
+        dxy = h.divergence(x, y); up += 2 * n8; down += 8
+        dzz = h.divergence(z1, z); up += 2 * n8; down += 8
+        z = z1
+    return F, up, down
+
+
+def native_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    import accbpg_and_fw_b200 as acc
+    from accbpg_and_fw_b200 import _native as nat
+    lib = nat.lib
+    import ctypes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    fp64_peak = measure_fp64_peak(torch) if not args.lean else float("nan")
+
+    n_total = N_PER_GPU * world
+    shard = acc.ColumnShard(n_total) if world > 1 else None
+    Hh = make_slab(rank, N_PER_GPU)
+    f = acc.DOptimalObj(Hh, shard=shard)
+    h = acc.BurgEntropySimplex(shard=shard)
+    L = 1.0
+    x0_host = (1.0 / n_total) * np.ones(N_PER_GPU)
+    x0 = torch.tensor(x0_host, device="cuda")
+    m, n = M_ROWS, N_PER_GPU
+
+    def prof_read():
+        out = {}
+        tot, cnt = ctypes.c_double(0), ctypes.c_int64(0)
+        for i in range(lib.accbpg_prof_count()):
+            nat.check(lib.accbpg_prof_read(i, ctypes.byref(tot), ctypes.byref(cnt)))
+            if cnt.value:
+                out[lib.accbpg_prof_name(i).decode()] = {"ms_total": tot.value, "launches": cnt.value,
+                                                         "ms_avg": tot.value / cnt.value}
+        return out
+
+    # ---- device-resident arm: W warm-up iterations, then exactly K timed iterations -----------------------
+    acc.ABPG(f, h, L, x0, gamma=GAMMA, maxitrs=max(args.warmup, 1), verbose=False)
+    lib.accbpg_prof_enable(1)
+    prof_read()
+    barrier()
+    launches0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        x, F, G, T = acc.ABPG(f, h, L, x0, gamma=GAMMA, maxitrs=args.steps, verbose=False)
+        e1.record()
+        barrier()
+    launches = nat.launch_count() - launches0
+    kern = prof_read()
+    lib.accbpg_prof_enable(0)
+    assert len(F) == args.steps, "ABPG stopped early: the timed region must contain exactly K iterations"
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms_total / args.steps
+    value = world * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e arm: host vectors through the public operator protocol ------------------------------------------
+    if args.lean:
+        if rank == 0:
+            print(json.dumps({"lean": True, "ms_per_step": ms_per_step, "value": value, "gpu_launches": launches,
+                              "kernel_ms_per_step": {k: v["ms_total"] / args.steps for k, v in kern.items()}}))
+        return
+    host_vector_abpg(f, h, L, x0_host, GAMMA, max(1, min(args.warmup, 3)))
+    barrier()
+    t0 = time.perf_counter()
+    Fh, up, down = host_vector_abpg(f, h, L, x0_host, GAMMA, args.steps)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert np.max(np.abs(Fh - F) / np.abs(F)) < 1e-9, "host-vector and device-resident runs disagree"
+    e2e = {"value": world * args.steps / e2e_s, "unit": "it/s", "h2d_bytes_per_step": up // args.steps,
+           "d2h_bytes_per_step": down // args.steps, "ms_per_step": e2e_s / args.steps * 1e3,
+           "how": "ABPG call sequence with NumPy vectors through f()/f.gradient()/h.div_prox_map()/h.divergence(); "
+                  "H stays bound to the operator (as f.H does in the reference)"}
+
+    # ---- second headline algorithm of this config: D_opt_FW_away (HBM-bound pass over V) --------------------
+    extra = {}
+    if world == 1:
+        lib.accbpg_prof_enable(1)
+        prof_read()
+        xa, Fa, SPa, SNa, Ta = acc.D_opt_FW_away(f._Hd, x0, 1e-12, 1500, verbose=False)
+        kfw = prof_read()
+        lib.accbpg_prof_enable(0)
+        if len(Ta) > 1:
+            extra["fw_away_it_per_s"] = (len(Ta) - 1) / (Ta[-1] - Ta[0])
+        p = kfw.get("fw_pass_kernel")
+        if p:
+            gbs = 8.0 * m * n / (p["ms_avg"] * 1e-3) / 1e9
+            extra["fw_pass_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                         "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                                         "ms_avg": p["ms_avg"], "bytes_per_launch": 8 * m * n,
+                                         "note": "V (200 MB) exceeds the 126 MB L2"}
+        it = kfw.get("fw_iteration(5 kernels)")
+        if it:
+            extra["fw_iteration_ms_avg"] = it["ms_avg"]
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------
+    syrk = kern.get("syrk_dmma_kernel")
+    roof = None
+    if syrk:
+        flops = float(m) * m * n                     # algorithmic SYRK count of SURVEY 8(d): m^2 n per launch
+        tf = flops / (syrk["ms_avg"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "syrk_dmma_kernel (FP64 DMMA.8x8x4)", "achieved": tf, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": tf / fp64_peak, "traffic": None,
+                "flops_per_launch": flops, "ms_avg": syrk["ms_avg"], "launches": syrk["launches"],
+                "peak_source": "torch.matmul float64 8192^3 burst measured in this run "
+                               "(MEASURED_PEAKS.json records no FP64 figure)"}
+    step_ms = {k: v["ms_total"] / args.steps for k, v in kern.items()}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        per_it, Fc = run_cpu_abpg(Hh, args.cpu_iters)
+        kk = min(len(Fc), len(F))
+        cpu = {"value": 1.0 / per_it, "unit": "it/s", "cores": cpu_threads(), "kind": "port",
+               "sample": f"{args.cpu_iters} ABPG iterations of the NumPy oracle port on the same {m}x{n} instance "
+                         f"(os.cpu_count()={os.cpu_count()}); F agrees with the GPU run to "
+                         f"{float(np.max(np.abs(Fc[:kk] - F[:kk]) / np.abs(Fc[:kk]))):.1e} over {kk} iterations"}
+
+    if rank == 0:
+        line = {
+            "metric": "abpg_gamma2_iterations_per_sec", "value": value,
+            "unit": "it/s (x N slabs of 500x50000 under weak scaling)", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"D-opt {m}x{n * world} (H=randn, seed 1+rank per {m}x{n} slab), ABPG gamma=2, "
+                                   f"x0=1/n, L=1, BurgEntropySimplex",
+                       "l2": "H slab is 200 MB per GPU (> 126 MB L2); no flush needed",
+                       "calls_per_step": "1 f(x) + 1 grad f(y) + 1 div_prox_map + 2 axpby + 2 divergence",
+                       "timing": "CUDA events on the launch stream around the K-iteration solve, max over ranks"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "kernel_ms_per_step": step_ms, "extra": extra,
+            "it_per_s_from_T": (len(T) - 1) / (T[-1] - T[0]) if len(T) > 1 else None,
+        }
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--cpu-iters", type=int, default=20, help="iterations of the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--lean", action="store_true",
+                    help="device-resident arm only (no FP64 probe, e2e, FW or CPU legs): the command profiled under ncu")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank == 0:
+            reference_arm(args, max(world, args.gpus if world == 1 else world))
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        native_arm(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,14 @@ const char* accbpg_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t    accbpg_launch_count(void);
 
+/* optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline line).
+ * ids 0..accbpg_prof_count()-1, names from accbpg_prof_name(); prof_read waits for the recorded events,
+ * returns the summed duration and the number of bracketed launches since the last read, and resets them. */
+int         accbpg_prof_enable(int on);
+int         accbpg_prof_count(void);
+const char* accbpg_prof_name(int id);
+int         accbpg_prof_read(int id, double* total_ms, int64_t* count);
+
 /* ---- context: small device scratch (reduction partials, 256 scalar slots,
  *      status word) + pinned host mirror.  One per device/thread of control. */
 int     accbpg_ctx_create(void** ctx);

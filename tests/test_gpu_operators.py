@@ -214,7 +214,8 @@ def test_burg_simplex_newton_replay(acc, n):
         x = h.prox_map(g, L) if yy is None else h.div_prox_map(yy, g, L)
         info = rt.scal[rt.S_AUX1:rt.S_AUX1 + 3].cpu().numpy()
         assert (int(info[0]), int(info[1])) == (nbis_o, nnewt_o)
-        assert abs(info[2] - c_o) <= 1e-12 * abs(c_o)
+        # the multiplier c is conditioned like n*eps (f'(c) = -sum 1/(gg+c)^2 ~ 1/n): compare on that scale
+        assert abs(info[2] - c_o) <= 1e-13 * n * max(1.0, abs(c_o))
         assert rel(x, xo) <= 1e-10
         assert abs(x.sum() - 1.0) <= 1e-7       # normalised only to eps, like the reference
 
