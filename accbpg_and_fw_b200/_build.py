@@ -24,6 +24,7 @@ SOURCES = {
     "linreg.cu": ["-fmad=false"],
     "fw.cu": ["-fmad=false"],
     "dopt.cu": [],
+    "chol.cu": [],
     "prof.cu": [],
 }
 
@@ -46,7 +47,7 @@ def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a and link the C-ABI shared library.  Returns its path."""
     os.makedirs(BUILD_DIR, exist_ok=True)
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, "common.cuh"),
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "dmma.cuh"),
                os.path.join(HERE, "..", "include", "accbpg_b200.h"),
                os.path.abspath(__file__)]
     objs = []

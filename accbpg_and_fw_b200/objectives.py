@@ -73,7 +73,7 @@ class DOptimalObj(RSmoothFunction):
         nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
                                        xd.data_ptr(), ws, self._M.data_ptr()))
         self.shard.sum_(self._M)
-        nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, self.m, self._M.data_ptr(), self._L.data_ptr(),
+        nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, self.m, self._M.data_ptr(), self._L.data_ptr(), ws,
                                          rt.slot(slot)))
         if flag >= 1:
             nat.check(lib.accbpg_dopt_grad(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),

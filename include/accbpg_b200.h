@@ -161,8 +161,9 @@ size_t accbpg_dopt_workspace_bytes(int m, int64_t n_local);
 int accbpg_dopt_gram(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
                      const double* d_x, void* d_ws, double* d_M);
 /* K2: blocked Cholesky M = L L^T, out of place (d_M symmetric m x m is only read; d_L m x m receives the lower
- * factor, zero above the diagonal); d_out[0] = -log det M = -sum log(pivot).  Sets ST_NOT_PD on a pivot <= 0. */
-int accbpg_dopt_factor(void* ctx, void* stream, int m, const double* d_M, double* d_L, double* d_out);
+ * factor, zero above the diagonal); d_out[0] = -log det M = -sum log(pivot).  Sets ST_NOT_PD on a pivot <= 0.
+ * d_ws is the dopt workspace (any n_local): two m x m trailing-matrix buffers ping-pong inside it. */
+int accbpg_dopt_factor(void* ctx, void* stream, int m, const double* d_M, double* d_L, void* d_ws, double* d_out);
 /* K3+K4: g_j = -|| L^{-1} h_j ||^2 for the local columns: triangular inverse, then a DMMA triangular
  * GEMM whose epilogue reduces squared column norms (M^{-1}H is never materialised). */
 int accbpg_dopt_grad(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
