@@ -315,8 +315,8 @@ static int launch_gemm(cudaStream_t s, const GemmNN& p) {
 }
 
 // ------------------------------------------------------------------------------------------ host entry points
-int chol_factor(Ctx* c, cudaStream_t s, int m, const double* M, double* L, double* Wa, double* Wb, double* d_out) {
-    double* acc = c->d_slots + 248;                  // running sum of log pivots
+int chol_factor(Ctx* c, cudaStream_t s, int m, const double* M, double* L, double* Wa, double* Wb, double* acc,
+                double* d_out) {                     // acc: device scalar, running sum of log pivots
     ACCBPG_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), s));
     ACCBPG_CUDA(cudaMemsetAsync(L, 0, (size_t)m * m * sizeof(double), s));
     {

@@ -27,6 +27,8 @@ struct Ctx {
     double* h_slots;        // pinned mirror (kSlots doubles)
     uint32_t* h_status;     // pinned
     int coop_blocks_burg;   // co-resident grid size for the Burg-simplex kernel
+    cudaStream_t side;      // side stream: a second latency-bound chain (Cholesky) runs next to the main one
+    cudaEvent_t ev_fork, ev_join;
 };
 
 extern thread_local char g_err[512];

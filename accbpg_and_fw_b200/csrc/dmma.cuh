@@ -106,23 +106,32 @@ __device__ __forceinline__ void mma_nn_slab(double (&acc)[MI][NI][2], const doub
                                             int g, int t) {
     const double* ap = As + (wm * 64 + g) * A_LD + t;
     const double* bp = Bs + t * BT_LD + wn * 32 + g;
+    // fragments are double buffered in registers: the LDS of step kk+1 are in flight under the DMMAs of step kk
+    double a[2][MI], b[2][NI];
+#pragma unroll
+    for (int i = 0; i < MI; ++i) a[0][i] = ap[i * 8 * A_LD];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) b[0][j] = bp[j * 8];
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
-        double a[MI], b[NI];
+        const int cur = kk & 1, nxt = cur ^ 1;
+        if (kk + 1 < BK / 4) {
 #pragma unroll
-        for (int i = 0; i < MI; ++i) a[i] = ap[i * 8 * A_LD + kk * 4];
+            for (int i = 0; i < MI; ++i) a[nxt][i] = ap[i * 8 * A_LD + (kk + 1) * 4];
 #pragma unroll
-        for (int j = 0; j < NI; ++j) b[j] = bp[kk * 4 * BT_LD + j * 8];
+            for (int j = 0; j < NI; ++j) b[nxt][j] = bp[(kk + 1) * 4 * BT_LD + j * 8];
+        }
 #pragma unroll
         for (int i = 0; i < MI; ++i)
 #pragma unroll
-            for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
     }
 }
 #endif  // __CUDACC__
 
 // defined in chol.cu (host side, stream ordered)
-int chol_factor(Ctx* c, cudaStream_t s, int m, const double* M, double* L, double* Wa, double* Wb, double* d_out);
+int chol_factor(Ctx* c, cudaStream_t s, int m, const double* M, double* L, double* Wa, double* Wb, double* acc,
+                double* d_out);
 int tri_inverse(Ctx* c, cudaStream_t s, int m, int mp, const double* L, double* Linv, double* T);
 
 }  // namespace accbpg

@@ -50,10 +50,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_dmma_kernel(SyrkParams p
 #pragma unroll
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // Per-thread copy descriptors of the fast path (aligned, k-slab fully inside the chunk): the same 16-byte column
+    // chunk of rows lr, lr+32, lr+64, lr+96 of the A block and of the B block.  Pointers advance by BK per k-slab, so
+    // a stage costs 8-9 cp.async and no address arithmetic beyond one add each.
+    const int ch = tid & 7, lr = tid >> 3;
+    const double* ga[4];
+    const double* gb[4];
+    int ba[4], bb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ra = bi * BM + lr + 32 * i, rb = bj * BN + lr + 32 * i;
+        ba[i] = ra < p.m ? 16 : 0;
+        bb[i] = rb < p.m ? 16 : 0;
+        ga[i] = p.H + (int64_t)(ba[i] ? ra : 0) * p.ldh + k_begin + ch * 2;
+        gb[i] = p.H + (int64_t)(bb[i] ? rb : 0) * p.ldh + k_begin + ch * 2;
+    }
+    const int soff = lr * A_LD + ch * 2;
+    const int KT_full = (k_end > k_begin) ? (int)((k_end - k_begin) / BK) : 0;
+
     auto load_stage = [&](int stage, int kt) {
         double* As = smem + stage * KMAJOR_STAGE_DOUBLES;
         double* Bs = As + BM * A_LD;
         double* Xs = Bs + BN * A_LD;
+        if (ALIGNED16 && kt < KT_full) {
+            const int64_t ko = (int64_t)kt * BK;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                cp_async16(As + soff + i * 32 * A_LD, ga[i] + ko, ba[i]);
+                cp_async16(Bs + soff + i * 32 * A_LD, gb[i] + ko, bb[i]);
+            }
+            if (tid < 8) cp_async16(Xs + tid * 2, p.x + k_begin + ko + tid * 2, 16);
+            return;
+        }
         const int64_t k0 = k_begin + (int64_t)kt * BK;
         load_kmajor_slab<ALIGNED16>(As, p.H, p.ldh, bi * BM, p.m, k0, k_end, tid);
         load_kmajor_slab<ALIGNED16>(Bs, p.H, p.ldh, bj * BN, p.m, k0, k_end, tid);
@@ -83,30 +111,43 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_dmma_kernel(SyrkParams p
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            int nk = kt + STAGES - 1;
-            if (nk < KT) load_stage(nk % STAGES, nk);
-            cp_async_commit();
-        }
+        // The two warps that share an SM sub-partition (wm = 0 / 1) issue their share of the next stage's copies at
+        // different points of the k-slab, so one of them is always feeding the DMMA pipe.
+        const int nk = kt + STAGES - 1;
+        if (wm == 0 && nk < KT) load_stage(nk % STAGES, nk);
         const double* As = smem + (kt % STAGES) * KMAJOR_STAGE_DOUBLES;
         const double* Bs = As + BM * A_LD;
         const double* Xs = Bs + BN * A_LD;
         const double* ap = As + (wm * 64 + g) * A_LD + t;
         const double* bp = Bs + (wn * 32 + g) * A_LD + t;
+        // fragments double buffered in registers: LDS (+ the diag(x) scaling) of step kk+1 run under the DMMAs of kk
+        double a[2][MI], b[2][NI];
+        {
+            const double xv = Xs[t];
+            neg |= (xv < 0.0);
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[0][i] = ap[i * 8 * A_LD];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) b[0][j] = bp[j * 8 * A_LD] * xv;
+        }
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            const double xv = Xs[kk * 4 + t];
-            neg |= (xv < 0.0);
-            double a[MI], b[NI];
+            const int cur = kk & 1, nxt = cur ^ 1;
+            if (kk == 2 && wm == 1 && nk < KT) load_stage(nk % STAGES, nk);
+            if (kk + 1 < BK / 4) {
+                const double xv = Xs[(kk + 1) * 4 + t];
+                neg |= (xv < 0.0);
 #pragma unroll
-            for (int i = 0; i < MI; ++i) a[i] = ap[i * 8 * A_LD + kk * 4];
+                for (int i = 0; i < MI; ++i) a[nxt][i] = ap[i * 8 * A_LD + (kk + 1) * 4];
 #pragma unroll
-            for (int j = 0; j < NI; ++j) b[j] = bp[j * 8 * A_LD + kk * 4] * xv;
+                for (int j = 0; j < NI; ++j) b[nxt][j] = bp[j * 8 * A_LD + (kk + 1) * 4] * xv;
+            }
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
         }
+        cp_async_commit();
     }
     cp_async_wait<0>();
     if (neg) atomicOr(p.status, ACCBPG_ST_X_NEGATIVE);
@@ -230,7 +271,7 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(const double* part, 
 struct DoptPlan {
     int mp, nt, ntri, nib, splits;
     int64_t kchunk, npad;
-    size_t off_P, off_Linv, off_T, off_part, off_M, off_L, off_Wa, off_Wb, total;
+    size_t off_P, off_Linv, off_T, off_part, off_M, off_L, off_Wa, off_Wb, off_M2, off_L2, off_Wa2, off_Wb2, total;
 };
 
 static DoptPlan make_plan(int m, int64_t n, int sm_count) {
@@ -265,6 +306,10 @@ static DoptPlan make_plan(int m, int64_t n, int sm_count) {
     pl.off_L = a;    a += mm;
     pl.off_Wa = a;   a += mm;
     pl.off_Wb = a;   a += mm;
+    pl.off_M2 = a;   a += mm;      // second set: the value-only evaluation that runs on the side stream
+    pl.off_L2 = a;   a += mm;
+    pl.off_Wa2 = a;  a += mm;
+    pl.off_Wb2 = a;  a += mm;
     pl.off_Linv = a; a += (size_t)pl.mp * pl.mp * 8;
     pl.off_T = a;    a += (size_t)pl.mp * pl.mp * 8;
     pl.off_P = a;    a += (size_t)pl.splits * pl.mp * pl.mp * 8;
@@ -350,7 +395,7 @@ int accbpg_dopt_factor(void* ctx, void* stream, int m, const double* M, double* 
     double* Wa = (double*)((char*)ws + pl.off_Wa);
     double* Wb = (double*)((char*)ws + pl.off_Wb);
     if (M == Wa || M == Wb || L == Wa || L == Wb) return arg_err("dopt_factor: M / L alias the factor scratch");
-    return chol_factor(c, s, m, M, L, Wa, Wb, d_out);
+    return chol_factor(c, s, m, M, L, Wa, Wb, c->d_slots + 248, d_out);
 }
 
 int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh, const double* L,
@@ -404,6 +449,38 @@ int accbpg_dopt_func_grad(void* ctx, void* stream, const double* H, int m, int64
     if (rc) return rc;
     if (flag >= 1) rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, L, ws, g);
     return rc;
+}
+
+// f(xf) and (f(yg), grad f(yg)) in one call: the two Gram matrices are formed back to back on the main stream, then
+// the value-only Cholesky runs on the context's side stream while the main stream factors M(yg), inverts L and
+// streams the gradient.  Both chains are latency bound on a handful of SMs, so they overlap almost completely.
+int accbpg_dopt_pair(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh, const double* xf,
+                     const double* yg, int flag_y, void* ws, double* d_fx_out, double* d_fy_out, double* g) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !ws || !xf || !yg || !d_fx_out) return arg_err("dopt_pair: NULL pointer");
+    if (flag_y < 1 || flag_y > 2 || !g) return arg_err("dopt_pair: flag_y must be 1 or 2 with a gradient buffer");
+    DoptPlan pl = make_plan(m, n, c->sm_count);
+    double* M1 = (double*)((char*)ws + pl.off_M);
+    double* L1 = (double*)((char*)ws + pl.off_L);
+    double* M2 = (double*)((char*)ws + pl.off_M2);
+    double* L2 = (double*)((char*)ws + pl.off_L2);
+    int rc = accbpg_dopt_gram(ctx, stream, H, m, n, ldh, xf, ws, M2);
+    if (rc) return rc;
+    ACCBPG_CUDA(cudaEventRecord(c->ev_fork, s));
+    ACCBPG_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    rc = chol_factor(c, c->side, m, M2, L2, (double*)((char*)ws + pl.off_Wa2), (double*)((char*)ws + pl.off_Wb2),
+                     c->d_slots + 246, d_fx_out);
+    if (rc) return rc;
+    ACCBPG_CUDA(cudaEventRecord(c->ev_join, c->side));
+    rc = accbpg_dopt_gram(ctx, stream, H, m, n, ldh, yg, ws, M1);
+    if (rc) return rc;
+    rc = accbpg_dopt_factor(ctx, stream, m, M1, L1, ws, d_fy_out ? d_fy_out : (c->d_slots + 249));
+    if (rc) return rc;
+    rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, L1, ws, g);
+    if (rc) return rc;
+    ACCBPG_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+    return ACCBPG_OK;
 }
 
 }  // extern "C"

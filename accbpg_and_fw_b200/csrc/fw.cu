@@ -10,6 +10,7 @@
 // here in a compensated (two-sum) accumulator; agreement with the per-iteration LU is ~1e-13 relative over
 // thousands of iterations (tests/test_fw_*.py).
 // Compiled with -fmad=false: the step-size formulas round as in NumPy.
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace accbpg {
@@ -219,33 +220,85 @@ __global__ void __launch_bounds__(256) fw_rank1_kernel(double* __restrict__ Hinv
 }
 
 // the one pass over V:  p_j = u^T v_j ;  w_j <- (w_j - cs p_j^2)/den ;  x_j <- x_j*den (+- t at the chosen column)
-constexpr int FWP_THREADS = 64;
-constexpr int FWP_UNROLL = 16;
+constexpr int FWP_THREADS = 64;      // 2 columns per thread -> 128 columns per CTA
+constexpr int FWP_UNROLL = 16;       // rows in flight per thread (16 x 16 B)
+constexpr int FWP_MAXSPLIT = 4;      // CTAs of one cluster split the rows of V; partials meet in distributed smem
+
+template <bool VEC2>
 __global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(const double* __restrict__ V, int m, int64_t n, int64_t ldv,
                                                               const double* __restrict__ u, double* __restrict__ x,
                                                               double* __restrict__ w, const double* ctrl) {
-    extern __shared__ double us[];
-    if (ld_cg(&ctrl[C_STOP]) != 0.0) return;
-    for (int r = threadIdx.x; r < m; r += blockDim.x) us[r] = __ldcg(u + r);
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ double us[];                         // this CTA's slice of u
+    __shared__ double part[2 * FWP_THREADS];
+    if (ld_cg(&ctrl[C_STOP]) != 0.0) return;               // uniform over the whole grid
+    const unsigned nsplit = cluster.num_blocks(), rank = cluster.block_rank();
+    const int rows_per = (m + nsplit - 1) / nsplit;
+    const int r0 = rank * rows_per;
+    const int r1 = min(m, r0 + rows_per);
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) us[r - r0] = __ldcg(u + r);
     __syncthreads();
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const double* col = V + j;
-    double s = 0.0;
-    int r = 0;
-    for (; r + FWP_UNROLL <= m; r += FWP_UNROLL) {
-        double a[FWP_UNROLL];
+    const int64_t j = ((int64_t)blockIdx.x * FWP_THREADS + threadIdx.x) * 2;
+    double s0 = 0.0, s1 = 0.0;
+    if (j < n) {
+        const double* col = V + j;
+        int r = r0;
+        if (VEC2 && j + 1 < n) {
+            for (; r + FWP_UNROLL <= r1; r += FWP_UNROLL) {
+                double2 a[FWP_UNROLL];
 #pragma unroll
-        for (int q = 0; q < FWP_UNROLL; ++q) a[q] = __ldcs(col + (int64_t)(r + q) * ldv);
+                for (int q = 0; q < FWP_UNROLL; ++q)
+                    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                                 : "=d"(a[q].x), "=d"(a[q].y) : "l"(col + (int64_t)(r + q) * ldv));
 #pragma unroll
-        for (int q = 0; q < FWP_UNROLL; ++q) s += us[r + q] * a[q];
+                for (int q = 0; q < FWP_UNROLL; ++q) {
+                    double uq = us[r - r0 + q];
+                    s0 += uq * a[q].x;
+                    s1 += uq * a[q].y;
+                }
+            }
+            for (; r < r1; ++r) {
+                double2 a;
+                asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                             : "=d"(a.x), "=d"(a.y) : "l"(col + (int64_t)r * ldv));
+                double uq = us[r - r0];
+                s0 += uq * a.x;
+                s1 += uq * a.y;
+            }
+        } else {
+            const bool two = (j + 1 < n);
+            for (; r < r1; ++r) {
+                double uq = us[r - r0];
+                s0 += uq * __ldcs(col + (int64_t)r * ldv);
+                if (two) s1 += uq * __ldcs(col + (int64_t)r * ldv + 1);
+            }
+        }
     }
-    for (; r < m; ++r) s += us[r] * __ldcs(col + (int64_t)r * ldv);
-    const double cs = ld_cg(&ctrl[C_CS]), den = ld_cg(&ctrl[C_DEN]);
-    w[j] = (w[j] - cs * (s * s)) / den;
-    double xn = x[j] * den;
-    if (j == (int64_t)ld_cg(&ctrl[C_IDX])) xn = xn + ld_cg(&ctrl[C_TSIGN]);
-    x[j] = xn;
+    part[2 * threadIdx.x] = s0;
+    part[2 * threadIdx.x + 1] = s1;
+    cluster.sync();
+    if (rank == 0 && j < n) {
+        for (unsigned q = 1; q < nsplit; ++q) {             // fixed order: row chunks 0, 1, 2, ...
+            const double* rp = cluster.map_shared_rank(part, q);
+            s0 += rp[2 * threadIdx.x];
+            s1 += rp[2 * threadIdx.x + 1];
+        }
+        const double cs = ld_cg(&ctrl[C_CS]), den = ld_cg(&ctrl[C_DEN]);
+        const int64_t idx = (int64_t)ld_cg(&ctrl[C_IDX]);
+        const double tsign = ld_cg(&ctrl[C_TSIGN]);
+        w[j] = (w[j] - cs * (s0 * s0)) / den;
+        double xn = x[j] * den;
+        if (j == idx) xn = xn + tsign;
+        x[j] = xn;
+        if (j + 1 < n) {
+            w[j + 1] = (w[j + 1] - cs * (s1 * s1)) / den;
+            xn = x[j + 1] * den;
+            if (j + 1 == idx) xn = xn + tsign;
+            x[j + 1] = xn;
+        }
+    }
+    cluster.sync();                                         // remote shared memory must outlive rank 0's reads
 }
 
 // Hinv = Linv^T Linv  (setup only; Linv lower triangular, zero padded, leading dimension mp)
@@ -342,12 +395,29 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
     const int sel_grid = grid_for(c, n, FW_THREADS, 4, 4);
     const int hv_grid = (m + 7) / 8;
     const int r1_grid = grid_for(c, (int64_t)m * m, 256, 2, 8);
-    const int64_t pass_grid = (n + FWP_THREADS - 1) / FWP_THREADS;
+    const int64_t pass_grid = (n + 2 * FWP_THREADS - 1) / (2 * FWP_THREADS);
     if (pass_grid > 2147483647LL) return arg_err("fw_run: n too large");
-    const size_t pass_smem = (size_t)m * sizeof(double);
+    // split the rows over a small cluster when the column blocks alone cannot fill the GPU evenly
+    int nsplit = 1;
+    while (nsplit < FWP_MAXSPLIT && pass_grid * nsplit < (int64_t)c->sm_count * 8 && m / (nsplit * 2) >= 64) nsplit *= 2;
+    const size_t pass_smem = (size_t)((m + nsplit - 1) / nsplit) * sizeof(double);
     if (pass_smem > 200 * 1024) return arg_err("fw_run: m too large for the shared-memory copy of u");
+    const bool pass_vec = ((reinterpret_cast<uintptr_t>(V) & 15u) == 0) && (ldv % 2 == 0);
+    auto pass_fn = pass_vec ? fw_pass_kernel<true> : fw_pass_kernel<false>;
     if (pass_smem > 48 * 1024)
-        ACCBPG_CUDA(cudaFuncSetAttribute(fw_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
+        ACCBPG_CUDA(cudaFuncSetAttribute(pass_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
+    cudaLaunchConfig_t pass_cfg = {};
+    pass_cfg.gridDim = dim3((unsigned)pass_grid, (unsigned)nsplit, 1);
+    pass_cfg.blockDim = dim3(FWP_THREADS, 1, 1);
+    pass_cfg.dynamicSmemBytes = pass_smem;
+    pass_cfg.stream = s;
+    cudaLaunchAttribute pass_attr[1];
+    pass_attr[0].id = cudaLaunchAttributeClusterDimension;
+    pass_attr[0].val.clusterDim.x = 1;
+    pass_attr[0].val.clusterDim.y = (unsigned)nsplit;
+    pass_attr[0].val.clusterDim.z = 1;
+    pass_cfg.attrs = pass_attr;
+    pass_cfg.numAttrs = 1;
     FwDecideParams p;
     p.n = n; p.ldv = ldv; p.V = V; p.x = x; p.w = w; p.m = m; p.away = away; p.eps = eps;
     p.ctrl = ctrl; p.v = v; p.hist_F = hist_F; p.hist_SP = hist_SP; p.hist_SN = hist_SN; p.hist_T = hist_T;
@@ -365,7 +435,7 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
         ACCBPG_LAUNCHED("fw_rank1_kernel");
         {
             ProfScope ps(P_FW_PASS, s);
-            fw_pass_kernel<<<(unsigned)pass_grid, FWP_THREADS, pass_smem, s>>>(V, m, n, ldv, u, x, w, ctrl);
+            ACCBPG_CUDA(cudaLaunchKernelEx(&pass_cfg, pass_fn, V, m, n, ldv, (const double*)u, x, w, (const double*)ctrl));
         }
         ACCBPG_LAUNCHED("fw_pass_kernel");
     }

@@ -473,6 +473,9 @@ int accbpg_ctx_create(void** out) {
     ACCBPG_CUDA(cudaMemset(c->d_counter, 0, 256));
     ACCBPG_CUDA(cudaMallocHost(&c->h_slots, kSlots * sizeof(double)));
     ACCBPG_CUDA(cudaMallocHost(&c->h_status, 64));
+    ACCBPG_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    ACCBPG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    ACCBPG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     int per_sm = 0;
     ACCBPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, burg_simplex_kernel, kBurgThreads, 0));
     if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "burg_simplex_kernel cannot be made resident"); return ACCBPG_E_CUDA; }
@@ -490,6 +493,7 @@ int accbpg_ctx_destroy(void* ctx) {
     cudaFree(c->d_slots); cudaFree(c->d_status); cudaFree(c->d_partials);
     cudaFree(c->d_ipartials); cudaFree(c->d_counter);
     cudaFreeHost(c->h_slots); cudaFreeHost(c->h_status);
+    cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
     delete c;
     return ACCBPG_OK;
 }

@@ -70,6 +70,17 @@ class _Loop:
         self.f._enqueue(x, 2, slot, g)
         return g
 
+    def enq_f_and_grad(self, x, slot_x, y, flag_y, slot_y):
+        """f(x) -> slot_x and (f(y), grad f(y)) -> slot_y: the two evaluations an accelerated iteration starts
+        with (algorithms.py:135+148, :231+245, :347+371).  Objectives that can overlap the two chains do so."""
+        g = self.rt.empty(self.n)
+        if hasattr(self.f, "_enqueue_pair"):
+            self.f._enqueue_pair(x, slot_x, y, flag_y, slot_y, g)
+        else:
+            self.f._enqueue(x, 0, slot_x, None)
+            self.f._enqueue(y, flag_y, slot_y, g)
+        return g
+
     def enq_psi(self, x):
         if self.h.has_psi:
             self.h._enq_extra_psi(x, self.rt.S_PSI)
@@ -85,7 +96,7 @@ class _Loop:
         self.h._enq_divergence(x, y, slot)
 
     def fetch(self):
-        return self.rt.read(0, 6)
+        return self.rt.read(0, 7)          # S_F .. S_PSI and S_AUX0 in one pinned read
 
     def psi(self, vals):
         return vals[self.rt.S_PSI] if self.h.has_psi else 0
@@ -165,10 +176,8 @@ def ABPG(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=False,
     theta = 1.0
     kk = 0
     for k in range(maxitrs):
-        lp.enq_f(x, rt.S_F)
-        lp.enq_psi(x)
-        vals = lp.fetch()
-        F[k] = vals[rt.S_F] + lp.psi(vals)
+        # F[k] = f(x_k) is only recorded (and used by restart rule 'f' at the end of the iteration), so it is
+        # evaluated together with the gradient at y_k and fetched with the divergences: one host sync per iteration.
         T[k] = lp.now()
         z_1, x_1 = z, x
         if theta_eq and kk > 0:
@@ -176,13 +185,14 @@ def ABPG(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=False,
         else:
             theta = gamma / (kk + gamma)
         y = lp.combo(1 - theta, x, theta, z_1)
-        g = rt.empty(lp.n)
-        f._enqueue(y, 1, rt.S_F2, g)
+        g = lp.enq_f_and_grad(x, rt.S_F, y, 1, rt.S_F2)
+        lp.enq_psi(x)
         z = lp.div_prox(z_1, g, theta ** (gamma - 1) * L)
         x = lp.combo(1 - theta, x, theta, z)
         lp.enq_div(x, y, rt.S_DXY)
         lp.enq_div(z, z_1, rt.S_DZZ)
         vals = lp.fetch()
+        F[k] = vals[rt.S_F] + lp.psi(vals)
         dxy, dzz = vals[rt.S_DXY], vals[rt.S_DZZ]
         Gdr = dxy / dzz / theta ** gamma
         G[k] = Gdr
@@ -218,19 +228,20 @@ def ABPG_expo(f, h, L, x0, gamma0, maxitrs, epsilon=1e-14, delta=0.2,
     z = lp.x0.clone()
     theta = 1.0
     kk = 0
+    fx_known = None      # f(x_k) when the previous iteration's line search already evaluated it at this very vector
     for k in range(maxitrs):
-        lp.enq_f(x, rt.S_F)
-        lp.enq_psi(x)
-        vals = lp.fetch()
-        F[k] = vals[rt.S_F] + lp.psi(vals)
         T[k] = lp.now()
+        lp.enq_psi(x)
         z_1, x_1 = z, x
         if theta_eq and kk > 0:
             theta = solve_theta(theta, gamma)
         else:
             theta = gamma / (kk + gamma)
         y = lp.combo(1 - theta, x_1, theta, z_1)
-        g = lp.enq_fg(y, rt.S_F2)
+        if fx_known is None:
+            g = lp.enq_f_and_grad(x_1, rt.S_AUX0, y, 2, rt.S_F2)     # F[k] = f(x_k) rides along with func_grad(y_k)
+        else:
+            g = lp.enq_fg(y, rt.S_F2)
         fy = None
         again = True
         while again:
@@ -244,6 +255,7 @@ def ABPG_expo(f, h, L, x0, gamma0, maxitrs, epsilon=1e-14, delta=0.2,
             vals = lp.fetch()
             if fy is None:
                 fy = vals[rt.S_F2]
+                F[k] = (vals[rt.S_AUX0] if fx_known is None else fx_known) + lp.psi(vals)
             dxy, dzz = vals[rt.S_DXY], vals[rt.S_DZZ]
             Gdr = dxy / dzz / theta ** gamma
             if checkdiv:
@@ -254,6 +266,7 @@ def ABPG_expo(f, h, L, x0, gamma0, maxitrs, epsilon=1e-14, delta=0.2,
                 gamma = max(gamma - delta, 1)
             else:
                 again = False
+        fx_known = None if checkdiv else vals[rt.S_F]       # f at the accepted x: next iteration's F[k+1]
         G[k] = Gdr
         Gamma[k] = gamma
         if verbose and k % verbskip == 0:
@@ -290,17 +303,16 @@ def ABPG_gain(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, G0=1,
     sumlogG = gamma * np.log(G)
     theta = 1.0
     kk = 0
+    fx_known = None      # f(x_k) when the previous iteration's line search already evaluated it at this very vector
     for k in range(maxitrs):
-        lp.enq_f(x, rt.S_F)
-        lp.enq_psi(x)
-        vals = lp.fetch()
-        F[k] = vals[rt.S_F] + lp.psi(vals)
         T[k] = lp.now()
+        lp.enq_psi(x)
         z_1, x_1 = z, x
         G_1 = G
         theta_1 = theta
         G = G / ls_dec
         again = True
+        first = True
         while again:
             if kk > 0:
                 if theta_eq:
@@ -309,7 +321,10 @@ def ABPG_gain(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, G0=1,
                     alpha = G / G_1
                     theta = theta_1 * ((1 + alpha * (gamma - 1)) / (gamma * alpha + theta_1))
             y = lp.combo(1 - theta, x_1, theta, z_1)
-            g = lp.enq_fg(y, rt.S_F2)
+            if first and fx_known is None:
+                g = lp.enq_f_and_grad(x_1, rt.S_AUX0, y, 2, rt.S_F2)     # F[k] = f(x_k) rides along
+            else:
+                g = lp.enq_fg(y, rt.S_F2)
             z = lp.div_prox(z_1, g, theta ** (gamma - 1) * G * L)
             x = lp.combo(1 - theta, x_1, theta, z)
             lp.enq_div(x, y, rt.S_DXY)
@@ -320,6 +335,9 @@ def ABPG_gain(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, G0=1,
                 lp.enq_f(x, rt.S_F)
                 lp.enq_dot_diff(g, x, y)
             vals = lp.fetch()
+            if first:
+                F[k] = (vals[rt.S_AUX0] if fx_known is None else fx_known) + lp.psi(vals)
+                first = False
             fy = vals[rt.S_F2]
             dxy, dzz = vals[rt.S_DXY], vals[rt.S_DZZ]
             if dzz < epsilon:
@@ -331,6 +349,7 @@ def ABPG_gain(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, G0=1,
                 again = (vals[rt.S_F] > fy + vals[rt.S_DOT] + theta ** gamma * G * L * dzz)   # algorithms.py:387
             if again:
                 G = G * ls_inc
+        fx_known = None if checkdiv else vals[rt.S_F]       # f at the accepted x: next iteration's F[k+1]
         Gain[k] = G
         Gdiv[k] = Gdr       # stale (or unbound on the very first trip) after the break above, as in the reference
         sumlogG += np.log(G)
@@ -367,10 +386,6 @@ def ABDA(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=True,
     gavg = rt.empty(lp.n).zero_()
     csum = 0
     for k in range(maxitrs):
-        lp.enq_f(x, rt.S_F)
-        lp.enq_psi(x)
-        vals = lp.fetch()
-        F[k] = vals[rt.S_F] + lp.psi(vals)
         T[k] = lp.now()
         z_1, x_1 = z, x
         if theta_eq and kk > 0:
@@ -378,8 +393,8 @@ def ABDA(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=True,
         else:
             theta = gamma / (kk + gamma)
         y = lp.combo(1 - theta, x_1, theta, z_1)
-        g = rt.empty(lp.n)
-        f._enqueue(y, 1, rt.S_F2, g)
+        g = lp.enq_f_and_grad(x_1, rt.S_F, y, 1, rt.S_F2)      # F[k] = f(x_k) rides along with the gradient at y_k
+        lp.enq_psi(x_1)
         wgt = theta ** (1 - gamma)
         gavg = lp.combo(1.0, gavg, wgt, g)            # gavg + theta^(1-gamma) * g   (1.0*gavg is exact)
         csum = csum + wgt
@@ -391,6 +406,7 @@ def ABDA(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=True,
         lp.enq_div(x, y, rt.S_DXY)
         lp.enq_div(z, z_1, rt.S_DZZ)
         vals = lp.fetch()
+        F[k] = vals[rt.S_F] + lp.psi(vals)
         dxy, dzz = vals[rt.S_DXY], vals[rt.S_DZZ]
         Gdr = dxy / dzz / theta ** gamma
         G[k] = Gdr

@@ -61,6 +61,19 @@ class DOptimalObj(RSmoothFunction):
             self._M = torch.empty(self.m, self.m, dtype=torch.float64, device=self.rt.device)
             self._L = torch.empty(self.m, self.m, dtype=torch.float64, device=self.rt.device)
 
+    def _enqueue_pair(self, xd, slot_x, yd, flag_y, slot_y, g):
+        """f(x) -> slot_x and (f(y), grad f(y)) -> (slot_y, g): what an accelerated iteration starts with.
+        On one GPU the value-only Cholesky chain overlaps the gradient chain (accbpg_dopt_pair)."""
+        rt = self.rt
+        if self.shard is not None and self.shard.world > 1:
+            self._enqueue(xd, 0, slot_x, None)
+            self._enqueue(yd, flag_y, slot_y, g)
+            return
+        H = self._Hd
+        nat.check(lib.accbpg_dopt_pair(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
+                                       xd.data_ptr(), yd.data_ptr(), flag_y, self._ws.data_ptr(), rt.slot(slot_x),
+                                       rt.slot(slot_y), g.data_ptr()))
+
     def _enqueue(self, xd, flag, slot, g):
         rt = self.rt
         H = self._Hd

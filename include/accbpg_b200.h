@@ -172,6 +172,13 @@ int accbpg_dopt_grad(void* ctx, void* stream, const double* d_H, int m, int64_t 
 int accbpg_dopt_func_grad(void* ctx, void* stream, const double* d_H, int m, int64_t n, int64_t ldh,
                           const double* d_x, int flag, void* d_ws, double* d_f_out, double* d_g);
 
+/* f(xf) and (f(yg), grad f(yg)) in one call (flag_y = 1 or 2): what one accelerated iteration needs (F[k] = f(x_k)
+ * and the gradient at y_k, accbpg/algorithms.py:135,148 / :231,245 / :347,371).  The value-only Cholesky overlaps the
+ * gradient chain on the context's side stream; results and status bits are identical to two separate calls. */
+int accbpg_dopt_pair(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
+                     const double* d_xf, const double* d_yg, int flag_y, void* d_ws, double* d_fx_out,
+                     double* d_fy_out, double* d_g);
+
 /* ---- Poisson / KL regression objectives (accbpg/functions.py:102-120, :140-158).  A is m x n_local. */
 #define ACCBPG_LINREG_POISSON 0   /* f = sum b log(b/Ax) + Ax - b ; r = 1 - b/Ax   */
 #define ACCBPG_LINREG_KL      1   /* f = sum Ax log(Ax/b) - Ax + b ; r = log(Ax/b) */
