@@ -483,4 +483,36 @@ int accbpg_dopt_pair(void* ctx, void* stream, const double* H, int m, int64_t n,
     return ACCBPG_OK;
 }
 
+// Same, starting from Gram matrices the caller already holds (M is linear in x, so the drivers can form
+// M((1-t)x + t z) = (1-t)M(x) + t M(z) instead of running another SYRK).  Mx may be NULL (gradient side only).
+int accbpg_dopt_pair_from_gram(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh,
+                               const double* Mx, const double* My, int flag_y, void* ws, double* d_fx_out,
+                               double* d_fy_out, double* g) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !ws || !My) return arg_err("dopt_pair_from_gram: NULL pointer");
+    if (flag_y < 0 || flag_y > 2 || (flag_y >= 1 && !g)) return arg_err("dopt_pair_from_gram: flag_y / gradient buffer");
+    if (Mx && !d_fx_out) return arg_err("dopt_pair_from_gram: d_fx_out is NULL");
+    DoptPlan pl = make_plan(m, n, c->sm_count);
+    double* L1 = (double*)((char*)ws + pl.off_L);
+    double* L2 = (double*)((char*)ws + pl.off_L2);
+    int rc;
+    if (Mx) {
+        ACCBPG_CUDA(cudaEventRecord(c->ev_fork, s));
+        ACCBPG_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        rc = chol_factor(c, c->side, m, Mx, L2, (double*)((char*)ws + pl.off_Wa2), (double*)((char*)ws + pl.off_Wb2),
+                         c->d_slots + 246, d_fx_out);
+        if (rc) return rc;
+        ACCBPG_CUDA(cudaEventRecord(c->ev_join, c->side));
+    }
+    rc = accbpg_dopt_factor(ctx, stream, m, My, L1, ws, d_fy_out ? d_fy_out : (c->d_slots + 249));
+    if (rc) return rc;
+    if (flag_y >= 1) {
+        rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, L1, ws, g);
+        if (rc) return rc;
+    }
+    if (Mx) ACCBPG_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+    return ACCBPG_OK;
+}
+
 }  // extern "C"

@@ -13,6 +13,7 @@ import time
 import numpy as np
 
 from . import _native as nat
+from . import config
 from .runtime import is_host, like_input
 
 lib = nat.lib
@@ -41,6 +42,44 @@ class _Loop:
         self.x0 = self.rt.to_device(x0).clone()
         self.n = self.x0.numel()
         self.t0 = time.time()
+        # carry the objective's linear image (M(x) for D-opt, A x for Poisson / KL) along with the iterates
+        self.lin = bool(config.linear_images and getattr(f, "_lin_capable", False))
+        self.reanchor = max(int(config.reanchor_every), 1)
+
+    # ---- linear images (all no-ops returning None when the switch is off) -----------------------------------
+    def img(self, x):
+        return self.f._img_compute(x) if self.lin else None
+
+    def img_combo(self, a, Ia, b, Ib):
+        return self.f._img_axpby(a, Ia, b, Ib) if self.lin else None
+
+    def img_refresh(self, k, x, Ix):
+        """Every `reanchor_every` iterations the image of x is re-formed from x itself."""
+        if self.lin and (k + 1) % self.reanchor == 0:
+            return self.f._img_compute(x)
+        return Ix
+
+    def enq_f_img(self, x, Ix, slot):
+        """f(x) -> slot, from the image when it is carried."""
+        if self.lin:
+            self.f._enqueue_img_pair(None, 0, Ix, 0, slot, None)
+        else:
+            self.f._enqueue(x, 0, slot, None)
+
+    def enq_start(self, x, Ix, slot_x, y, Iy, flag_y, slot_y):
+        """What an accelerated iteration starts with: f(x) -> slot_x (skipped when x is None) and
+        (f(y), grad f(y)) -> (slot_y, g).  Returns g."""
+        g = self.rt.empty(self.n)
+        if self.lin:
+            self.f._enqueue_img_pair(Ix if x is not None else None, slot_x, Iy, flag_y, slot_y, g)
+        elif x is None:
+            self.f._enqueue(y, flag_y, slot_y, g)
+        elif hasattr(self.f, "_enqueue_pair"):
+            self.f._enqueue_pair(x, slot_x, y, flag_y, slot_y, g)
+        else:
+            self.f._enqueue(x, 0, slot_x, None)
+            self.f._enqueue(y, flag_y, slot_y, g)
+        return g
 
     # vectors
     def combo(self, a, x, b, y):
@@ -173,6 +212,8 @@ def ABPG(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=False,
     T = np.zeros(maxitrs)
     x = lp.x0
     z = lp.x0.clone()
+    Ix = lp.img(x)           # linear image of x (None when config.linear_images is off); z starts at x
+    Iz = Ix
     theta = 1.0
     kk = 0
     for k in range(maxitrs):
@@ -180,15 +221,19 @@ def ABPG(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=False,
         # evaluated together with the gradient at y_k and fetched with the divergences: one host sync per iteration.
         T[k] = lp.now()
         z_1, x_1 = z, x
+        Iz_1, Ix_1 = Iz, Ix
         if theta_eq and kk > 0:
             theta = solve_theta(theta, gamma)
         else:
             theta = gamma / (kk + gamma)
         y = lp.combo(1 - theta, x, theta, z_1)
-        g = lp.enq_f_and_grad(x, rt.S_F, y, 1, rt.S_F2)
+        Iy = lp.img_combo(1 - theta, Ix_1, theta, Iz_1)
+        g = lp.enq_start(x, Ix_1, rt.S_F, y, Iy, 1, rt.S_F2)
         lp.enq_psi(x)
         z = lp.div_prox(z_1, g, theta ** (gamma - 1) * L)
+        Iz = lp.img(z)
         x = lp.combo(1 - theta, x, theta, z)
+        Ix = lp.img_refresh(k, x, lp.img_combo(1 - theta, Ix_1, theta, Iz))
         lp.enq_div(x, y, rt.S_DXY)
         lp.enq_div(z, z_1, rt.S_DZZ)
         vals = lp.fetch()
@@ -205,6 +250,7 @@ def ABPG(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=False,
                 theta = 1.0
                 kk = 0
                 z = x
+                Iz = Ix
         if dzz < epsilon:
             break
     return lp.result(x), F[0:k + 1], G[0:k + 1], T[0:k + 1]
@@ -226,6 +272,8 @@ def ABPG_expo(f, h, L, x0, gamma0, maxitrs, epsilon=1e-14, delta=0.2,
     gamma = gamma0
     x = lp.x0
     z = lp.x0.clone()
+    Ix = lp.img(x)           # linear image of x (None when config.linear_images is off); z starts at x
+    Iz = Ix
     theta = 1.0
     kk = 0
     fx_known = None      # f(x_k) when the previous iteration's line search already evaluated it at this very vector
@@ -237,20 +285,22 @@ def ABPG_expo(f, h, L, x0, gamma0, maxitrs, epsilon=1e-14, delta=0.2,
             theta = solve_theta(theta, gamma)
         else:
             theta = gamma / (kk + gamma)
+        Iz_1, Ix_1 = Iz, Ix
         y = lp.combo(1 - theta, x_1, theta, z_1)
-        if fx_known is None:
-            g = lp.enq_f_and_grad(x_1, rt.S_AUX0, y, 2, rt.S_F2)     # F[k] = f(x_k) rides along with func_grad(y_k)
-        else:
-            g = lp.enq_fg(y, rt.S_F2)
+        Iy = lp.img_combo(1 - theta, Ix_1, theta, Iz_1)
+        # F[k] = f(x_k) rides along with func_grad(y_k) unless the last line search already produced it
+        g = lp.enq_start(x_1 if fx_known is None else None, Ix_1, rt.S_AUX0, y, Iy, 2, rt.S_F2)
         fy = None
         again = True
         while again:
             z = lp.div_prox(z_1, g, theta ** (gamma - 1) * L)
+            Iz = lp.img(z)
             x = lp.combo(1 - theta, x_1, theta, z)
+            Ix = lp.img_combo(1 - theta, Ix_1, theta, Iz)
             lp.enq_div(x, y, rt.S_DXY)
             lp.enq_div(z, z_1, rt.S_DZZ)
             if not checkdiv:
-                lp.enq_f(x, rt.S_F)
+                lp.enq_f_img(x, Ix, rt.S_F)
                 lp.enq_dot_diff(g, x, y)
             vals = lp.fetch()
             if fy is None:
@@ -267,6 +317,7 @@ def ABPG_expo(f, h, L, x0, gamma0, maxitrs, epsilon=1e-14, delta=0.2,
             else:
                 again = False
         fx_known = None if checkdiv else vals[rt.S_F]       # f at the accepted x: next iteration's F[k+1]
+        Ix = lp.img_refresh(k, x, Ix)
         G[k] = Gdr
         Gamma[k] = gamma
         if verbose and k % verbskip == 0:
@@ -278,6 +329,7 @@ def ABPG_expo(f, h, L, x0, gamma0, maxitrs, epsilon=1e-14, delta=0.2,
                 theta = 1.0
                 kk = 0
                 z = x
+                Iz = Ix
         if dzz < epsilon:
             break
     return lp.result(x), F[0:k + 1], Gamma[0:k + 1], G[0:k + 1], T[0:k + 1]
@@ -299,6 +351,8 @@ def ABPG_gain(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, G0=1,
     T = np.zeros(maxitrs)
     x = lp.x0
     z = lp.x0.clone()
+    Ix = lp.img(x)           # linear image of x (None when config.linear_images is off); z starts at x
+    Iz = Ix
     G = G0
     sumlogG = gamma * np.log(G)
     theta = 1.0
@@ -308,6 +362,7 @@ def ABPG_gain(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, G0=1,
         T[k] = lp.now()
         lp.enq_psi(x)
         z_1, x_1 = z, x
+        Iz_1, Ix_1 = Iz, Ix
         G_1 = G
         theta_1 = theta
         G = G / ls_dec
@@ -321,18 +376,19 @@ def ABPG_gain(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, G0=1,
                     alpha = G / G_1
                     theta = theta_1 * ((1 + alpha * (gamma - 1)) / (gamma * alpha + theta_1))
             y = lp.combo(1 - theta, x_1, theta, z_1)
-            if first and fx_known is None:
-                g = lp.enq_f_and_grad(x_1, rt.S_AUX0, y, 2, rt.S_F2)     # F[k] = f(x_k) rides along
-            else:
-                g = lp.enq_fg(y, rt.S_F2)
+            Iy = lp.img_combo(1 - theta, Ix_1, theta, Iz_1)
+            # F[k] = f(x_k) rides along with the first func_grad(y) unless the last line search already produced it
+            g = lp.enq_start(x_1 if (first and fx_known is None) else None, Ix_1, rt.S_AUX0, y, Iy, 2, rt.S_F2)
             z = lp.div_prox(z_1, g, theta ** (gamma - 1) * G * L)
+            Iz = lp.img(z)
             x = lp.combo(1 - theta, x_1, theta, z)
+            Ix = lp.img_combo(1 - theta, Ix_1, theta, Iz)
             lp.enq_div(x, y, rt.S_DXY)
             lp.enq_div(z, z_1, rt.S_DZZ)
             if not checkdiv:
                 # the reference evaluates f(x) only when dzz >= epsilon; doing it unconditionally here saves a
                 # second round trip per trip and does not change any recorded value
-                lp.enq_f(x, rt.S_F)
+                lp.enq_f_img(x, Ix, rt.S_F)
                 lp.enq_dot_diff(g, x, y)
             vals = lp.fetch()
             if first:
@@ -350,6 +406,7 @@ def ABPG_gain(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, G0=1,
             if again:
                 G = G * ls_inc
         fx_known = None if checkdiv else vals[rt.S_F]       # f at the accepted x: next iteration's F[k+1]
+        Ix = lp.img_refresh(k, x, Ix)
         Gain[k] = G
         Gdiv[k] = Gdr       # stale (or unbound on the very first trip) after the break above, as in the reference
         sumlogG += np.log(G)
@@ -363,6 +420,7 @@ def ABPG_gain(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, G0=1,
                 theta = 1.0
                 kk = 0
                 z = x
+                Iz = Ix
         if dzz < epsilon:
             break
     return lp.result(x), F[0:k + 1], Gain[0:k + 1], Gdiv[0:k + 1], Gavg[0:k + 1], T[0:k + 1]
@@ -381,6 +439,8 @@ def ABDA(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=True,
     T = np.zeros(maxitrs)
     x = lp.x0
     z = lp.x0.clone()
+    Ix = lp.img(x)           # linear image of x (None when config.linear_images is off); z starts at x
+    Iz = Ix
     theta = 1.0
     kk = 0
     gavg = rt.empty(lp.n).zero_()
@@ -392,8 +452,10 @@ def ABDA(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=True,
             theta = solve_theta(theta, gamma)
         else:
             theta = gamma / (kk + gamma)
+        Iz_1, Ix_1 = Iz, Ix
         y = lp.combo(1 - theta, x_1, theta, z_1)
-        g = lp.enq_f_and_grad(x_1, rt.S_F, y, 1, rt.S_F2)      # F[k] = f(x_k) rides along with the gradient at y_k
+        Iy = lp.img_combo(1 - theta, Ix_1, theta, Iz_1)
+        g = lp.enq_start(x_1, Ix_1, rt.S_F, y, Iy, 1, rt.S_F2)      # F[k] = f(x_k) rides along with the gradient at y_k
         lp.enq_psi(x_1)
         wgt = theta ** (1 - gamma)
         gavg = lp.combo(1.0, gavg, wgt, g)            # gavg + theta^(1-gamma) * g   (1.0*gavg is exact)
@@ -402,7 +464,9 @@ def ABDA(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=True,
         gq = rt.empty(lp.n)
         nat.check(lib.accbpg_vec_divide(rt.ctx, rt.stream, lp.n, gavg.data_ptr(), float(csum), gq.data_ptr()))
         z = lp.prox(gq, L / csum)
+        Iz = lp.img(z)
         x = lp.combo(1 - theta, x_1, theta, z)
+        Ix = lp.img_refresh(k, x, lp.img_combo(1 - theta, Ix_1, theta, Iz))
         lp.enq_div(x, y, rt.S_DXY)
         lp.enq_div(z, z_1, rt.S_DZZ)
         vals = lp.fetch()

@@ -61,6 +61,36 @@ class DOptimalObj(RSmoothFunction):
             self._M = torch.empty(self.m, self.m, dtype=torch.float64, device=self.rt.device)
             self._L = torch.empty(self.m, self.m, dtype=torch.float64, device=self.rt.device)
 
+    # ---- linear image M(x) = H diag(x) H^T (config.linear_images) ------------------------------------------
+    _lin_capable = True
+
+    def _img_compute(self, xd):
+        """M(x) as a new m x m device tensor (K1 SYRK; all-reduced when H is column-sharded)."""
+        rt = self.rt
+        H = self._Hd
+        M = torch.empty(self.m, self.m, dtype=torch.float64, device=rt.device)
+        nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
+                                       xd.data_ptr(), self._ws.data_ptr(), M.data_ptr()))
+        if self.shard is not None and self.shard.world > 1:
+            self.shard.sum_(M)
+        return M
+
+    def _img_axpby(self, a, Ia, b, Ib):
+        rt = self.rt
+        out = torch.empty_like(Ia)
+        nat.check(lib.accbpg_vec_axpby(rt.ctx, rt.stream, Ia.numel(), float(a), Ia.data_ptr(), float(b),
+                                       Ib.data_ptr(), out.data_ptr()))
+        return out
+
+    def _enqueue_img_pair(self, Ix, slot_x, Iy, flag_y, slot_y, g):
+        """f from M(x) -> slot_x (skipped when Ix is None) and (f, grad f) from M(y) -> (slot_y, g): K2-K4 only."""
+        rt = self.rt
+        H = self._Hd
+        nat.check(lib.accbpg_dopt_pair_from_gram(
+            rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
+            Ix.data_ptr() if Ix is not None else None, Iy.data_ptr(), flag_y, self._ws.data_ptr(),
+            rt.slot(slot_x) if Ix is not None else None, rt.slot(slot_y), g.data_ptr() if g is not None else None))
+
     def _enqueue_pair(self, xd, slot_x, yd, flag_y, slot_y, g):
         """f(x) -> slot_x and (f(y), grad f(y)) -> (slot_y, g): what an accelerated iteration starts with.
         On one GPU the value-only Cholesky chain overlaps the gradient chain (accbpg_dopt_pair)."""
@@ -110,6 +140,41 @@ class _LinearInverse(RSmoothFunction):
                                      lib.accbpg_linreg_workspace_bytes(self.m, self.n_local))
         self._Ax = self.rt.empty(self.m)
         self._r = self.rt.empty(self.m)
+
+    # ---- linear image A x (config.linear_images) -------------------------------------------------------------
+    _lin_capable = True
+
+    def _img_compute(self, xd):
+        """A x as a new m-vector (K5; all-reduced when A is column-sharded)."""
+        rt = self.rt
+        A = self._Ad
+        Ax = rt.empty(self.m)
+        nat.check(lib.accbpg_linreg_matvec(rt.ctx, rt.stream, A.data_ptr(), self.m, self.n_local, A.stride(0),
+                                           xd.data_ptr(), self._ws.data_ptr(), Ax.data_ptr()))
+        if self.shard is not None and self.shard.world > 1:
+            self.shard.sum_(Ax)
+        return Ax
+
+    def _img_axpby(self, a, Ia, b, Ib):
+        rt = self.rt
+        out = torch.empty_like(Ia)
+        nat.check(lib.accbpg_vec_axpby(rt.ctx, rt.stream, Ia.numel(), float(a), Ia.data_ptr(), float(b),
+                                       Ib.data_ptr(), out.data_ptr()))
+        return out
+
+    def _enqueue_img_pair(self, Ix, slot_x, Iy, flag_y, slot_y, g):
+        """f from A x -> slot_x (skipped when Ix is None); (f, grad f) from A y -> (slot_y, g): K7 (+ K6) only."""
+        rt = self.rt
+        A = self._Ad
+        if Ix is not None:
+            nat.check(lib.accbpg_linreg_value_resid(rt.ctx, rt.stream, self._kind, self.m, Ix.data_ptr(),
+                                                    self._bd.data_ptr(), rt.slot(slot_x), None))
+        nat.check(lib.accbpg_linreg_value_resid(rt.ctx, rt.stream, self._kind, self.m, Iy.data_ptr(),
+                                                self._bd.data_ptr(), rt.slot(slot_y),
+                                                self._r.data_ptr() if flag_y >= 1 else None))
+        if flag_y >= 1:
+            nat.check(lib.accbpg_linreg_rmatvec(rt.ctx, rt.stream, A.data_ptr(), self.m, self.n_local, A.stride(0),
+                                                self._r.data_ptr(), self._ws.data_ptr(), g.data_ptr()))
 
     def _enqueue(self, xd, flag, slot, g):
         rt = self.rt

@@ -179,6 +179,13 @@ int accbpg_dopt_pair(void* ctx, void* stream, const double* d_H, int m, int64_t 
                      const double* d_xf, const double* d_yg, int flag_y, void* d_ws, double* d_fx_out,
                      double* d_fy_out, double* d_g);
 
+/* Same evaluation from Gram matrices the caller already holds (M(x) is linear in x: the drivers form
+ * M((1-t)x + t z) = (1-t)M(x) + t M(z) with accbpg_vec_axpby instead of another SYRK).  d_Mx may be NULL
+ * (then only (f(y), grad f(y)) is produced); flag_y 0 / 1 / 2. */
+int accbpg_dopt_pair_from_gram(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
+                               const double* d_Mx, const double* d_My, int flag_y, void* d_ws, double* d_fx_out,
+                               double* d_fy_out, double* d_g);
+
 /* ---- Poisson / KL regression objectives (accbpg/functions.py:102-120, :140-158).  A is m x n_local. */
 #define ACCBPG_LINREG_POISSON 0   /* f = sum b log(b/Ax) + Ax - b ; r = 1 - b/Ax   */
 #define ACCBPG_LINREG_KL      1   /* f = sum Ax log(Ax/b) - Ax + b ; r = log(Ax/b) */

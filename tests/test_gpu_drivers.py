@@ -173,3 +173,30 @@ def test_midsize_trajectory_vs_oracle(acc):
     a = acc.ABPG_gain(f, h, L, x0, gamma=2, maxitrs=15, verbose=False)
     b = orc.ABPG_gain(fo, ho, L, x0, gamma=2, maxitrs=15)
     assert ferr(a[1], b[1]) <= FTOL and np.array_equal(a[2], b[2])
+
+
+def test_direct_evaluation_mode_matches_too(acc, dopt, golden_traj):
+    """config.linear_images = False: every f / grad f is evaluated from scratch (no carried Gram matrix / A x)."""
+    from accbpg_and_fw_b200 import config
+    f, h, L, x0 = dopt
+    old = config.linear_images
+    try:
+        for mode in (False, True):
+            config.linear_images = mode
+            x, F, G, T = acc.ABPG(f, h, L, x0, gamma=2, maxitrs=1000, theta_eq=False, verbose=False)
+            assert ferr(F, golden_traj["abpg_F"]) <= FTOL
+            x, F, Gain, Gdiv, Gavg, T = acc.ABPG_gain(f, h, L, x0, gamma=2, maxitrs=300, G0=0.1, verbose=False)
+            assert ferr(F, golden_traj["gain_F"][:300]) <= FTOL
+            assert first_fork(Gain, golden_traj["gain_Gain"][:300]) >= 290
+            x, F, G, T = acc.ABDA(f, h, L, x0, gamma=2, maxitrs=300, verbose=False)
+            assert ferr(F, golden_traj["abda_F"][:300]) <= FTOL
+            x, F, Gamma, G, T = acc.ABPG_expo(f, h, L, x0, gamma0=3, maxitrs=300, verbose=False)
+            assert ferr(F, golden_traj["expo_F"][:300]) <= FTOL
+            x, F, G, T = acc.ABPG(f, h, L, x0, gamma=2, maxitrs=400, theta_eq=True, restart=True, verbose=False)
+            assert ferr(F, golden_traj["abpg_rs_F"]) <= FTOL
+            fk = acc.KLdivRegression(golden_traj["kls_A"], golden_traj["kls_b"])
+            hk = acc.ShannonEntropySimplex()
+            out = acc.ABPG_gain(fk, hk, 1.0, np.ones(400) / 400, gamma=2.0, maxitrs=120, verbose=False)
+            assert ferr(out[1], golden_traj["kls_gain_F"][:120]) <= FTOL
+    finally:
+        config.linear_images = old
