@@ -130,8 +130,7 @@ __device__ __forceinline__ void mma_nn_slab(double (&acc)[MI][NI][2], const doub
 #endif  // __CUDACC__
 
 // defined in chol.cu (host side, stream ordered)
-int chol_factor(Ctx* c, cudaStream_t s, int m, const double* M, double* L, double* Wa, double* Wb, double* acc,
-                double* d_out);
-int tri_inverse(Ctx* c, cudaStream_t s, int m, int mp, const double* L, double* Linv, double* T);
+int chol_factor_inv(Ctx* c, cudaStream_t s, int m, int mp, const double* M, double* L, int want_inv, double* Linv,
+                    double* W, double* Y, double* acc, double* d_out);
 
 }  // namespace accbpg

@@ -3,8 +3,8 @@
 //
 //   K1  gram     M = H diag(x) H^T     FP64 DMMA (mma.sync m8n8k4) SYRK, lower 128x128 tiles, split over the
 //                                      n (column) dimension, partials reduced in a fixed order (deterministic)
-//   K2  factor   M = L L^T             chol.cu: right-looking blocked Cholesky, -log det from the pivots
-//   K3  trinv    Linv = L^{-1}         chol.cu: in-CTA 128-blocks + recursive doubling on the DMMA GEMM
+//   K2+K3 factor M = L L^T, L^{-1}     chol.cu: right-looking 64-block Cholesky whose launches also carry the block
+//                                      forward substitution for L^{-1}; -log det from the pivots
 //   K4  grad     g_j = -||Linv h_j||^2 DMMA triangular GEMM Linv*H streamed over column panels of H; the epilogue
 //                                      squares and column-reduces the 128x128 tile, so M^{-1}H never exists in HBM
 //
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(const double* part, 
 struct DoptPlan {
     int mp, nt, ntri, nib, splits;
     int64_t kchunk, npad;
-    size_t off_P, off_Linv, off_T, off_part, off_M, off_L, off_Wa, off_Wb, off_M2, off_L2, off_Wa2, off_Wb2, total;
+    size_t off_P, off_Linv, off_Y, off_part, off_M, off_L, off_W, off_M2, off_W2, total;
 };
 
 static DoptPlan make_plan(int m, int64_t n, int sm_count) {
@@ -304,14 +304,11 @@ static DoptPlan make_plan(int m, int64_t n, int sm_count) {
     size_t a = 0;
     pl.off_M = a;    a += mm;
     pl.off_L = a;    a += mm;
-    pl.off_Wa = a;   a += mm;
-    pl.off_Wb = a;   a += mm;
+    pl.off_W = a;    a += mm;      // trailing matrix of the factorisation
     pl.off_M2 = a;   a += mm;      // second set: the value-only evaluation that runs on the side stream
-    pl.off_L2 = a;   a += mm;
-    pl.off_Wa2 = a;  a += mm;
-    pl.off_Wb2 = a;  a += mm;
+    pl.off_W2 = a;   a += mm;
     pl.off_Linv = a; a += (size_t)pl.mp * pl.mp * 8;
-    pl.off_T = a;    a += (size_t)pl.mp * pl.mp * 8;
+    pl.off_Y = a;    a += (size_t)pl.mp * pl.mp * 8;      // running sums of the block forward substitution
     pl.off_P = a;    a += (size_t)pl.splits * pl.mp * pl.mp * 8;
     pl.off_part = a; a += (size_t)pl.nib * pl.npad * 8;
     pl.total = a;
@@ -384,34 +381,31 @@ int accbpg_dopt_gram(void* ctx, void* stream, const double* H, int m, int64_t n,
     return ACCBPG_OK;
 }
 
-int accbpg_dopt_factor(void* ctx, void* stream, int m, const double* M, double* L, void* ws, double* d_out) {
+int accbpg_dopt_factor(void* ctx, void* stream, int m, const double* M, double* L, int want_inverse, void* ws,
+                       double* d_out) {
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!c || !M || !L || !ws || !d_out) return arg_err("dopt_factor: NULL pointer");
+    if (!c || !M || !ws || !d_out) return arg_err("dopt_factor: NULL pointer");
     if (m < 1) return arg_err("dopt_factor: m");
     if (M == L) return arg_err("dopt_factor: in-place factorisation is not supported");
-    // the ping-pong trailing-matrix buffers live in the m-only head of the workspace (independent of n_local)
+    // the factor scratch lives in the m-only head of the workspace (independent of n_local)
     DoptPlan pl = make_plan(m, 2, c->sm_count);
-    double* Wa = (double*)((char*)ws + pl.off_Wa);
-    double* Wb = (double*)((char*)ws + pl.off_Wb);
-    if (M == Wa || M == Wb || L == Wa || L == Wb) return arg_err("dopt_factor: M / L alias the factor scratch");
-    return chol_factor(c, s, m, M, L, Wa, Wb, c->d_slots + 248, d_out);
+    double* W = (double*)((char*)ws + pl.off_W);
+    if (M == W || L == W) return arg_err("dopt_factor: M / L alias the factor scratch");
+    return chol_factor_inv(c, s, m, pl.mp, M, L, want_inverse ? 1 : 0, (double*)((char*)ws + pl.off_Linv), W,
+                           (double*)((char*)ws + pl.off_Y), c->d_slots + 248, d_out);
 }
 
-int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh, const double* L,
-                     void* ws, double* g) {
+int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh, void* ws, double* g) {
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!c || !H || !L || !ws || !g) return arg_err("dopt_grad: NULL pointer");
+    if (!c || !H || !ws || !g) return arg_err("dopt_grad: NULL pointer");
     if (m < 1 || n < 1 || ldh < n) return arg_err("dopt_grad: shape");
     int rc = ensure_smem_attrs();
     if (rc) return rc;
     DoptPlan pl = make_plan(m, n, c->sm_count);
-    double* Linv = (double*)((char*)ws + pl.off_Linv);
-    double* T = (double*)((char*)ws + pl.off_T);
+    double* Linv = (double*)((char*)ws + pl.off_Linv);      // left there by accbpg_dopt_factor(want_inverse = 1)
     double* part = (double*)((char*)ws + pl.off_part);
-    rc = tri_inverse(c, s, m, pl.mp, L, Linv, T);
-    if (rc) return rc;
     TrmmParams p;
     p.Linv = Linv; p.H = H; p.part = part; p.m = m; p.mp = pl.mp; p.nib = pl.nib;
     p.n = n; p.ldh = ldh; p.npad = pl.npad;
@@ -442,12 +436,11 @@ int accbpg_dopt_func_grad(void* ctx, void* stream, const double* H, int m, int64
     if (flag >= 1 && !g) return arg_err("dopt_func_grad: gradient buffer is NULL");
     DoptPlan pl = make_plan(m, n, c->sm_count);
     double* M = (double*)((char*)ws + pl.off_M);
-    double* L = (double*)((char*)ws + pl.off_L);
     int rc = accbpg_dopt_gram(ctx, stream, H, m, n, ldh, x, ws, M);
     if (rc) return rc;
-    rc = accbpg_dopt_factor(ctx, stream, m, M, L, ws, d_f_out ? d_f_out : (c->d_slots + 249));
+    rc = accbpg_dopt_factor(ctx, stream, m, M, NULL, flag >= 1, ws, d_f_out ? d_f_out : (c->d_slots + 249));
     if (rc) return rc;
-    if (flag >= 1) rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, L, ws, g);
+    if (flag >= 1) rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, ws, g);
     return rc;
 }
 
@@ -462,22 +455,20 @@ int accbpg_dopt_pair(void* ctx, void* stream, const double* H, int m, int64_t n,
     if (flag_y < 1 || flag_y > 2 || !g) return arg_err("dopt_pair: flag_y must be 1 or 2 with a gradient buffer");
     DoptPlan pl = make_plan(m, n, c->sm_count);
     double* M1 = (double*)((char*)ws + pl.off_M);
-    double* L1 = (double*)((char*)ws + pl.off_L);
     double* M2 = (double*)((char*)ws + pl.off_M2);
-    double* L2 = (double*)((char*)ws + pl.off_L2);
     int rc = accbpg_dopt_gram(ctx, stream, H, m, n, ldh, xf, ws, M2);
     if (rc) return rc;
     ACCBPG_CUDA(cudaEventRecord(c->ev_fork, s));
     ACCBPG_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
-    rc = chol_factor(c, c->side, m, M2, L2, (double*)((char*)ws + pl.off_Wa2), (double*)((char*)ws + pl.off_Wb2),
-                     c->d_slots + 246, d_fx_out);
+    rc = chol_factor_inv(c, c->side, m, pl.mp, M2, NULL, 0, NULL, (double*)((char*)ws + pl.off_W2), NULL,
+                         c->d_slots + 246, d_fx_out);
     if (rc) return rc;
     ACCBPG_CUDA(cudaEventRecord(c->ev_join, c->side));
     rc = accbpg_dopt_gram(ctx, stream, H, m, n, ldh, yg, ws, M1);
     if (rc) return rc;
-    rc = accbpg_dopt_factor(ctx, stream, m, M1, L1, ws, d_fy_out ? d_fy_out : (c->d_slots + 249));
+    rc = accbpg_dopt_factor(ctx, stream, m, M1, NULL, 1, ws, d_fy_out ? d_fy_out : (c->d_slots + 249));
     if (rc) return rc;
-    rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, L1, ws, g);
+    rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, ws, g);
     if (rc) return rc;
     ACCBPG_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
     return ACCBPG_OK;
@@ -494,21 +485,19 @@ int accbpg_dopt_pair_from_gram(void* ctx, void* stream, const double* H, int m, 
     if (flag_y < 0 || flag_y > 2 || (flag_y >= 1 && !g)) return arg_err("dopt_pair_from_gram: flag_y / gradient buffer");
     if (Mx && !d_fx_out) return arg_err("dopt_pair_from_gram: d_fx_out is NULL");
     DoptPlan pl = make_plan(m, n, c->sm_count);
-    double* L1 = (double*)((char*)ws + pl.off_L);
-    double* L2 = (double*)((char*)ws + pl.off_L2);
     int rc;
     if (Mx) {
         ACCBPG_CUDA(cudaEventRecord(c->ev_fork, s));
         ACCBPG_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
-        rc = chol_factor(c, c->side, m, Mx, L2, (double*)((char*)ws + pl.off_Wa2), (double*)((char*)ws + pl.off_Wb2),
-                         c->d_slots + 246, d_fx_out);
+        rc = chol_factor_inv(c, c->side, m, pl.mp, Mx, NULL, 0, NULL, (double*)((char*)ws + pl.off_W2), NULL,
+                             c->d_slots + 246, d_fx_out);
         if (rc) return rc;
         ACCBPG_CUDA(cudaEventRecord(c->ev_join, c->side));
     }
-    rc = accbpg_dopt_factor(ctx, stream, m, My, L1, ws, d_fy_out ? d_fy_out : (c->d_slots + 249));
+    rc = accbpg_dopt_factor(ctx, stream, m, My, NULL, flag_y >= 1, ws, d_fy_out ? d_fy_out : (c->d_slots + 249));
     if (rc) return rc;
     if (flag_y >= 1) {
-        rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, L1, ws, g);
+        rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, ws, g);
         if (rc) return rc;
     }
     if (Mx) ACCBPG_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));

@@ -59,7 +59,6 @@ class DOptimalObj(RSmoothFunction):
                                      lib.accbpg_dopt_workspace_bytes(self.m, self.n_local))
         if shard is not None and shard.world > 1:
             self._M = torch.empty(self.m, self.m, dtype=torch.float64, device=self.rt.device)
-            self._L = torch.empty(self.m, self.m, dtype=torch.float64, device=self.rt.device)
 
     # ---- linear image M(x) = H diag(x) H^T (config.linear_images) ------------------------------------------
     _lin_capable = True
@@ -116,11 +115,10 @@ class DOptimalObj(RSmoothFunction):
         nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
                                        xd.data_ptr(), ws, self._M.data_ptr()))
         self.shard.sum_(self._M)
-        nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, self.m, self._M.data_ptr(), self._L.data_ptr(), ws,
+        nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, self.m, self._M.data_ptr(), None, int(flag >= 1), ws,
                                          rt.slot(slot)))
         if flag >= 1:
-            nat.check(lib.accbpg_dopt_grad(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
-                                           self._L.data_ptr(), ws, gp))
+            nat.check(lib.accbpg_dopt_grad(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0), ws, gp))
 
 
 class _LinearInverse(RSmoothFunction):

@@ -160,14 +160,17 @@ size_t accbpg_dopt_workspace_bytes(int m, int64_t n_local);
  * as a full symmetric m x m matrix with leading dimension m.  Sets ST_X_NEGATIVE if some x < 0. */
 int accbpg_dopt_gram(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
                      const double* d_x, void* d_ws, double* d_M);
-/* K2: blocked Cholesky M = L L^T, out of place (d_M symmetric m x m is only read; d_L m x m receives the lower
- * factor, zero above the diagonal); d_out[0] = -log det M = -sum log(pivot).  Sets ST_NOT_PD on a pivot <= 0.
- * d_ws is the dopt workspace (any n_local): two m x m trailing-matrix buffers ping-pong inside it. */
-int accbpg_dopt_factor(void* ctx, void* stream, int m, const double* d_M, double* d_L, void* d_ws, double* d_out);
-/* K3+K4: g_j = -|| L^{-1} h_j ||^2 for the local columns: triangular inverse, then a DMMA triangular
- * GEMM whose epilogue reduces squared column norms (M^{-1}H is never materialised). */
-int accbpg_dopt_grad(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
-                     const double* d_L, void* d_ws, double* d_g);
+/* K2 (+K3): blocked Cholesky M = L L^T, out of place (d_M symmetric m x m is only read); d_out[0] = -log det M =
+ * -sum log(pivot).  d_L (m x m, may be NULL) receives the lower factor, zero above the diagonal.  want_inverse != 0
+ * also leaves L^{-1} in the workspace for accbpg_dopt_grad: the block forward substitution rides in the same launches
+ * as the factorisation.  Sets ST_NOT_PD on a pivot <= 0.  d_ws is the dopt workspace (any n_local). */
+int accbpg_dopt_factor(void* ctx, void* stream, int m, const double* d_M, double* d_L, int want_inverse, void* d_ws,
+                       double* d_out);
+/* K4: g_j = -|| L^{-1} h_j ||^2 for the local columns, with the L^{-1} that the last accbpg_dopt_factor(want_inverse = 1)
+ * on this workspace left there: a DMMA triangular GEMM whose epilogue reduces squared column norms
+ * (M^{-1}H is never materialised). */
+int accbpg_dopt_grad(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh, void* d_ws,
+                     double* d_g);
 /* whole func_grad on one GPU: flag 0 value, 1 gradient, 2 both (value always computed, as in the reference) */
 int accbpg_dopt_func_grad(void* ctx, void* stream, const double* d_H, int m, int64_t n, int64_t ldh,
                           const double* d_x, int flag, void* d_ws, double* d_f_out, double* d_g);

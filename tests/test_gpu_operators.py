@@ -43,6 +43,40 @@ def test_dopt_func_grad_vs_oracle(acc, m, n, seed):
         assert abs(float(np.dot(xx, g)) + m) <= 1e-9 * m
 
 
+@pytest.mark.parametrize("m", [1, 13, 63, 64, 65, 150, 257, 500, 777])
+def test_dopt_factor_entry_point(acc, m):
+    """accbpg_dopt_factor through the C ABI: L L^T = M, -log det, and the cached L^{-1} used by accbpg_dopt_grad."""
+    from accbpg_and_fw_b200 import _native as nat
+    lib = nat.lib
+    rt = acc.Runtime.get()
+    rng = np.random.RandomState(100 + m)
+    n = 2 * m + 6
+    H = rng.randn(m, n)
+    x = rng.rand(n) + 0.05
+    M = (H * x) @ H.T
+    Md = torch.tensor(M, device="cuda")
+    Hd = torch.tensor(H, device="cuda")
+    Ld = torch.full((m, m), 7.0, dtype=torch.float64, device="cuda")
+    gd = torch.empty(n, dtype=torch.float64, device="cuda")
+    ws = torch.empty(lib.accbpg_dopt_workspace_bytes(m, n), dtype=torch.uint8, device="cuda")
+    for want_inv in (0, 1):
+        nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, m, Md.data_ptr(), Ld.data_ptr(), want_inv, ws.data_ptr(),
+                                         rt.slot(40)))
+        val = rt.read(40, 1)[0]
+        L = Ld.cpu().numpy()
+        assert np.array_equal(L, np.tril(L))
+        assert np.max(np.abs(L @ L.T - M)) <= 1e-12 * np.max(np.abs(M))
+        sign, logdet = np.linalg.slogdet(M)
+        assert abs(val + logdet) <= 1e-11 * max(1.0, abs(logdet))
+    nat.check(lib.accbpg_dopt_grad(rt.ctx, rt.stream, Hd.data_ptr(), m, n, n, ws.data_ptr(), gd.data_ptr()))
+    rt.read(40, 0)
+    gref = -np.sum(H * np.linalg.solve(M, H), axis=0)
+    assert rel(gd.cpu().numpy(), gref) <= 1e-9
+    # value-only factorisation without an L output
+    nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, m, Md.data_ptr(), None, 0, ws.data_ptr(), rt.slot(41)))
+    assert rt.read(41, 1)[0] == val
+
+
 def test_dopt_golden_fixtures(acc, golden_ops):
     for tag, (m, n, seed) in {"dopt_80x200": (80, 200, 10), "dopt_30x1000": (30, 1000, 3),
                               "dopt_129x517": (129, 517, 7)}.items():

@@ -59,8 +59,8 @@ for (m, n) in [(500, 50000), (2000, 200000), (80, 200)]:
     g = torch.empty(n, dtype=torch.float64, device=dev)
     tag = f"dopt_{m}x{n}"
     t_gram = timeit(lambda: nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, H.data_ptr(), m, n, n, x.data_ptr(), ws, M.data_ptr())))
-    t_fac = timeit(lambda: nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, m, M.data_ptr(), L.data_ptr(), ws, rt.slot(40))))
-    t_grad = timeit(lambda: nat.check(lib.accbpg_dopt_grad(rt.ctx, rt.stream, H.data_ptr(), m, n, n, L.data_ptr(), ws, g.data_ptr())))
+    t_fac = timeit(lambda: nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, m, M.data_ptr(), L.data_ptr(), 1, ws, rt.slot(40))))
+    t_grad = timeit(lambda: nat.check(lib.accbpg_dopt_grad(rt.ctx, rt.stream, H.data_ptr(), m, n, n, ws, g.data_ptr())))
     t_all = timeit(lambda: f._enqueue(x, 2, 40, g))
     out[tag] = {"gram_ms": t_gram, "factor_ms": t_fac, "grad_ms": t_grad, "func_grad_ms": t_all,
                 "gram_tflops": m * m * n / t_gram[0] / 1e9, "grad_tflops": m * m * n / t_grad[0] / 1e9}
