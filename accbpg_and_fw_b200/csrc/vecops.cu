@@ -169,6 +169,10 @@ struct BurgSimplexFinishF {
     const double* gg; double c; double* out;
     __device__ void operator()(int64_t i, uint32_t&) const { out[i] = 1.0 / (gg[i] + c); }
 };
+struct BurgSimplexFinishDevF {
+    const double* gg; const double* c; double* out;
+    __device__ void operator()(int64_t i, uint32_t&) const { out[i] = 1.0 / (gg[i] + ld_cg(c)); }
+};
 
 // ---------------------------------------------------------------- functors: Shannon entropy
 struct ShannonValueF {
@@ -358,20 +362,27 @@ __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, double a, double
     rb = block_sum(sb, sh);
 }
 
+// gg_in != NULL: root-find only, on a ready vector gg (the column-sharded path gathers every rank's slice; padding
+// entries are +inf and drop out of the minimum and of both sums); the kernel then writes nothing but `info`.
 __global__ void __launch_bounds__(kBurgThreads) burg_simplex_kernel(int64_t n, const double* y, const double* g,
                                                                     double L, double eps, double* out,
                                                                     double* info, double* partials,
-                                                                    uint32_t* status) {
+                                                                    uint32_t* status, const double* gg_in) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t st = 0;
     double lo = kInf;
-    for (int64_t i = first; i < n; i += stride) {
-        double gg = burg_shift(y, g, L, i, st) / L;
-        out[i] = gg;
-        lo = fmin(lo, gg);
+    const double* ggp = gg_in ? gg_in : out;
+    if (gg_in) {
+        for (int64_t i = first; i < n; i += stride) lo = fmin(lo, gg_in[i]);
+    } else {
+        for (int64_t i = first; i < n; i += stride) {
+            double gg = burg_shift(y, g, L, i, st) / L;
+            out[i] = gg;
+            lo = fmin(lo, gg);
+        }
     }
     lo = block_min(lo, sh);
     if (threadIdx.x == 0) partials[blockIdx.x] = lo;
@@ -387,7 +398,7 @@ __global__ void __launch_bounds__(kBurgThreads) burg_simplex_kernel(int64_t n, c
     for (;;) {
         double a = 0.0, b = 0.0;
         for (int64_t i = first; i < n; i += stride) {
-            double t = out[i] + c;
+            double t = ggp[i] + c;
             a += 1.0 / t;
             b += -1.0 / (t * t);
         }
@@ -405,7 +416,7 @@ __global__ void __launch_bounds__(kBurgThreads) burg_simplex_kernel(int64_t n, c
         c = cn;
         double a = 0.0, b = 0.0;
         for (int64_t i = first; i < n; i += stride) {
-            double t = out[i] + c;
+            double t = ggp[i] + c;
             a += 1.0 / t;
             b += -1.0 / (t * t);
         }
@@ -415,7 +426,8 @@ __global__ void __launch_bounds__(kBurgThreads) burg_simplex_kernel(int64_t n, c
         if (++nnewton >= 200) { st |= ACCBPG_ST_NEWTON_MAXIT; break; }
     }
     // the grid.sync inside the last grid_sum2 came after every block's read loop: gg may be overwritten
-    for (int64_t i = first; i < n; i += stride) out[i] = 1.0 / (out[i] + c);
+    if (!gg_in)
+        for (int64_t i = first; i < n; i += stride) out[i] = 1.0 / (out[i] + c);
     if (st) atomicOr(status, st);
     if (info != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         info[0] = (double)nbis; info[1] = (double)nnewton; info[2] = c;
@@ -601,11 +613,36 @@ int accbpg_burg_simplex_prox(void* ctx, void* stream, int64_t n, const double* y
     int grid = (int)(want < c->coop_blocks_burg ? want : c->coop_blocks_burg);
     double* partials = c->d_partials;
     uint32_t* status = c->d_status;
-    void* args[] = {&n, &y, &g, &L, &eps, &out, &info, &partials, &status};
+    const double* gg_in = nullptr;
+    void* args[] = {&n, &y, &g, &L, &eps, &out, &info, &partials, &status, &gg_in};
     ProfScope ps(P_BURG_SIMPLEX, s);
     ACCBPG_CUDA(cudaLaunchCooperativeKernel((void*)burg_simplex_kernel, dim3(grid), dim3(kBurgThreads), args, 0, s));
     ACCBPG_LAUNCHED("burg_simplex_prox");
     return ACCBPG_OK;
+}
+int accbpg_burg_simplex_root(void* ctx, void* stream, int64_t n, const double* gg, double eps, double* d_info) {
+    CTX_STREAM
+    if (!gg || !d_info) return arg_err("burg_simplex_root: NULL pointer");
+    if (n < 1) return arg_err("n must be >= 1");
+    int64_t want = (n + kBurgThreads - 1) / kBurgThreads;
+    int grid = (int)(want < c->coop_blocks_burg ? want : c->coop_blocks_burg);
+    double* partials = c->d_partials;
+    uint32_t* status = c->d_status;
+    const double* y = nullptr;
+    const double* g = nullptr;
+    double* out = nullptr;
+    double L = 1.0;
+    void* args[] = {&n, &y, &g, &L, &eps, &out, &d_info, &partials, &status, &gg};
+    ProfScope ps(P_BURG_SIMPLEX, s);
+    ACCBPG_CUDA(cudaLaunchCooperativeKernel((void*)burg_simplex_kernel, dim3(grid), dim3(kBurgThreads), args, 0, s));
+    ACCBPG_LAUNCHED("burg_simplex_root");
+    return ACCBPG_OK;
+}
+int accbpg_burg_simplex_finish_dev(void* ctx, void* stream, int64_t n, const double* gg, const double* d_c, double* out) {
+    CTX_STREAM
+    if (n == 0) return ACCBPG_OK;
+    if (!gg || !d_c || !out) return arg_err("burg_simplex_finish_dev: NULL pointer");
+    return launch_map(c, s, n, BurgSimplexFinishDevF{gg, d_c, out}, "burg_simplex_finish_dev");
 }
 int accbpg_burg_simplex_prepare(void* ctx, void* stream, int64_t n, const double* y, const double* g, double L,
                                 double* gg, double* d_out) {

@@ -122,6 +122,13 @@ int accbpg_burg_simplex_prepare(void* ctx, void* stream, int64_t n, const double
 int accbpg_burg_simplex_sums(void* ctx, void* stream, int64_t n, const double* d_gg, double c, double* d_out);
 int accbpg_burg_simplex_finish(void* ctx, void* stream, int64_t n, const double* d_gg, double c,
                                double* d_out_vec);
+/* the same root-find without a host round trip: every rank all-gathers the slices of gg (padding entries +inf),
+ * runs the whole recurrence of functions.py:341-356 on the gathered vector in one cooperative kernel -- the result
+ * does not depend on how the columns are sharded -- and finishes its own slice with the c left on the device.
+ * d_info (3 slots): bisection steps, Newton steps, c. */
+int accbpg_burg_simplex_root(void* ctx, void* stream, int64_t n, const double* d_gg, double eps, double* d_info);
+int accbpg_burg_simplex_finish_dev(void* ctx, void* stream, int64_t n, const double* d_gg, const double* d_c,
+                                   double* d_out_vec);
 
 /* ---- Shannon entropy kernels  h(x) = sum x log x   (accbpg/functions.py:398-490) */
 int accbpg_shannon_value(void* ctx, void* stream, int64_t n, const double* d_x, double delta, double* d_out);   /* :405-408 */
