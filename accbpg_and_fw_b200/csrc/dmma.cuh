@@ -1,6 +1,7 @@
-// FP64 tensor-core (DMMA.8x8x4) tile machinery shared by the SYRK, the triangular GEMM and the GEMMs of the
-// triangular inverse: 128x128 CTA tile, 8 warps (2 x 4), warp tile 64x32 = 8x4 mma.sync.m8n8k4 tiles,
-// k-slabs of 16 staged through a 4-deep cp.async pipeline into padded (bank-conflict-free) shared memory.
+// FP64 tensor-core (DMMA.8x8x4) tile machinery shared by the SYRK and the triangular GEMM: 128x128 CTA tile,
+// 16 warps (4 x 4, four per SM sub-partition so the DMMA pipe always has a ready warp), warp tile 32x32 = 4x4
+// mma.sync.m8n8k4 tiles, k-slabs of 16 staged through a 4-deep cp.async pipeline into padded (bank-conflict-free)
+// shared memory.
 #pragma once
 #include "common.cuh"
 
@@ -10,10 +11,10 @@ constexpr int BM = 128;            // CTA tile rows
 constexpr int BN = 128;            // CTA tile cols
 constexpr int BK = 16;             // k-slab per pipeline stage
 constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 256;  // 8 warps: 2 (rows) x 4 (cols)
+constexpr int GEMM_THREADS = 512;  // 16 warps: 4 (rows) x 4 (cols)
 constexpr int A_LD = BK + 4;       // 20 doubles: (g*20 + t) mod 16 distinct over a half warp -> conflict-free LDS.64
 constexpr int BT_LD = BN + 4;      // 132 doubles for a k-major B tile: (t*132 + g) mod 16 distinct
-constexpr int MI = 8, NI = 4;
+constexpr int MI = 4, NI = 4;       // warp tile 32 x 32
 
 constexpr int KMAJOR_STAGE_DOUBLES = BM * A_LD + BN * A_LD + BK;   // A[i][k], B[j][k], x[k]      (SYRK)
 constexpr int KMAJOR_SMEM = STAGES * KMAJOR_STAGE_DOUBLES * 8;
@@ -101,30 +102,26 @@ __device__ __forceinline__ void load_nmajor_slab(double* dst, const double* src,
     }
 }
 
-// one k-slab of the "NN" product: acc += A_s[128 x 16] * B_s[16 x 128]
+// one k-slab of the "NN" product: acc += A_s[128 x 16] * B_s[16 x 128]; only the first k4_count 4-wide steps of the
+// slab are issued (the triangular GEMM stops each warp at its own diagonal).  With four warps per sub-partition the
+// fragment loads of one warp hide under the DMMAs of the others: no register double buffering.
 __device__ __forceinline__ void mma_nn_slab(double (&acc)[MI][NI][2], const double* As, const double* Bs, int wm, int wn,
-                                            int g, int t) {
-    const double* ap = As + (wm * 64 + g) * A_LD + t;
+                                            int g, int t, int k4_count) {
+    const double* ap = As + (wm * 32 + g) * A_LD + t;
     const double* bp = Bs + t * BT_LD + wn * 32 + g;
-    // fragments are double buffered in registers: the LDS of step kk+1 are in flight under the DMMAs of step kk
-    double a[2][MI], b[2][NI];
-#pragma unroll
-    for (int i = 0; i < MI; ++i) a[0][i] = ap[i * 8 * A_LD];
-#pragma unroll
-    for (int j = 0; j < NI; ++j) b[0][j] = bp[j * 8];
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
-        const int cur = kk & 1, nxt = cur ^ 1;
-        if (kk + 1 < BK / 4) {
+        if (kk < k4_count) {
+            double a[MI], b[NI];
 #pragma unroll
-            for (int i = 0; i < MI; ++i) a[nxt][i] = ap[i * 8 * A_LD + (kk + 1) * 4];
+            for (int i = 0; i < MI; ++i) a[i] = ap[i * 8 * A_LD + kk * 4];
 #pragma unroll
-            for (int j = 0; j < NI; ++j) b[nxt][j] = bp[(kk + 1) * 4 * BT_LD + j * 8];
+            for (int j = 0; j < NI; ++j) b[j] = bp[kk * 4 * BT_LD + j * 8];
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
-#pragma unroll
-        for (int i = 0; i < MI; ++i)
-#pragma unroll
-            for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
     }
 }
 #endif  // __CUDACC__

@@ -10,19 +10,34 @@
 //
 // Blackwell's tcgen05 tensor path has no FP64 kind, so FP64 tensor work is issued as warp-level DMMA.8x8x4
 // (every f64 mma.sync shape lowers to that SASS on sm_100a) fed from shared memory through a 4-stage cp.async pipeline.
+#include <cuda.h>
+#include <cstdlib>
+#include <map>
+#include <tuple>
+#include <vector>
 #include "dmma.cuh"
 
 namespace accbpg {
 
 // ------------------------------------------------------------------------------------------ K1: SYRK
+// Lower 128x128 tiles only.  Off-diagonal tiles use all 16 warps; in a diagonal tile the six warp tiles strictly above
+// the diagonal are skipped and the ten that remain are numbered so that the four SM sub-partitions carry 3/3/2/2 of
+// them: a diagonal tile costs 3/4 of a full one (and stages its 128 rows of H once, as both operands).  The column
+// range is split differently for the two kinds of tile so that every CTA carries about the same work.
 struct SyrkParams {
     const double* H;
     const double* x;
-    double* P;          // [splits][mp][mp] partial tiles (lower tiles only are written)
-    int m, mp, splits;
-    int64_t n, ldh, kchunk;
+    double* P;          // [split][mp][mp] partial tiles (lower tiles only are written)
+    int m, mp, nt;
+    int n_off;          // number of strictly-lower tiles
+    int s_off, s_diag;  // column splits of an off-diagonal / a diagonal tile
+    int diag_first;     // CTA order: the longer kind first
+    int64_t n, ldh, kchunk_off, kchunk_diag;
     uint32_t* status;
 };
+
+__constant__ signed char kDiagWm[16] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, -1, -1, -1, -1, -1, -1};
+__constant__ signed char kDiagWn[16] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, -1, -1, -1, -1, -1, -1};
 
 template <bool ALIGNED16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_dmma_kernel(SyrkParams p) {
@@ -30,17 +45,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_dmma_kernel(SyrkParams p
     double* smem = reinterpret_cast<double*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;
 
-    // lower-triangular tile index -> (bi, bj), bi >= bj
-    int tt = blockIdx.x;
-    int bi = (int)((sqrt(8.0 * tt + 1.0) - 1.0) * 0.5);
-    while ((bi + 1) * (bi + 2) / 2 <= tt) ++bi;
-    while (bi * (bi + 1) / 2 > tt) --bi;
-    const int bj = tt - bi * (bi + 1) / 2;
+    // ---- which tile, which column chunk
+    int b = blockIdx.x;
+    const int n_off_ctas = p.n_off * p.s_off, n_diag_ctas = p.nt * p.s_diag;
+    bool diag;
+    if (p.diag_first) { diag = b < n_diag_ctas; if (!diag) b -= n_diag_ctas; }
+    else              { diag = b >= n_off_ctas; if (diag) b -= n_off_ctas; }
+    int bi, bj, split;
+    int64_t kchunk;
+    if (diag) {
+        bi = bj = b % p.nt;
+        split = b / p.nt;
+        kchunk = p.kchunk_diag;
+    } else {
+        const int tt = b % p.n_off;                   // strictly-lower tile index -> (bi, bj), bi > bj
+        split = b / p.n_off;
+        bi = (int)((sqrt(8.0 * tt + 1.0) + 1.0) * 0.5);
+        while (bi * (bi - 1) / 2 > tt) --bi;
+        while ((bi + 1) * bi / 2 <= tt) ++bi;
+        bj = tt - bi * (bi - 1) / 2;
+        kchunk = p.kchunk_off;
+    }
+    int wm = warp >> 2, wn = warp & 3;
+    if (diag) { wm = kDiagWm[warp]; wn = kDiagWn[warp]; }
+    const bool active = wm >= 0;
 
-    const int64_t k_begin = (int64_t)blockIdx.y * p.kchunk;
-    int64_t k_end = k_begin + p.kchunk;
+    const int64_t k_begin = (int64_t)split * kchunk;
+    int64_t k_end = k_begin + kchunk;
     if (k_end > p.n) k_end = p.n;
     const int KT = (k_end > k_begin) ? (int)((k_end - k_begin + BK - 1) / BK) : 0;
 
@@ -51,15 +83,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_dmma_kernel(SyrkParams p
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // Per-thread copy descriptors of the fast path (aligned, k-slab fully inside the chunk): the same 16-byte column
-    // chunk of rows lr, lr+32, lr+64, lr+96 of the A block and of the B block.  Pointers advance by BK per k-slab, so
-    // a stage costs 8-9 cp.async and no address arithmetic beyond one add each.
+    // chunk of rows lr and lr+64 of the A block and of the B block.  Pointers advance by BK per k-slab.
     const int ch = tid & 7, lr = tid >> 3;
-    const double* ga[4];
-    const double* gb[4];
-    int ba[4], bb[4];
+    const double* ga[2];
+    const double* gb[2];
+    int ba[2], bb[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int ra = bi * BM + lr + 32 * i, rb = bj * BN + lr + 32 * i;
+    for (int i = 0; i < 2; ++i) {
+        const int ra = bi * BM + lr + 64 * i, rb = bj * BN + lr + 64 * i;
         ba[i] = ra < p.m ? 16 : 0;
         bb[i] = rb < p.m ? 16 : 0;
         ga[i] = p.H + (int64_t)(ba[i] ? ra : 0) * p.ldh + k_begin + ch * 2;
@@ -67,6 +98,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_dmma_kernel(SyrkParams p
     }
     const int soff = lr * A_LD + ch * 2;
     const int KT_full = (k_end > k_begin) ? (int)((k_end - k_begin) / BK) : 0;
+    const int b_off = diag ? 0 : BM * A_LD;          // a diagonal tile reads its B operand from the A slab
 
     auto load_stage = [&](int stage, int kt) {
         double* As = smem + stage * KMAJOR_STAGE_DOUBLES;
@@ -75,16 +107,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_dmma_kernel(SyrkParams p
         if (ALIGNED16 && kt < KT_full) {
             const int64_t ko = (int64_t)kt * BK;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                cp_async16(As + soff + i * 32 * A_LD, ga[i] + ko, ba[i]);
-                cp_async16(Bs + soff + i * 32 * A_LD, gb[i] + ko, bb[i]);
+            for (int i = 0; i < 2; ++i) {
+                cp_async16(As + soff + i * 64 * A_LD, ga[i] + ko, ba[i]);
+                if (!diag) cp_async16(Bs + soff + i * 64 * A_LD, gb[i] + ko, bb[i]);
             }
             if (tid < 8) cp_async16(Xs + tid * 2, p.x + k_begin + ko + tid * 2, 16);
             return;
         }
         const int64_t k0 = k_begin + (int64_t)kt * BK;
         load_kmajor_slab<ALIGNED16>(As, p.H, p.ldh, bi * BM, p.m, k0, k_end, tid);
-        load_kmajor_slab<ALIGNED16>(Bs, p.H, p.ldh, bj * BN, p.m, k0, k_end, tid);
+        if (!diag) load_kmajor_slab<ALIGNED16>(Bs, p.H, p.ldh, bj * BN, p.m, k0, k_end, tid);
         if (ALIGNED16) {
             if (tid < 8) {
                 int64_t gk = k0 + tid * 2;
@@ -111,52 +143,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_dmma_kernel(SyrkParams p
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        // The two warps that share an SM sub-partition (wm = 0 / 1) issue their share of the next stage's copies at
-        // different points of the k-slab, so one of them is always feeding the DMMA pipe.
-        const int nk = kt + STAGES - 1;
-        if (wm == 0 && nk < KT) load_stage(nk % STAGES, nk);
-        const double* As = smem + (kt % STAGES) * KMAJOR_STAGE_DOUBLES;
-        const double* Bs = As + BM * A_LD;
-        const double* Xs = Bs + BN * A_LD;
-        const double* ap = As + (wm * 64 + g) * A_LD + t;
-        const double* bp = Bs + (wn * 32 + g) * A_LD + t;
-        // fragments double buffered in registers: LDS (+ the diag(x) scaling) of step kk+1 run under the DMMAs of kk
-        double a[2][MI], b[2][NI];
         {
-            const double xv = Xs[t];
-            neg |= (xv < 0.0);
-#pragma unroll
-            for (int i = 0; i < MI; ++i) a[0][i] = ap[i * 8 * A_LD];
-#pragma unroll
-            for (int j = 0; j < NI; ++j) b[0][j] = bp[j * 8 * A_LD] * xv;
+            const int nk = kt + STAGES - 1;
+            if (nk < KT) load_stage(nk % STAGES, nk);
+            cp_async_commit();
         }
+        if (active) {
+            const double* As = smem + (kt % STAGES) * KMAJOR_STAGE_DOUBLES;
+            const double* Xs = As + (BM + BN) * A_LD;
+            const double* ap = As + (wm * 32 + g) * A_LD + t;
+            const double* bp = As + b_off + (wn * 32 + g) * A_LD + t;
 #pragma unroll
-        for (int kk = 0; kk < BK / 4; ++kk) {
-            const int cur = kk & 1, nxt = cur ^ 1;
-            if (kk == 2 && wm == 1 && nk < KT) load_stage(nk % STAGES, nk);
-            if (kk + 1 < BK / 4) {
-                const double xv = Xs[(kk + 1) * 4 + t];
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                const double xv = Xs[kk * 4 + t];
                 neg |= (xv < 0.0);
+                double a[MI], bq[NI];
 #pragma unroll
-                for (int i = 0; i < MI; ++i) a[nxt][i] = ap[i * 8 * A_LD + (kk + 1) * 4];
+                for (int i = 0; i < MI; ++i) a[i] = ap[i * 8 * A_LD + kk * 4];
 #pragma unroll
-                for (int j = 0; j < NI; ++j) b[nxt][j] = bp[j * 8 * A_LD + (kk + 1) * 4] * xv;
+                for (int j = 0; j < NI; ++j) bq[j] = bp[j * 8 * A_LD + kk * 4] * xv;      // diag(x) fused into the operand
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bq[j]);
             }
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
         }
-        cp_async_commit();
     }
     cp_async_wait<0>();
     if (neg) atomicOr(p.status, ACCBPG_ST_X_NEGATIVE);
+    if (!active) return;
 
     // partial tile -> workspace (mp is a multiple of 128: no bounds checks, 16-byte stores)
-    double* P = p.P + (size_t)blockIdx.y * p.mp * p.mp;
+    double* P = p.P + (size_t)split * p.mp * p.mp;
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
-        int row = bi * BM + wm * 64 + i * 8 + g;
+        int row = bi * BM + wm * 32 + i * 8 + g;
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
             int col = bj * BN + wn * 32 + j * 8 + 2 * t;
@@ -166,11 +187,188 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_dmma_kernel(SyrkParams p
     }
 }
 
+// ------------------------------------------------------------------------------------------ K1, TMA mainloop
+// Same tiling and work split as syrk_dmma_kernel, with the operand traffic taken off the warps: one elected thread
+// issues a 2-D TMA box (128 rows x 16 columns of H, 128-byte swizzle) per operand and a 1-D box of x per k-slab,
+// completion is signalled on per-stage mbarriers (full / empty), and there is no CTA-wide barrier in the main loop.
+// With the 128-byte swizzle the 16-byte chunk index of (row, k) is (k/2) ^ (row & 7).  A DMMA fragment read touches
+// rows g = 0..3 and 32 contiguous bytes per row in a half warp, which would be a 2-way conflict under the natural row
+// order; mma row g of tile i is therefore mapped to tile row 16*(i/2) + 2g + (i&1) (and the same for the columns of
+// the output), which makes the half warp's eight (row, chunk) pairs land on eight distinct chunks.
+constexpr int TMA_STAGES = 6;
+constexpr int TMA_PREFETCH = 4;                          // slabs in flight ahead of the consumers
+constexpr int TMA_STAGE_BYTES = 2 * BM * BK * 8 + 1024;  // A box, B box, x slab (padded to keep 1024-byte alignment)
+constexpr int TMA_SMEM = TMA_STAGES * TMA_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* mbarriers */;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol error traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (int spin = 0; spin < (1 << 24); ++spin) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* tmap, int c0, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(bar) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+syrk_tma_kernel(SyrkParams p, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmX) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem0 = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;      // 1024-byte aligned
+    const uint32_t bars = smem0 + TMA_STAGES * TMA_STAGE_BYTES;      // full[0..S), empty[0..S): 8 bytes each
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    int b = blockIdx.x;
+    const int n_off_ctas = p.n_off * p.s_off, n_diag_ctas = p.nt * p.s_diag;
+    bool diag;
+    if (p.diag_first) { diag = b < n_diag_ctas; if (!diag) b -= n_diag_ctas; }
+    else              { diag = b >= n_off_ctas; if (diag) b -= n_off_ctas; }
+    int bi, bj, split;
+    int64_t kchunk;
+    if (diag) {
+        bi = bj = b % p.nt;
+        split = b / p.nt;
+        kchunk = p.kchunk_diag;
+    } else {
+        const int tt = b % p.n_off;
+        split = b / p.n_off;
+        bi = (int)((sqrt(8.0 * tt + 1.0) + 1.0) * 0.5);
+        while (bi * (bi - 1) / 2 > tt) --bi;
+        while ((bi + 1) * bi / 2 <= tt) ++bi;
+        bj = tt - bi * (bi - 1) / 2;
+        kchunk = p.kchunk_off;
+    }
+    int wm = warp >> 2, wn = warp & 3;
+    if (diag) { wm = kDiagWm[warp]; wn = kDiagWn[warp]; }
+    const bool active = wm >= 0;
+    const int n_active = diag ? 10 : 16;
+
+    const int64_t k_begin = (int64_t)split * kchunk;             // multiple of BK: chunk edges fall on slab edges
+    int64_t k_end = k_begin + kchunk;
+    if (k_end > p.n) k_end = p.n;
+    const int KT = (k_end > k_begin) ? (int)((k_end - k_begin + BK - 1) / BK) : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < TMA_STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);                          // full: the producer's arrive.expect_tx
+            mbar_init(bars + 8 * (TMA_STAGES + s), n_active);    // empty: one arrival per consuming warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t stage_tx = (diag ? 1u : 2u) * BM * BK * 8 + BK * 8;
+    auto issue = [&](int s) {                                    // one thread: arm the stage and launch its copies
+        const int st = s % TMA_STAGES;
+        const uint32_t base = smem0 + st * TMA_STAGE_BYTES, full = bars + 8 * st;
+        const int kcol = (int)(k_begin + (int64_t)s * BK);
+        mbar_arrive_expect_tx(full, stage_tx);
+        tma_load_2d(base, &tmH, kcol, bi * BM, full);
+        if (!diag) tma_load_2d(base + BM * BK * 8, &tmH, kcol, bj * BN, full);
+        tma_load_1d(base + 2 * BM * BK * 8, &tmX, kcol, full);
+    };
+    if (tid == 0) {
+        const int pre = KT < TMA_PREFETCH ? KT : TMA_PREFETCH;
+        for (int s = 0; s < pre; ++s) issue(s);
+    }
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // per-thread byte offsets inside a stage: tile row of mma row g for even / odd tiles, with the swizzle term folded in
+    //   element (row, k = 4kk + t):  row*128 + ((2kk + t/2) ^ (row & 7))*16 + (t & 1)*8 = base ^ (kk << 5)
+    uint32_t offA[2], offB[2];
+#pragma unroll
+    for (int pq = 0; pq < 2; ++pq) {
+        const int ra = (active ? wm : 0) * 32 + 2 * g + pq, rb = (active ? wn : 0) * 32 + 2 * g + pq;
+        offA[pq] = ra * 128 + ((((t >> 1) ^ (ra & 7))) << 4) + (t & 1) * 8;
+        offB[pq] = rb * 128 + ((((t >> 1) ^ (rb & 7))) << 4) + (t & 1) * 8 + (diag ? 0 : BM * BK * 8);
+    }
+
+    bool neg = false;
+    for (int s = 0; s < KT; ++s) {
+        const int st = s % TMA_STAGES;
+        const uint32_t base = smem0 + st * TMA_STAGE_BYTES;
+        if (tid == 0) {                                          // keep TMA_PREFETCH slabs in flight
+            const int sn = s + TMA_PREFETCH;
+            if (sn < KT) {
+                if (sn >= TMA_STAGES) mbar_wait(bars + 8 * (TMA_STAGES + sn % TMA_STAGES), ((sn / TMA_STAGES) + 1) & 1);
+                issue(sn);
+            }
+        }
+        if (active) {
+            mbar_wait(bars + 8 * st, (s / TMA_STAGES) & 1);
+            const uint32_t xs = base + 2 * BM * BK * 8 + t * 8;
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                const double xv = lds_f64(xs + kk * 32);
+                neg |= (xv < 0.0);
+                double a[MI], bq[NI];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) a[i] = lds_f64(base + ((offA[i & 1] ^ (kk << 5)) + (i >> 1) * 16 * 128));
+#pragma unroll
+                for (int j = 0; j < NI; ++j) bq[j] = lds_f64(base + ((offB[j & 1] ^ (kk << 5)) + (j >> 1) * 16 * 128)) * xv;
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bq[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * (TMA_STAGES + st));
+        }
+    }
+    if (neg) atomicOr(p.status, ACCBPG_ST_X_NEGATIVE);
+    if (!active) return;
+
+    // partial tile -> workspace; rows and columns follow the permuted mma mapping
+    double* P = p.P + (size_t)split * p.mp * p.mp;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int row = bi * BM + wm * 32 + 16 * (i >> 1) + 2 * g + (i & 1);
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = bj * BN + wn * 32 + 16 * (j >> 1) + 2 * (2 * t + e) + (j & 1);
+                P[(size_t)row * p.mp + col] = acc[i][j][e];
+            }
+        }
+    }
+}
+
 // M[i][j] = M[j][i] = sum_s P[s][i][j]  (i >= j), splits added in index order
-__global__ void __launch_bounds__(256) syrk_reduce_kernel(const double* P, int splits, int m, int mp, double* M) {
+__global__ void __launch_bounds__(256) syrk_reduce_kernel(const double* P, int s_off, int s_diag, int m, int mp,
+                                                          double* M) {
     int j = blockIdx.x * 32 + (threadIdx.x & 31);
     int i = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (i >= m || j > i) return;
+    const int splits = ((i >> 7) == (j >> 7)) ? s_diag : s_off;
     const size_t off = (size_t)i * mp + j, sz = (size_t)mp * mp;
     double s = 0.0;
     for (int k = 0; k < splits; ++k) s += __ldcg(P + k * sz + off);
@@ -180,7 +378,7 @@ __global__ void __launch_bounds__(256) syrk_reduce_kernel(const double* P, int s
 
 // ------------------------------------------------------------------------------------------ K4: gradient
 struct TrmmParams {
-    const double* Linv;   // [mp][mp], zero above the diagonal (identity on the padded diagonal)
+    const double* Linv;   // [mp][mp], zero above the diagonal
     const double* H;
     double* part;         // [nib][npad] partial column sums of squares
     int m, mp, nib;
@@ -200,6 +398,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_colnorm_kernel(TrmmParam
     const int m16 = (p.m + BK - 1) / BK * BK;
     if (kmax > m16) kmax = m16;
     const int KT = kmax / BK;
+    // inside the diagonal block of Linv a warp's 32 rows end at column ib*128 + wm*32 + 31: it stops issuing there
+    // (each sub-partition hosts one warp of every wm, so the four pipes stay evenly loaded)
+    const int klim = ib * BM + wm * 32 + 32;
 
     double acc[MI][NI][2];
 #pragma unroll
@@ -230,13 +431,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_colnorm_kernel(TrmmParam
             cp_async_commit();
         }
         const double* As = smem + (kt % STAGES) * NN_STAGE_DOUBLES;
-        mma_nn_slab(acc, As, As + BM * A_LD, wm, wn, g, t);
+        int k4 = (klim - kt * BK) >> 2;
+        k4 = k4 < 0 ? 0 : (k4 > BK / 4 ? BK / 4 : k4);
+        mma_nn_slab(acc, As, As + BM * A_LD, wm, wn, g, t, k4);
     }
     cp_async_wait<0>();
     __syncthreads();      // pipeline buffers are dead: reuse the front of smem for the column exchange
 
     // epilogue: column sums of squares over this tile's 128 rows, fixed order
-    double* colx = smem;                              // [2][128]
+    double* colx = smem;                              // [4][128]
 #pragma unroll
     for (int j = 0; j < NI; ++j) {
 #pragma unroll
@@ -253,7 +456,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_colnorm_kernel(TrmmParam
     __syncthreads();
     if (tid < BN) {
         int64_t col = j0 + tid;
-        if (col < p.n) p.part[(size_t)ib * p.npad + col] = colx[tid] + colx[BN + tid];
+        if (col < p.n)
+            p.part[(size_t)ib * p.npad + col] = ((colx[tid] + colx[BN + tid]) + colx[2 * BN + tid]) + colx[3 * BN + tid];
     }
 }
 
@@ -269,36 +473,64 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(const double* part, 
 
 // ------------------------------------------------------------------------------------------ host side plan
 struct DoptPlan {
-    int mp, nt, ntri, nib, splits;
-    int64_t kchunk, npad;
+    int mp, nt, n_off, nib;
+    int s_off, s_diag, smax, diag_first;
+    int64_t kchunk_off, kchunk_diag, npad;
     size_t off_P, off_Linv, off_Y, off_part, off_M, off_L, off_W, off_M2, off_W2, total;
 };
 
+// Makespan (in k-slab units) of the SYRK grid under in-order dispatch onto `sms` single-CTA SMs.
+static double syrk_makespan(int n_off, int nt, int64_t ktiles, int s_off, int s_diag, int sms, int* diag_first) {
+    const double ovh = 2.0, diag_cost = 0.75;
+    const double d_off = n_off ? (double)((ktiles + s_off - 1) / s_off) + ovh : 0.0;
+    const double d_diag = (double)((ktiles + s_diag - 1) / s_diag) * diag_cost + ovh;
+    const int c_off = n_off * s_off, c_diag = nt * s_diag;
+    *diag_first = d_diag > d_off;
+    std::vector<double> sm(sms, 0.0);      // min-heap emulated by a linear scan: sms <= a few hundred
+    auto put = [&](int count, double d) {
+        for (int i = 0; i < count; ++i) {
+            int best = 0;
+            for (int q = 1; q < sms; ++q) if (sm[q] < sm[best]) best = q;
+            sm[best] += d;
+        }
+    };
+    if (*diag_first) { put(c_diag, d_diag); put(c_off, d_off); }
+    else             { put(c_off, d_off); put(c_diag, d_diag); }
+    double mx = 0.0;
+    for (double v : sm) mx = v > mx ? v : mx;
+    return mx;
+}
+
 static DoptPlan make_plan(int m, int64_t n, int sm_count) {
+    static std::map<std::tuple<int, int64_t, int>, DoptPlan> cache;
+    auto key = std::make_tuple(m, n, sm_count);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
     DoptPlan pl;
     pl.nt = (m + BM - 1) / BM;
     pl.mp = pl.nt * BM;
-    pl.ntri = pl.nt * (pl.nt + 1) / 2;
+    pl.n_off = pl.nt * (pl.nt - 1) / 2;
     pl.nib = pl.nt;
     pl.npad = (n + 1) / 2 * 2;
-    int64_t ktiles = (n + BK - 1) / BK;
-    int64_t max_splits = ktiles / 64;                 // at least 64 k-slabs (1024 columns) per CTA
+    const int64_t ktiles = (n + BK - 1) / BK;
+    int64_t max_splits = ktiles / 32;                 // at least 32 k-slabs (512 columns) per CTA
     if (max_splits < 1) max_splits = 1;
     if (max_splits > 64) max_splits = 64;
-    int best = 1;
-    double best_eff = 0.0;
-    for (int w = 1; w <= 2; ++w) {
-        int64_t s = (int64_t)sm_count * w / pl.ntri;
-        if (s < 1) s = 1;
-        if (s > max_splits) s = max_splits;
-        int64_t ctas = (int64_t)pl.ntri * s;
-        int64_t waves = (ctas + sm_count - 1) / sm_count;
-        double eff = (double)ctas / (double)(waves * sm_count);
-        if (eff > best_eff + 0.02) { best_eff = eff; best = (int)s; }
+    pl.smax = (int)max_splits;                        // workspace is sized for the largest split count
+    double best = 1e300;
+    pl.s_off = pl.s_diag = 1; pl.diag_first = 0;
+    for (int so = 1; so <= max_splits; ++so) {
+        for (int d = -2; d <= 2; ++d) {
+            int sd = (int)(0.75 * so + 0.5) + d;
+            if (sd < 1 || sd > max_splits) continue;
+            if ((int64_t)(pl.n_off * so + pl.nt * sd) > 6LL * sm_count) continue;
+            int df = 0;
+            double mk = syrk_makespan(pl.n_off, pl.nt, ktiles, so, sd, sm_count, &df);
+            if (mk < best * (1.0 - 1e-9)) { best = mk; pl.s_off = so; pl.s_diag = sd; pl.diag_first = df; }
+        }
     }
-    pl.splits = best;
-    int64_t per = (ktiles + pl.splits - 1) / pl.splits;
-    pl.kchunk = per * BK;
+    pl.kchunk_off = (ktiles + pl.s_off - 1) / pl.s_off * BK;
+    pl.kchunk_diag = (ktiles + pl.s_diag - 1) / pl.s_diag * BK;
     // layout: the m-only buffers first (their offsets do not depend on n_local), then the n-dependent ones
     const size_t mm = ((size_t)m * m * 8 + 255) / 256 * 256;
     size_t a = 0;
@@ -309,9 +541,10 @@ static DoptPlan make_plan(int m, int64_t n, int sm_count) {
     pl.off_W2 = a;   a += mm;
     pl.off_Linv = a; a += (size_t)pl.mp * pl.mp * 8;
     pl.off_Y = a;    a += (size_t)pl.mp * pl.mp * 8;      // running sums of the block forward substitution
-    pl.off_P = a;    a += (size_t)pl.splits * pl.mp * pl.mp * 8;
+    pl.off_P = a;    a += (size_t)pl.smax * pl.mp * pl.mp * 8;
     pl.off_part = a; a += (size_t)pl.nib * pl.npad * 8;
     pl.total = a;
+    cache[key] = pl;
     return pl;
 }
 
@@ -326,6 +559,7 @@ static int ensure_smem_attrs() {
     if (g_attr_done) return ACCBPG_OK;
     ACCBPG_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMAJOR_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMAJOR_SMEM));
+    ACCBPG_CUDA(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(trmm_colnorm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(trmm_colnorm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
     g_attr_done = true;
@@ -333,6 +567,34 @@ static int ensure_smem_attrs() {
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links no libcuda symbol directly)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qr = cudaDriverEntryPointSymbolNotFound;
+        cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &ptr, 12000, cudaEnableDefault, &qr);
+        if (e == cudaSuccess && qr == cudaDriverEntryPointSuccess && ptr) fn = (EncodeTiledFn)ptr;
+        if (getenv("ACCBPG_VERBOSE"))
+            fprintf(stderr, "[accbpg] cuTensorMapEncodeTiled entry point: rc %d, query %d, ptr %p\n", (int)e, (int)qr, ptr);
+    }
+    return fn;
+}
+// 0: cp.async mainloop, 1: TMA mainloop (default when the operands allow it); ACCBPG_SYRK_TMA=0 switches it off
+static bool syrk_tma_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ACCBPG_SYRK_TMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
 
 size_t dopt_linv_offset(int m, int64_t n, int sm_count, int* mp_out) {
     DoptPlan pl = make_plan(m, n, sm_count);
@@ -362,11 +624,45 @@ int accbpg_dopt_gram(void* ctx, void* stream, const double* H, int m, int64_t n,
     DoptPlan pl = make_plan(m, n, c->sm_count);
     SyrkParams p;
     p.H = H; p.x = x; p.P = (double*)((char*)ws + pl.off_P);
-    p.m = m; p.mp = pl.mp; p.splits = pl.splits; p.n = n; p.ldh = ldh; p.kchunk = pl.kchunk;
+    p.m = m; p.mp = pl.mp; p.nt = pl.nt; p.n_off = pl.n_off; p.s_off = pl.s_off; p.s_diag = pl.s_diag;
+    p.diag_first = pl.diag_first; p.n = n; p.ldh = ldh; p.kchunk_off = pl.kchunk_off; p.kchunk_diag = pl.kchunk_diag;
     p.status = c->d_status;
-    dim3 grid(pl.ntri, pl.splits);
+    dim3 grid(pl.n_off * pl.s_off + pl.nt * pl.s_diag);
     bool al = aligned16(H) && aligned16(x) && (ldh % 2 == 0);
-    {
+    bool launched = false;
+    if (al && syrk_tma_enabled() && encode_tiled_fn() && n < (1LL << 31)) {
+        CUtensorMap tmH, tmX;
+        cuuint64_t dimH[2] = {(cuuint64_t)n, (cuuint64_t)m};
+        cuuint64_t strH[1] = {(cuuint64_t)ldh * 8};
+        cuuint32_t boxH[2] = {BK, BM};
+        cuuint32_t one[2] = {1, 1};
+        cuuint64_t dimX[1] = {(cuuint64_t)n};
+        cuuint32_t boxX[1] = {BK};
+        CUresult r1 = encode_tiled_fn()(&tmH, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)H, dimH, strH, boxH, one,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r2 = encode_tiled_fn()(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 1, (void*)x, dimX, strH /* unused for rank 1 */, boxX, one,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        static bool said = false;
+        if (!said && getenv("ACCBPG_VERBOSE")) {
+            said = true;
+            fprintf(stderr, "[accbpg] SYRK: TMA mainloop, encode rc %d %d, grid %u (s_off %d, s_diag %d, diag_first %d)\n", (int)r1,
+                    (int)r2, grid.x, pl.s_off, pl.s_diag, pl.diag_first);
+        }
+        if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) {
+            ProfScope ps(P_SYRK, s);
+            syrk_tma_kernel<<<grid, GEMM_THREADS, TMA_SMEM, s>>>(p, tmH, tmX);
+            launched = true;
+        }
+    }
+    if (!launched) {
+        static bool said2 = false;
+        if (!said2 && getenv("ACCBPG_VERBOSE")) {
+            said2 = true;
+            fprintf(stderr, "[accbpg] SYRK: cp.async mainloop (aligned %d), grid %u (s_off %d, s_diag %d)\n", (int)al, grid.x, pl.s_off,
+                    pl.s_diag);
+        }
         ProfScope ps(P_SYRK, s);
         if (al) syrk_dmma_kernel<true><<<grid, GEMM_THREADS, KMAJOR_SMEM, s>>>(p);
         else    syrk_dmma_kernel<false><<<grid, GEMM_THREADS, KMAJOR_SMEM, s>>>(p);
@@ -375,7 +671,7 @@ int accbpg_dopt_gram(void* ctx, void* stream, const double* H, int m, int64_t n,
     dim3 rg((m + 31) / 32, (m + 7) / 8);
     {
         ProfScope ps(P_SYRK_REDUCE, s);
-        syrk_reduce_kernel<<<rg, 256, 0, s>>>(p.P, pl.splits, m, pl.mp, M);
+        syrk_reduce_kernel<<<rg, 256, 0, s>>>(p.P, pl.s_off, pl.s_diag, m, pl.mp, M);
     }
     ACCBPG_LAUNCHED("syrk_reduce_kernel");
     return ACCBPG_OK;
