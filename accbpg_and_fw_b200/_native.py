@@ -20,6 +20,7 @@ _CTYPES = {
     "double*": ctypes.c_void_p,
     "uint32_t*": ctypes.POINTER(ctypes.c_uint32),
     "int": ctypes.c_int,
+    "int*": ctypes.POINTER(ctypes.c_int),
     "int64_t": ctypes.c_int64,
     "int64_t*": ctypes.POINTER(ctypes.c_int64),
     "uint64_t": ctypes.c_uint64,

@@ -8,6 +8,14 @@ linear_images
     ("linearity shortcuts are allowed as optimisations").  Values agree with the
     direct evaluation to rounding (the tests run both ways); the image of x is re-formed from scratch every
     `reanchor_every` iterations so rounding cannot accumulate.  Set to False to evaluate every point from scratch.
+
+pipeline
+    ABPG, ABDA and BPG without line search take no data-dependent decision inside an iteration except the stopping
+    test, so the drivers enqueue iteration k+1 before the scalars of iteration k have been read back (deferred read,
+    accbpg_ctx_read_async): the GPU never idles between iterations.  Recorded values and the returned iterate are
+    those of the synchronous loop; when the stopping test fires, the one iteration enqueued beyond it is discarded.
+    Switched off automatically with verbose=True or restart=True.
 """
 linear_images = True
 reanchor_every = 64
+pipeline = True

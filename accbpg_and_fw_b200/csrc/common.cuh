@@ -29,7 +29,12 @@ struct Ctx {
     int coop_blocks_burg;   // co-resident grid size for the Burg-simplex kernel
     cudaStream_t side;      // side stream: a second latency-bound chain (Cholesky) runs next to the main one
     cudaEvent_t ev_fork, ev_join;
+    // deferred reads (accbpg_ctx_read_async / _wait): a ring of pinned buffers, one event each
+    double* h_ring;         // kReadRing * (kSlots + 1) doubles; the last double of a row carries the status word
+    cudaEvent_t ring_ev[8];
+    int ring_next;
 };
+constexpr int kReadRing = 8;
 
 extern thread_local char g_err[512];
 extern unsigned long long g_launches;

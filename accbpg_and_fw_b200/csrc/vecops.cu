@@ -485,6 +485,9 @@ int accbpg_ctx_create(void** out) {
     ACCBPG_CUDA(cudaMemset(c->d_counter, 0, 256));
     ACCBPG_CUDA(cudaMallocHost(&c->h_slots, kSlots * sizeof(double)));
     ACCBPG_CUDA(cudaMallocHost(&c->h_status, 64));
+    ACCBPG_CUDA(cudaMallocHost(&c->h_ring, (size_t)kReadRing * (kSlots + 1) * sizeof(double)));
+    for (int i = 0; i < kReadRing; ++i) ACCBPG_CUDA(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
+    c->ring_next = 0;
     ACCBPG_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     ACCBPG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     ACCBPG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -526,6 +529,34 @@ int accbpg_ctx_read(void* ctx, void* stream, const double* d_src, int count, dou
     ACCBPG_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < count; ++i) h_out[i] = c->h_slots[i];
     if (h_status) *h_status = *c->h_status;
+    return ACCBPG_OK;
+}
+
+int accbpg_ctx_read_async(void* ctx, void* stream, const double* d_src, int count, int* ticket) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !ticket) return arg_err("ctx_read_async: NULL pointer");
+    if (count < 0 || count > kSlots) return arg_err("ctx_read_async: count must be in [0, 256]");
+    if (count > 0 && !d_src) return arg_err("ctx_read_async: NULL pointer");
+    const int t = c->ring_next;
+    c->ring_next = (t + 1) % kReadRing;
+    double* row = c->h_ring + (size_t)t * (kSlots + 1);
+    if (count > 0) ACCBPG_CUDA(cudaMemcpyAsync(row, d_src, count * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ACCBPG_CUDA(cudaMemcpyAsync(row + kSlots, c->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ACCBPG_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(uint32_t), s));
+    ACCBPG_CUDA(cudaEventRecord(c->ring_ev[t], s));
+    *ticket = t;
+    return ACCBPG_OK;
+}
+int accbpg_ctx_read_wait(void* ctx, int ticket, int count, double* h_out, uint32_t* h_status) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return arg_err("ctx is NULL");
+    if (ticket < 0 || ticket >= kReadRing) return arg_err("ctx_read_wait: bad ticket");
+    if (count < 0 || count > kSlots || (count > 0 && !h_out)) return arg_err("ctx_read_wait: count / NULL pointer");
+    ACCBPG_CUDA(cudaEventSynchronize(c->ring_ev[ticket]));
+    const double* row = c->h_ring + (size_t)ticket * (kSlots + 1);
+    for (int i = 0; i < count; ++i) h_out[i] = row[i];
+    if (h_status) *h_status = *reinterpret_cast<const uint32_t*>(row + kSlots);
     return ACCBPG_OK;
 }
 

@@ -137,6 +137,17 @@ class _Loop:
     def fetch(self):
         return self.rt.read(0, 7)          # S_F .. S_PSI and S_AUX0 in one pinned read
 
+    def fetch_async(self):
+        """Deferred fetch: the copy is enqueued now, `fetch_wait(ticket)` collects it later."""
+        return self.rt.read_async(0, 7)
+
+    def fetch_wait(self, ticket):
+        return self.rt.read_wait(ticket, 7)
+
+    def pipeline_depth(self, verbose, restart=False):
+        """How many iterations may be enqueued beyond the one whose scalars the host has seen (config.pipeline)."""
+        return 1 if (config.pipeline and not verbose and not restart) else 0
+
     def psi(self, vals):
         return vals[self.rt.S_PSI] if self.h.has_psi else 0
 
@@ -159,6 +170,32 @@ def BPG(f, h, L, x0, maxitrs, epsilon=1e-14, linesearch=True, ls_ratio=1.2,
     Ls = np.ones(maxitrs) * L
     T = np.zeros(maxitrs)
     x = lp.x0
+    if not linesearch and lp.pipeline_depth(verbose):
+        # no decision inside an iteration: iteration k+1 is enqueued before F[k] has come back
+        pend = None                      # (k, ticket)
+        stop = None
+        for k in range(maxitrs):
+            g = lp.enq_fg(x, rt.S_F)
+            lp.enq_psi(x)
+            ticket = lp.fetch_async()
+            x_next = lp.div_prox(x, g, L)
+            if pend is not None:
+                pk = pend[0]
+                vals = lp.fetch_wait(pend[1])
+                F[pk] = vals[rt.S_F] + lp.psi(vals)
+                T[pk] = lp.now()
+                if pk > 0 and abs(F[pk] - F[pk - 1]) < epsilon:
+                    stop = pk            # x currently holds the iterate produced by iteration pk
+                    break
+            pend = (k, ticket)
+            x = x_next
+        if stop is None:
+            pk = pend[0]
+            vals = lp.fetch_wait(pend[1])
+            F[pk] = vals[rt.S_F] + lp.psi(vals)
+            T[pk] = lp.now()
+            stop = pk
+        return lp.result(x), F[0:stop + 1], Ls[0:stop + 1], T[0:stop + 1]
     for k in range(maxitrs):
         g = lp.enq_fg(x, rt.S_F)
         lp.enq_psi(x)
@@ -216,10 +253,13 @@ def ABPG(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=False,
     Iz = Ix
     theta = 1.0
     kk = 0
+    depth = lp.pipeline_depth(verbose, restart)
+    pend = None                  # (k, ticket, theta_k) of the iteration whose scalars are still in flight
     for k in range(maxitrs):
         # F[k] = f(x_k) is only recorded (and used by restart rule 'f' at the end of the iteration), so it is
         # evaluated together with the gradient at y_k and fetched with the divergences: one host sync per iteration.
-        T[k] = lp.now()
+        if not depth or k == 0:
+            T[k] = lp.now()          # pipelined: T[k] is stamped when iteration k-1's scalars arrive
         z_1, x_1 = z, x
         Iz_1, Ix_1 = Iz, Ix
         if theta_eq and kk > 0:
@@ -236,6 +276,21 @@ def ABPG(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=False,
         Ix = lp.img_refresh(k, x, lp.img_combo(1 - theta, Ix_1, theta, Iz))
         lp.enq_div(x, y, rt.S_DXY)
         lp.enq_div(z, z_1, rt.S_DZZ)
+        if depth:
+            # deferred read: iteration k+1 is enqueued before these scalars are looked at; when the stopping test of
+            # iteration k-1 fires, the iteration just enqueued is dropped and the iterate it started from is returned
+            ticket = lp.fetch_async()
+            if pend is not None:
+                pk, ptheta = pend[0], pend[2]
+                vals = lp.fetch_wait(pend[1])
+                T[pk + 1] = lp.now()
+                F[pk] = vals[rt.S_F] + lp.psi(vals)
+                G[pk] = vals[rt.S_DXY] / vals[rt.S_DZZ] / ptheta ** gamma
+                if vals[rt.S_DZZ] < epsilon:
+                    return lp.result(x_1), F[0:pk + 1], G[0:pk + 1], T[0:pk + 1]
+            pend = (k, ticket, theta)
+            kk += 1
+            continue
         vals = lp.fetch()
         F[k] = vals[rt.S_F] + lp.psi(vals)
         dxy, dzz = vals[rt.S_DXY], vals[rt.S_DZZ]
@@ -253,6 +308,11 @@ def ABPG(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=False,
                 Iz = Ix
         if dzz < epsilon:
             break
+    if depth and pend is not None:
+        pk, ptheta = pend[0], pend[2]
+        vals = lp.fetch_wait(pend[1])
+        F[pk] = vals[rt.S_F] + lp.psi(vals)
+        G[pk] = vals[rt.S_DXY] / vals[rt.S_DZZ] / ptheta ** gamma
     return lp.result(x), F[0:k + 1], G[0:k + 1], T[0:k + 1]
 
 
@@ -445,8 +505,11 @@ def ABDA(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=True,
     kk = 0
     gavg = rt.empty(lp.n).zero_()
     csum = 0
+    depth = lp.pipeline_depth(verbose)
+    pend = None
     for k in range(maxitrs):
-        T[k] = lp.now()
+        if not depth or k == 0:
+            T[k] = lp.now()
         z_1, x_1 = z, x
         if theta_eq and kk > 0:
             theta = solve_theta(theta, gamma)
@@ -469,6 +532,19 @@ def ABDA(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=True,
         Ix = lp.img_refresh(k, x, lp.img_combo(1 - theta, Ix_1, theta, Iz))
         lp.enq_div(x, y, rt.S_DXY)
         lp.enq_div(z, z_1, rt.S_DZZ)
+        if depth:
+            ticket = lp.fetch_async()
+            if pend is not None:
+                pk, ptheta = pend[0], pend[2]
+                vals = lp.fetch_wait(pend[1])
+                T[pk + 1] = lp.now()
+                F[pk] = vals[rt.S_F] + lp.psi(vals)
+                G[pk] = vals[rt.S_DXY] / vals[rt.S_DZZ] / ptheta ** gamma
+                if vals[rt.S_DZZ] < epsilon:
+                    return lp.result(x_1), F[0:pk + 1], G[0:pk + 1], T[0:pk + 1]
+            pend = (k, ticket, theta)
+            kk += 1
+            continue
         vals = lp.fetch()
         F[k] = vals[rt.S_F] + lp.psi(vals)
         dxy, dzz = vals[rt.S_DXY], vals[rt.S_DZZ]
@@ -480,4 +556,9 @@ def ABDA(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, theta_eq=True,
         kk += 1
         if dzz < epsilon:
             break
+    if depth and pend is not None:
+        pk, ptheta = pend[0], pend[2]
+        vals = lp.fetch_wait(pend[1])
+        F[pk] = vals[rt.S_F] + lp.psi(vals)
+        G[pk] = vals[rt.S_DXY] / vals[rt.S_DZZ] / ptheta ** gamma
     return lp.result(x), F[0:k + 1], G[0:k + 1], T[0:k + 1]

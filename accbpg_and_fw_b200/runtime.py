@@ -88,6 +88,20 @@ class Runtime:
                                       ctypes.byref(self._hstat)))
         return self._hbuf[0:count], self._hstat.value
 
+    def read_async(self, first, count):
+        """Enqueue the fetch of scal[first:first+count] behind the work already on the stream; returns a ticket."""
+        t = ctypes.c_int(0)
+        nat.check(lib.accbpg_ctx_read_async(self.ctx, self.stream, self.slot(first), count, ctypes.byref(t)))
+        return t.value
+
+    def read_wait(self, ticket, count):
+        """Wait for a deferred fetch; raises on a status bit like read()."""
+        nat.check(lib.accbpg_ctx_read_wait(self.ctx, ticket, count, self._hbuf_addr, ctypes.byref(self._hstat)))
+        st = self._hstat.value
+        if st:
+            self.raise_status(st)
+        return self._hbuf[0:count]
+
     @staticmethod
     def raise_status(st):
         for name, exc, msg in _STATUS_ERRORS:

@@ -79,6 +79,14 @@ int     accbpg_ctx_sm_count(void* ctx);
 int     accbpg_ctx_read(void* ctx, void* stream, const double* d_src, int count,
                         double* h_out, uint32_t* h_status);
 
+/* Deferred form of accbpg_ctx_read: _async enqueues the copy (and the read-and-clear of the status word) behind the
+ * work already on the stream and returns a ticket; _wait blocks until that copy has landed.  The drivers use it to
+ * enqueue iteration k+1 while iteration k is still running, so the GPU never waits for the host between iterations.
+ * At most ACCBPG_READ_RING tickets may be outstanding; tickets are reused round-robin. */
+#define ACCBPG_READ_RING 8
+int     accbpg_ctx_read_async(void* ctx, void* stream, const double* d_src, int count, int* ticket);
+int     accbpg_ctx_read_wait(void* ctx, int ticket, int count, double* h_out, uint32_t* h_status);
+
 /* ---- iterate arithmetic inlined in the drivers (accbpg/algorithms.py:147,150,
  *      243,250,369,374,478,483; np.dot at :53,168,260,279,387,406;
  *      algorithms_fw.py:39,231) ---------------------------------------- */

@@ -36,7 +36,11 @@ def test_library_is_sm100a_with_dmma():
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN6accbpg16syrk_dmma_kernelILb1EEEvNS_10SyrkParamsE",
                            nat.LIB_PATH], capture_output=True, text=True).stdout
-    assert sass.count("DMMA.8x8x4") >= 128 and "LDGSTS" in sass
+    assert sass.count("DMMA.8x8x4") >= 64 and "LDGSTS" in sass           # cp.async fallback mainloop
+    tma = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN6accbpg15syrk_tma_kernelENS_10SyrkParamsE14CUtensorMap_stS1_",
+                          nat.LIB_PATH], capture_output=True, text=True).stdout
+    # TMA mainloop: tensor-map bulk loads signalled on mbarriers feed the FP64 tensor pipe
+    assert tma.count("DMMA.8x8x4") >= 64 and "UTMALDG" in tma and "SYNCS" in tma
 
 
 def test_no_cpu_fallback_without_gpu():
