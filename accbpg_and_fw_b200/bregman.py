@@ -31,7 +31,11 @@ class LegendreFunction:
             self._rt = Runtime.get(self._device)
         return self._rt
 
+    _defer_reduce = False      # set by the drivers: partial scalars are summed over the ranks once per fetch
+
     def _reduce(self, slot, count=1):
+        if self._defer_reduce and slot < self.rt.S_TMP:
+            return
         if self.shard is not None and self.shard.world > 1:
             self.shard.sum_(self.rt.scal[slot:slot + count])
 
@@ -192,35 +196,24 @@ class BurgEntropySimplex(BurgEntropy):
             nat.check(lib.accbpg_burg_simplex_prox(rt.ctx, rt.stream, n, yp, gd.data_ptr(), L, float(self.eps),
                                                    out.data_ptr(), info))
             return
-        # column-sharded: same recurrence, scalars all-reduced between the three local kernels
+        # column-sharded: every rank gathers all slices of gg = (g [+ L/y]) / L (padding +inf) and replays the whole
+        # recurrence on the gathered vector in one cooperative kernel, so there is one collective per prox call, no
+        # host round trip, and the multiplier c is bit-identical on every rank (and independent of the sharding)
         sh = self.shard
+        key = (n, sh.width, sh.world)
+        if getattr(self, "_gg_key", None) != key:
+            self._gg_key = key
+            self._gg_loc = torch.full((sh.width,), float("inf"), dtype=torch.float64, device=rt.device)
+            self._gg_all = torch.empty(sh.width * sh.world, dtype=torch.float64, device=rt.device)
+        gg = self._gg_loc
         s0 = rt.S_TMP + 8
-        gg = rt.empty(n)
         nat.check(lib.accbpg_burg_simplex_prepare(rt.ctx, rt.stream, n, yp, gd.data_ptr(), L, gg.data_ptr(),
                                                   rt.slot(s0)))
-        sh.min_(rt.scal[s0:s0 + 1])
-        cmin = -rt.read(s0, 1)[0]
-        c = cmin + 1
-
-        def sums(cc):
-            nat.check(lib.accbpg_burg_simplex_sums(rt.ctx, rt.stream, n, gg.data_ptr(), cc, rt.slot(s0)))
-            sh.sum_(rt.scal[s0:s0 + 2])
-            v = rt.read(s0, 2)
-            return v[0], v[1]
-
-        s1, s2 = sums(c)
-        while s1 - 1 < 0:                         # functions.py:345-346
-            c = (cmin + c) / 2.0
-            s1, s2 = sums(c)
-        fc = s1 - 1
-        while abs(fc) > self.eps:                 # functions.py:349-354
-            fpc = s2
-            if (c - (c - fc / fpc)) == 0:
-                break
-            c = c - fc / fpc
-            s1, s2 = sums(c)
-            fc = s1 - 1
-        nat.check(lib.accbpg_burg_simplex_finish(rt.ctx, rt.stream, n, gg.data_ptr(), c, out.data_ptr()))
+        sh.all_gather_equal(self._gg_all, gg)
+        info = rt.slot(rt.S_AUX1)
+        nat.check(lib.accbpg_burg_simplex_root(rt.ctx, rt.stream, sh.width * sh.world, self._gg_all.data_ptr(),
+                                               float(self.eps), info))
+        nat.check(lib.accbpg_burg_simplex_finish_dev(rt.ctx, rt.stream, n, gg.data_ptr(), info + 16, out.data_ptr()))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256, 1) chol_inv_step_kernel(CholStep p) {
     // ---- one CTA publishes the diagonal results: the last one, whose own job is the lightest
     if (blockIdx.x == gridDim.x - 1) {
         if (p.L) smem_to_global(sD, p.L, m, j0, j0, m, m, tid);
-        if (p.want_inv) smem_to_global(sX, p.Linv, p.mp, j0, j0, p.mp, p.mp, tid);
+        if (p.want_inv) smem_to_global(sX, p.Linv, p.mp, j0, j0, m, m, tid);      // the padding of Linv stays zero
         if (tid == 0) {
             double tot = (J == 0 ? 0.0 : p.logacc[0]) + logsum;
             p.logacc[0] = tot;
@@ -539,7 +539,7 @@ static int ensure_attrs() {
 
 // ------------------------------------------------------------------------------------------ host entry point
 // M (m x m, symmetric, only read) -> d_out[0] = -log det M;  L (may be NULL) <- lower factor;  when want_inv:
-// Linv (mp x mp, ld mp) <- L^{-1}, zero above the diagonal and on rows / columns >= 64*ceil(m/64).
+// Linv (mp x mp, ld mp) <- L^{-1}, zero above the diagonal and on rows / columns >= m.
 // W: m x m scratch (trailing matrix), Y: mp x mp scratch (running sums), acc: device scalar.
 // Launches are chained with programmatic dependent launch: launch J+1 is resident and past its prologue when
 // launch J retires, so the ~4 us launch gap drops out of the critical path.

@@ -102,27 +102,32 @@ __device__ __forceinline__ void load_nmajor_slab(double* dst, const double* src,
     }
 }
 
-// one k-slab of the "NN" product: acc += A_s[128 x 16] * B_s[16 x 128]; only the first k4_count 4-wide steps of the
-// slab are issued (the triangular GEMM stops each warp at its own diagonal).  With four warps per sub-partition the
-// fragment loads of one warp hide under the DMMAs of the others: no register double buffering.
+// one k-slab of the "NN" product: acc += A_s[128 x 16] * B_s[16 x 128], first K4 4-wide steps of the slab only (the
+// triangular GEMM stops each warp at its own diagonal).  With four warps per sub-partition the fragment loads of one
+// warp hide under the DMMAs of the others: no register double buffering.
+template <int K4>
+__device__ __forceinline__ void mma_nn_steps(double (&acc)[MI][NI][2], const double* ap, const double* bp) {
+#pragma unroll
+    for (int kk = 0; kk < K4; ++kk) {
+        double a[MI], b[NI];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) a[i] = ap[i * 8 * A_LD + kk * 4];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) b[j] = bp[kk * 4 * BT_LD + j * 8];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
 __device__ __forceinline__ void mma_nn_slab(double (&acc)[MI][NI][2], const double* As, const double* Bs, int wm, int wn,
                                             int g, int t, int k4_count) {
     const double* ap = As + (wm * 32 + g) * A_LD + t;
     const double* bp = Bs + t * BT_LD + wn * 32 + g;
-#pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
-        if (kk < k4_count) {
-            double a[MI], b[NI];
-#pragma unroll
-            for (int i = 0; i < MI; ++i) a[i] = ap[i * 8 * A_LD + kk * 4];
-#pragma unroll
-            for (int j = 0; j < NI; ++j) b[j] = bp[kk * 4 * BT_LD + j * 8];
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
-    }
+    if (k4_count >= BK / 4) mma_nn_steps<BK / 4>(acc, ap, bp);      // the common case, fully unrolled
+    else if (k4_count == 3) mma_nn_steps<3>(acc, ap, bp);
+    else if (k4_count == 2) mma_nn_steps<2>(acc, ap, bp);
+    else if (k4_count == 1) mma_nn_steps<1>(acc, ap, bp);
 }
 #endif  // __CUDACC__
 

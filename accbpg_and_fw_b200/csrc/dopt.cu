@@ -461,6 +461,151 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_colnorm_kernel(TrmmParam
     }
 }
 
+// ------------------------------------------------------------------------------------------ K4, TMA mainloop
+// Same tile and triangular stop as trmm_colnorm_kernel.  A (rows of Linv) arrives as one swizzled 2-D TMA box per
+// k-slab, read with the permuted row mapping of syrk_tma_kernel (the column sums do not care which row is which);
+// B (16 rows of the H panel, 1 KB each) arrives as sixteen 1-D bulk copies into rows padded to BT_LD doubles, so the
+// B fragments keep the conflict-free padded addressing.  Rows k >= m of the last slab are not copied: Linv is zero
+// in those columns, so whatever finite values the (zero-initialised) stage holds there contribute nothing.
+constexpr int TRT_STAGES = 6;
+constexpr int TRT_PREFETCH = 4;
+constexpr int TRT_A_BYTES = BM * BK * 8;                                  // 16 KB, 1024-byte aligned
+constexpr int TRT_B_BYTES = ((BK * BT_LD * 8 + 1023) / 1024) * 1024;      // 16 x 132 doubles, padded to 17 KB
+constexpr int TRT_STAGE_BYTES = TRT_A_BYTES + TRT_B_BYTES;
+constexpr int TRT_SMEM = TRT_STAGES * TRT_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int K4>
+__device__ __forceinline__ void trmm_tma_slab(double (&acc)[MI][NI][2], uint32_t base, const uint32_t (&offA)[2],
+                                              uint32_t offB) {
+#pragma unroll
+    for (int kk = 0; kk < K4; ++kk) {
+        double a[MI], bq[NI];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) a[i] = lds_f64(base + ((offA[i & 1] ^ (kk << 5)) + (i >> 1) * 16 * 128));
+#pragma unroll
+        for (int j = 0; j < NI; ++j) bq[j] = lds_f64(base + offB + (kk * 4 * BT_LD + j * 8) * 8);
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bq[j]);
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+trmm_tma_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem0 = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
+    unsigned char* smem_gen = smem_raw + (smem0 - (uint32_t)__cvta_generic_to_shared(smem_raw));
+    const uint32_t bars = smem0 + TRT_STAGES * TRT_STAGE_BYTES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int ib = p.nib - 1 - blockIdx.x;            // heavy row blocks first
+    const int64_t j0 = (int64_t)blockIdx.y * BN;
+    int kmax = (ib + 1) * BM;
+    const int m16 = (p.m + BK - 1) / BK * BK;
+    if (kmax > m16) kmax = m16;
+    const int KT = kmax / BK;
+    const int klim = ib * BM + wm * 32 + 32;          // this warp's rows end at this column of Linv
+    int64_t ncols = p.n - j0;                         // valid columns of the panel (even: the aligned path only)
+    if (ncols > BN) ncols = BN;
+    const uint32_t row_bytes = (uint32_t)ncols * 8;
+
+    // zero the B regions once (see above), then set up the barriers
+    for (int st = 0; st < TRT_STAGES; ++st) {
+        double* bz = reinterpret_cast<double*>(smem_gen + st * TRT_STAGE_BYTES + TRT_A_BYTES);
+        for (int e = tid; e < BK * BT_LD; e += GEMM_THREADS) bz[e] = 0.0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < TRT_STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (TRT_STAGES + s), GEMM_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy zero fill before async-proxy writes
+    __syncthreads();
+
+    auto issue = [&](int s) {
+        const int st = s % TRT_STAGES;
+        const uint32_t base = smem0 + st * TRT_STAGE_BYTES, full = bars + 8 * st;
+        const int k0 = s * BK;
+        int rows = p.m - k0;
+        rows = rows > BK ? BK : rows;
+        mbar_arrive_expect_tx(full, TRT_A_BYTES + (uint32_t)rows * row_bytes);
+        tma_load_2d(base, &tmL, k0, ib * BM, full);
+        const double* src = p.H + (int64_t)k0 * p.ldh + j0;
+        for (int r = 0; r < rows; ++r)
+            bulk_load_1d(base + TRT_A_BYTES + r * BT_LD * 8, src + (int64_t)r * p.ldh, row_bytes, full);
+    };
+    if (tid == 0) {
+        const int pre = KT < TRT_PREFETCH ? KT : TRT_PREFETCH;
+        for (int s = 0; s < pre; ++s) issue(s);
+    }
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    uint32_t offA[2];
+#pragma unroll
+    for (int pq = 0; pq < 2; ++pq) {
+        const int ra = wm * 32 + 2 * g + pq;
+        offA[pq] = ra * 128 + ((((t >> 1) ^ (ra & 7))) << 4) + (t & 1) * 8;
+    }
+    const uint32_t offB = TRT_A_BYTES + (t * BT_LD + wn * 32 + g) * 8;
+
+    for (int s = 0; s < KT; ++s) {
+        const int st = s % TRT_STAGES;
+        const uint32_t base = smem0 + st * TRT_STAGE_BYTES;
+        if (tid == 0) {
+            const int sn = s + TRT_PREFETCH;
+            if (sn < KT) {
+                if (sn >= TRT_STAGES) mbar_wait(bars + 8 * (TRT_STAGES + sn % TRT_STAGES), ((sn / TRT_STAGES) + 1) & 1);
+                issue(sn);
+            }
+        }
+        mbar_wait(bars + 8 * st, (s / TRT_STAGES) & 1);
+        int k4 = (klim - s * BK) >> 2;
+        k4 = k4 < 0 ? 0 : (k4 > BK / 4 ? BK / 4 : k4);
+        if (k4 == BK / 4) trmm_tma_slab<BK / 4>(acc, base, offA, offB);       // the common case, fully unrolled
+        else if (k4 == 3) trmm_tma_slab<3>(acc, base, offA, offB);
+        else if (k4 == 2) trmm_tma_slab<2>(acc, base, offA, offB);
+        else if (k4 == 1) trmm_tma_slab<1>(acc, base, offA, offB);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * (TRT_STAGES + st));
+    }
+    __syncthreads();      // every stage has been consumed: reuse the front of smem for the column exchange
+
+    double* colx = reinterpret_cast<double*>(smem_gen);      // [4][128]
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double sq = 0.0;
+#pragma unroll
+            for (int i = 0; i < MI; ++i) sq = fma(acc[i][j][e], acc[i][j][e], sq);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+            if (g == 0) colx[wm * BN + wn * 32 + j * 8 + 2 * t + e] = sq;
+        }
+    }
+    __syncthreads();
+    if (tid < BN) {
+        int64_t col = j0 + tid;
+        if (col < p.n)
+            p.part[(size_t)ib * p.npad + col] = ((colx[tid] + colx[BN + tid]) + colx[2 * BN + tid]) + colx[3 * BN + tid];
+    }
+}
+
 __global__ void __launch_bounds__(256) grad_finalize_kernel(const double* part, int nib, int64_t npad, int64_t n,
                                                             double* g) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -560,6 +705,7 @@ static int ensure_smem_attrs() {
     ACCBPG_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMAJOR_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMAJOR_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
+    ACCBPG_CUDA(cudaFuncSetAttribute(trmm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRT_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(trmm_colnorm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(trmm_colnorm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
     g_attr_done = true;
@@ -709,7 +855,23 @@ int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n,
     if (npanels > 65535) return arg_err("dopt_grad: n_local too large for one launch (max 65535*128 columns)");
     dim3 grid(pl.nib, (unsigned)npanels);
     bool al = aligned16(H) && (ldh % 2 == 0);
-    {
+    bool launched = false;
+    if (al && (n % 2 == 0) && syrk_tma_enabled() && encode_tiled_fn()) {
+        CUtensorMap tmL;
+        cuuint64_t dimL[2] = {(cuuint64_t)pl.mp, (cuuint64_t)pl.mp};
+        cuuint64_t strL[1] = {(cuuint64_t)pl.mp * 8};
+        cuuint32_t boxL[2] = {BK, BM};
+        cuuint32_t one[2] = {1, 1};
+        CUresult r1 = encode_tiled_fn()(&tmL, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)Linv, dimL, strL, boxL, one,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r1 == CUDA_SUCCESS) {
+            ProfScope ps(P_TRMM, s);
+            trmm_tma_kernel<<<grid, GEMM_THREADS, TRT_SMEM, s>>>(p, tmL);
+            launched = true;
+        }
+    }
+    if (!launched) {
         ProfScope ps(P_TRMM, s);
         if (al) trmm_colnorm_kernel<true><<<grid, GEMM_THREADS, NN_SMEM, s>>>(p);
         else    trmm_colnorm_kernel<false><<<grid, GEMM_THREADS, NN_SMEM, s>>>(p);

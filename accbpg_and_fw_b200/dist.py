@@ -23,6 +23,7 @@ class ColumnShard:
         self.offsets = self.partition(self.n, self.world)
         self.lo, self.hi = self.offsets[self.rank], self.offsets[self.rank + 1]
         self.n_local = self.hi - self.lo
+        self.width = max(self.offsets[i + 1] - self.offsets[i] for i in range(self.world))
 
     @staticmethod
     def partition(n, world):
@@ -59,6 +60,18 @@ class ColumnShard:
         bufs = [torch.empty_like(pad) for _ in range(self.world)]
         dist.all_gather(bufs, pad, group=self.group)
         return torch.cat([bufs[i][: self.offsets[i + 1] - self.offsets[i]] for i in range(self.world)])
+
+    def all_gather_equal(self, out, t):
+        """out[r*len(t):(r+1)*len(t)] = rank r's t (every rank passes the same length): one collective."""
+        if self.world == 1:
+            out.copy_(t)
+            return out
+        if t.is_cuda:
+            dist.all_gather_into_tensor(out, t, group=self.group)
+        else:                                   # gloo (CPU tests)
+            bufs = list(out.view(self.world, -1).unbind(0))
+            dist.all_gather(bufs, t, group=self.group)
+        return out
 
     # ---- collectives ----------------------------------------------------------------------
     def sum_(self, t):

@@ -45,6 +45,10 @@ class _Loop:
         # carry the objective's linear image (M(x) for D-opt, A x for Poisson / KL) along with the iterates
         self.lin = bool(config.linear_images and getattr(f, "_lin_capable", False))
         self.reanchor = max(int(config.reanchor_every), 1)
+        # column-sharded runs: the partial scalars of a trip (divergences, dot product, Psi) are summed over the
+        # ranks by ONE all-reduce at fetch time instead of one per scalar
+        self.sharded = self.shard is not None and self.shard.world > 1
+        h._defer_reduce = self.sharded
 
     # ---- linear images (all no-ops returning None when the switch is off) -----------------------------------
     def img(self, x):
@@ -128,17 +132,22 @@ class _Loop:
         rt = self.rt
         nat.check(lib.accbpg_vec_dot_diff(rt.ctx, rt.stream, self.n, g.data_ptr(), a.data_ptr(), b.data_ptr(),
                                           rt.slot(rt.S_DOT)))
-        if self.shard is not None and self.shard.world > 1:
-            self.shard.sum_(rt.scal[rt.S_DOT:rt.S_DOT + 1])
 
     def enq_div(self, x, y, slot):
         self.h._enq_divergence(x, y, slot)
 
+    def _sum_partials(self):
+        if self.sharded:
+            rt = self.rt
+            self.shard.sum_(rt.scal[rt.S_DXY:rt.S_PSI + 1])      # S_DXY, S_DZZ, S_DOT, S_PSI are per-rank partials
+
     def fetch(self):
+        self._sum_partials()
         return self.rt.read(0, 7)          # S_F .. S_PSI and S_AUX0 in one pinned read
 
     def fetch_async(self):
         """Deferred fetch: the copy is enqueued now, `fetch_wait(ticket)` collects it later."""
+        self._sum_partials()
         return self.rt.read_async(0, 7)
 
     def fetch_wait(self, ticket):
