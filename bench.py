@@ -289,14 +289,33 @@ def native_arm(args, rank, local_rank, world):
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------
     syrk = kern.get("syrk_dmma_kernel")
     roof = None
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+    except Exception:
+        pass
     if syrk:
         flops = float(m) * m * n                     # algorithmic SYRK count of SURVEY 8(d): m^2 n per launch
         tf = flops / (syrk["ms_avg"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "syrk_dmma_kernel (FP64 DMMA.8x8x4)", "achieved": tf, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": tf / fp64_peak, "traffic": None,
+        tr = traffic.get("syrk_kernel", {})
+        roof = {"bound": "tensor", "kernel": "syrk_tma_kernel (FP64 DMMA.8x8x4 fed by a TMA + mbarrier pipeline)",
+                "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+                "algorithmic_bytes_per_launch": 8 * m * n,
                 "flops_per_launch": flops, "ms_avg": syrk["ms_avg"], "launches": syrk["launches"],
                 "peak_source": "torch.matmul float64 8192^3 burst measured in this run "
-                               "(MEASURED_PEAKS.json records no FP64 figure)"}
+                               "(MEASURED_PEAKS.json records no FP64 figure); the bare DMMA issue rate measured by "
+                               "tools/pipe_probe.cu on this pool is 37.1 TFLOP/s"}
+    trmm = kern.get("trmm_colnorm_kernel")
+    if trmm:
+        flops = float(m) * m * n                     # triangular solve-as-GEMM: m^2 n per launch
+        tf = flops / (trmm["ms_avg"] * 1e-3) / 1e12
+        extra_roof = {"bound": "tensor", "kernel": "trmm_tma_kernel (L^-1 H with fused column norms)", "achieved": tf,
+                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                      "traffic": traffic.get("trmm_colnorm_kernel", {}).get("dram_bytes_per_launch"),
+                      "flops_per_launch": flops, "ms_avg": trmm["ms_avg"], "launches": trmm["launches"]}
+    else:
+        extra_roof = None
     step_ms = {k: v["ms_total"] / args.steps for k, v in kern.items()}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -------------------------------
@@ -318,10 +337,12 @@ def native_arm(args, rank, local_rank, world):
             "config": {"workload": f"D-opt {m}x{n * world} (H=randn, seed 1+rank per {m}x{n} slab), ABPG gamma=2, "
                                    f"x0=1/n, L=1, BurgEntropySimplex",
                        "l2": "H slab is 200 MB per GPU (> 126 MB L2); no flush needed",
-                       "calls_per_step": "1 f(x) + 1 grad f(y) + 1 div_prox_map + 2 axpby + 2 divergence",
+                       "calls_per_step": "1 f(x) + 1 grad f(y) + 1 div_prox_map + 2 axpby + 2 divergence "
+                                         "(f(x_k), f(y_k) are evaluated from Gram matrices carried along the "
+                                         "iterates, so one SYRK per iteration: accbpg_and_fw_b200/config.py)",
                        "timing": "CUDA events on the launch stream around the K-iteration solve, max over ranks"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "kernel_ms_per_step": step_ms, "extra": extra,
+            "kernel_ms_per_step": step_ms, "extra": extra, "roofline_trmm": extra_roof,
             "it_per_s_from_T": (len(T) - 1) / (T[-1] - T[0]) if len(T) > 1 else None,
         }
         print(json.dumps(line), flush=True)
