@@ -58,82 +58,90 @@ __device__ __forceinline__ void fw_block_argmin(double& v, long long& i, double*
     }
 }
 
-// i = argmax w (first occurrence)            D_opt_alg.py:59 / :145
-__global__ void __launch_bounds__(FW_THREADS) fw_argmax_kernel(int64_t n, const double* __restrict__ w,
-                                                               double* partials, long long* ipartials,
-                                                               unsigned int* counter, double* ctrl) {
-    __shared__ double shv[32];
-    __shared__ long long shi[32];
-    __shared__ bool is_last;
-    if (ld_cg(&ctrl[C_STOP]) != 0.0) return;
-    double v = FW_INF;
-    long long idx = 0x7fffffffffffffffLL;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        double wi = -w[i];
-        if (wi < v) { v = wi; idx = i; }
+// ---------------------------------------------------------------------------------------------------------------
+// Selection (D_opt_alg.py:59-61 / :145-147) in ONE sweep over (w, x), carried as three candidates:
+//   amax   (-w_i, i)  minimised            -> i = argmax w, first occurrence
+//   smin   (w_i, i) over the support x_i > thr, minimised -> the masked argmin while some support entry is below w_max
+//   fmask  first index outside the support -> decides the tie when every support entry equals w_max
+//                                            (then (w - w_max)*[x > thr] is 0 everywhere and np.argmin returns the first index)
+// thr = 1e-8 with away steps (:147), 0 without (:60).
+struct FwCand {
+    double amax; long long imax;
+    double smin; long long imin;
+    long long fmask;
+};
+constexpr long long FW_NOIDX = 0x7fffffffffffffffLL;
+__device__ __forceinline__ void fw_cand_init(FwCand& c) {
+    c.amax = FW_INF; c.imax = FW_NOIDX; c.smin = FW_INF; c.imin = FW_NOIDX; c.fmask = FW_NOIDX;
+}
+__device__ __forceinline__ void fw_cand_add(FwCand& c, double wi, double xi, long long i, double thr) {
+    fw_arg_combine(c.amax, c.imax, -wi, i);
+    if (xi > thr) fw_arg_combine(c.smin, c.imin, wi, i);
+    else if (i < c.fmask) c.fmask = i;
+}
+__device__ __forceinline__ void fw_cand_merge(FwCand& c, const FwCand& o) {
+    fw_arg_combine(c.amax, c.imax, o.amax, o.imax);
+    fw_arg_combine(c.smin, c.imin, o.smin, o.imin);
+    if (o.fmask < c.fmask) c.fmask = o.fmask;
+}
+__device__ __forceinline__ void fw_cand_warp(FwCand& c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        FwCand q;
+        q.amax = __shfl_xor_sync(0xffffffffu, c.amax, o);
+        q.imax = __shfl_xor_sync(0xffffffffu, c.imax, o);
+        q.smin = __shfl_xor_sync(0xffffffffu, c.smin, o);
+        q.imin = __shfl_xor_sync(0xffffffffu, c.imin, o);
+        q.fmask = __shfl_xor_sync(0xffffffffu, c.fmask, o);
+        fw_cand_merge(c, q);
     }
-    fw_block_argmin(v, idx, shv, shi);
-    if (threadIdx.x == 0) { partials[blockIdx.x] = v; ipartials[blockIdx.x] = idx; }
-    if (last_block_ticket(counter, &is_last)) {
-        v = FW_INF; idx = 0x7fffffffffffffffLL;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
-            fw_arg_combine(v, idx, ld_cg(&partials[b]), __ldcg(&ipartials[b]));
-        fw_block_argmin(v, idx, shv, shi);
-        if (threadIdx.x == 0) { ctrl[C_WMAX] = -v; ctrl[C_IMAX] = (double)idx; }
+}
+// block-wide merge; the result is valid in warp 0 (every lane)
+__device__ __forceinline__ void fw_cand_block(FwCand& c, FwCand* sh /* >= 32 */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    fw_cand_warp(c);
+    __syncthreads();
+    if (lane == 0) sh[wid] = c;
+    __syncthreads();
+    if (wid == 0) {
+        if (lane < nw) c = sh[lane]; else fw_cand_init(c);
+        fw_cand_warp(c);
     }
 }
 
-// masked argmin, then (last block) the scalar step rule, history entry k and the gather of the chosen column
-struct FwDecideParams {
-    int64_t n, ldv;
-    const double* V;
-    const double* x;
-    const double* w;
-    int m, away, k;
-    double eps;
+struct FwParams {
+    const double* V; int m; int64_t n, ldv;
+    double* x; double* w; double* Hinv; double* u; double* v;
     double* ctrl;
-    double* v;           // m doubles: the chosen column of V
     double* hist_F; double* hist_SP; double* hist_SN; double* hist_T;
-    double* partials; long long* ipartials; unsigned int* counter;
+    FwCand* parts;            // one candidate record per selecting CTA
+    unsigned int* counter;
+    int away; double eps;
+    int k;                    // iteration whose decision the tail of this kernel takes
+    int nblk;                 // column blocks of the pass
+    int nr1;                  // leading CTAs that update Hinv instead (they start first, so they read the step's
+                              // coefficients long before the tail of the same launch replaces them)
+    int decide;               // pass kernel: take the decision of iteration k in the tail
+    int reverse;              // pass kernel: walk the column blocks from the end
 };
 
-__global__ void __launch_bounds__(FW_THREADS) fw_argmin_decide_kernel(FwDecideParams p) {
-    __shared__ double shv[32];
-    __shared__ long long shi[32];
-    __shared__ bool is_last;
-    __shared__ long long sh_idx;
-    __shared__ int sh_go;
-    if (ld_cg(&p.ctrl[C_STOP]) != 0.0) return;
-    const double wmax = ld_cg(&p.ctrl[C_WMAX]);
-    double v = FW_INF;
-    long long idx = 0x7fffffffffffffffLL;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
-        double xi = p.x[i], val;
-        if (p.away) {
-            // j = argmin((w - w[i]) * [x > 1e-8])     D_opt_alg.py:146-147
-            val = (xi > 1.0e-8) ? (p.w[i] - wmax) : 0.0;
-        } else {
-            // j = argmin(w[x > 0])                    D_opt_alg.py:60-61
-            if (!(xi > 0.0)) continue;
-            val = p.w[i];
-        }
-        if (val < v) { v = val; idx = i; }
-    }
-    fw_block_argmin(v, idx, shv, shi);
-    if (threadIdx.x == 0) { p.partials[blockIdx.x] = v; p.ipartials[blockIdx.x] = idx; }
-    if (!last_block_ticket(p.counter, &is_last)) return;
-
-    v = FW_INF; idx = 0x7fffffffffffffffLL;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
-        fw_arg_combine(v, idx, ld_cg(&p.partials[b]), __ldcg(&p.ipartials[b]));
-    fw_block_argmin(v, idx, shv, shi);
+// The decision of iteration p.k from the merged candidates (thread 0 of the last CTA), then the gather of the chosen
+// column by the whole CTA.  D_opt_alg.py:52-82 / :136-179.
+__device__ __forceinline__ void fw_decide(const FwParams& p, const FwCand& cd, int* sh_go, long long* sh_idx) {
     if (threadIdx.x == 0) {
         double* c = p.ctrl;
         const double md = (double)p.m;
-        const long long imax = (long long)c[C_IMAX];
-        const long long jmin = (idx < p.n) ? idx : 0;   // empty support cannot happen for x on the simplex
+        const double wmax = -cd.amax;
+        const long long imax = cd.imax;
+        long long jmin;
+        if (p.away) {
+            // argmin((w - w_max) * [x > 1e-8]): the support minimum unless it ties with the zeros of the mask
+            if (cd.imin != FW_NOIDX && cd.smin < wmax) jmin = cd.imin;
+            else jmin = cd.imin < cd.fmask ? cd.imin : cd.fmask;
+        } else {
+            jmin = cd.imin;
+        }
+        if (jmin == FW_NOIDX) jmin = 0;              // empty support cannot happen for x on the simplex
         const double wj = p.w[jmin];
         const double xj = p.x[jmin];
         const double logdet = c[C_LOGDET_HI] + c[C_LOGDET_LO];
@@ -145,6 +153,7 @@ __global__ void __launch_bounds__(FW_THREADS) fw_argmin_decide_kernel(FwDecidePa
         unsigned long long ns;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
         p.hist_T[p.k] = (double)ns;
+        c[C_WMAX] = wmax; c[C_IMAX] = (double)imax;
         c[C_WMIN] = wj; c[C_JMIN] = (double)jmin;
         c[C_NITER] = (double)(p.k + 1);
         int go = 1;
@@ -180,80 +189,138 @@ __global__ void __launch_bounds__(FW_THREADS) fw_argmin_decide_kernel(FwDecidePa
             c[C_LOGDET_LO] += err;
             c[C_MODE] = (double)mode; c[C_T] = t; c[C_CS] = cs; c[C_DEN] = den;
             c[C_IDX] = (double)chosen; c[C_TSIGN] = tsign;
-            sh_idx = chosen;
+            *sh_idx = chosen;
         }
-        sh_go = go;
+        *sh_go = go;
     }
     __syncthreads();
-    if (sh_go) {
-        const long long col = sh_idx;
+    if (*sh_go) {
+        const long long col = *sh_idx;
         for (int r = threadIdx.x; r < p.m; r += blockDim.x) p.v[r] = p.V[(int64_t)r * p.ldv + col];
     }
+}
+
+// publish this CTA's candidates; the last of `nparts` CTAs merges them in index order and decides
+__device__ __forceinline__ void fw_select_tail(const FwParams& p, FwCand& cd, int part, int nparts, FwCand* sh_c,
+                                               bool* sh_last, int* sh_go, long long* sh_idx) {
+    fw_cand_block(cd, sh_c);
+    if (threadIdx.x == 0) p.parts[part] = cd;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tk = atomicAdd(p.counter, 1u);
+        bool last = (tk == (unsigned)nparts - 1);
+        *sh_last = last;
+        if (last) *p.counter = 0u;
+    }
+    __syncthreads();
+    if (!*sh_last) return;
+    __threadfence();
+    fw_cand_init(cd);
+    for (int b = threadIdx.x; b < nparts; b += blockDim.x) {
+        FwCand q;
+        q.amax = ld_cg(&p.parts[b].amax); q.imax = __ldcg(&p.parts[b].imax);
+        q.smin = ld_cg(&p.parts[b].smin); q.imin = __ldcg(&p.parts[b].imin);
+        q.fmask = __ldcg(&p.parts[b].fmask);
+        fw_cand_merge(cd, q);
+    }
+    fw_cand_block(cd, sh_c);
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) sh_c[0] = cd;
+    }
+    __syncthreads();
+    cd = sh_c[0];
+    fw_decide(p, cd, sh_go, sh_idx);
+}
+
+// standalone selection + decision (first iteration of a batch)
+__global__ void __launch_bounds__(FW_THREADS) fw_select_kernel(FwParams p) {
+    __shared__ FwCand sh_c[32];
+    __shared__ bool sh_last;
+    __shared__ int sh_go;
+    __shared__ long long sh_idx;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (ld_cg(&p.ctrl[C_STOP]) != 0.0) return;
+    const double thr = p.away ? 1.0e-8 : 0.0;
+    FwCand cd;
+    fw_cand_init(cd);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride)
+        fw_cand_add(cd, p.w[i], p.x[i], i, thr);
+    fw_select_tail(p, cd, blockIdx.x, gridDim.x, sh_c, &sh_last, &sh_go, &sh_idx);
 }
 
 // u = Hinv v (warp per row)            D_opt_alg.py:78 / :165 / :174
 __global__ void __launch_bounds__(256) fw_hv_kernel(const double* __restrict__ Hinv, int m, const double* __restrict__ v,
                                                     double* __restrict__ u, const double* ctrl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (ld_cg(&ctrl[C_STOP]) != 0.0) return;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= m) return;
     const double* hr = Hinv + (size_t)row * m;
     double s = 0.0;
-    for (int c = lane; c < m; c += 32) s += hr[c] * __ldcg(v + c);
+    for (int c = lane; c < m; c += 32) s += __ldcg(hr + c) * __ldcg(v + c);
     s = warp_sum(s);
     if (lane == 0) u[row] = s;
 }
 
-// Hinv <- (Hinv - cs * u u^T) / den     D_opt_alg.py:79 / :166 / :175
-__global__ void __launch_bounds__(256) fw_rank1_kernel(double* __restrict__ Hinv, int m, const double* __restrict__ u,
-                                                       const double* ctrl) {
-    if (ld_cg(&ctrl[C_STOP]) != 0.0) return;
-    const double cs = ld_cg(&ctrl[C_CS]), den = ld_cg(&ctrl[C_DEN]);
-    const int64_t total = (int64_t)m * m;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        int r = (int)(e / m), c = (int)(e - (int64_t)r * m);
-        double o = __ldcg(u + r) * __ldcg(u + c);
-        Hinv[e] = (Hinv[e] - cs * o) / den;
-    }
-}
-
-// the one pass over V:  p_j = u^T v_j ;  w_j <- (w_j - cs p_j^2)/den ;  x_j <- x_j*den (+- t at the chosen column)
-constexpr int FWP_THREADS = 64;      // 2 columns per thread -> 128 columns per CTA
-constexpr int FWP_UNROLL = 16;       // rows in flight per thread (16 x 16 B)
-constexpr int FWP_MAXSPLIT = 4;      // CTAs of one cluster split the rows of V; partials meet in distributed smem
+// The one pass over V of iteration k-1 (p_j = u^T v_j; w_j <- (w_j - cs p_j^2)/den; x_j <- x_j*den (+- t at the chosen
+// column)), the rank-one update Hinv <- (Hinv - cs u u^T)/den on the CTAs beyond the column blocks, and -- in the tail --
+// the selection and decision of iteration k on the freshly updated (w, x): one kernel per iteration besides u = Hinv v.
+// A CTA owns 128 columns; its four 64-thread groups split the rows and meet in shared memory (fixed order).
+// Column blocks are walked in alternating directions from one iteration to the next, so the part of V the previous
+// pass read last -- still resident in the 126 MB L2 -- is read first.
+constexpr int FWP_THREADS = 256;
+constexpr int FWP_COLS = 128;
+constexpr int FWP_UNROLL = 8;        // rows in flight per thread (8 x 16 B)
 
 template <bool VEC2>
-__global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(const double* __restrict__ V, int m, int64_t n, int64_t ldv,
-                                                              const double* __restrict__ u, double* __restrict__ x,
-                                                              double* __restrict__ w, const double* ctrl) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ double us[];                         // this CTA's slice of u
-    __shared__ double part[2 * FWP_THREADS];
-    if (ld_cg(&ctrl[C_STOP]) != 0.0) return;               // uniform over the whole grid
-    const unsigned nsplit = cluster.num_blocks(), rank = cluster.block_rank();
-    const int rows_per = (m + nsplit - 1) / nsplit;
-    const int r0 = rank * rows_per;
-    const int r1 = min(m, r0 + rows_per);
-    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) us[r - r0] = __ldcg(u + r);
+__global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(FwParams p) {
+    extern __shared__ double us[];                         // u (m doubles)
+    __shared__ double part[4][FWP_COLS];
+    __shared__ FwCand sh_c[32];
+    __shared__ bool sh_last;
+    __shared__ int sh_go;
+    __shared__ long long sh_idx;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (ld_cg(&p.ctrl[C_STOP]) != 0.0) return;               // uniform over the whole grid
+    const double cs = ld_cg(&p.ctrl[C_CS]), den = ld_cg(&p.ctrl[C_DEN]);
+    const int m = p.m;
+    if ((int)blockIdx.x < p.nr1) {                           // Hinv <- (Hinv - cs u u^T)/den     D_opt_alg.py:79 / :166 / :175
+        const int64_t total = (int64_t)m * m;
+        const int64_t stride = (int64_t)p.nr1 * blockDim.x;
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+            int r = (int)(e / m), c = (int)(e - (int64_t)r * m);
+            double o = __ldcg(p.u + r) * __ldcg(p.u + c);
+            p.Hinv[e] = (p.Hinv[e] - cs * o) / den;
+        }
+        return;
+    }
+    for (int r = threadIdx.x; r < m; r += blockDim.x) us[r] = __ldcg(p.u + r);
     __syncthreads();
-    const int64_t j = ((int64_t)blockIdx.x * FWP_THREADS + threadIdx.x) * 2;
+    const int blk = (int)blockIdx.x - p.nr1;
+    const int cb = p.reverse ? (p.nblk - 1 - blk) : blk;
+    const int rg = threadIdx.x >> 6, ct = threadIdx.x & 63;
+    const int rows_per = (m + 3) / 4;
+    const int r0 = rg * rows_per, r1 = min(m, r0 + rows_per);
+    const int64_t j = ((int64_t)cb * 64 + ct) * 2;
     double s0 = 0.0, s1 = 0.0;
-    if (j < n) {
-        const double* col = V + j;
+    if (j < p.n) {
+        const double* col = p.V + j;
         int r = r0;
-        if (VEC2 && j + 1 < n) {
+        if (VEC2 && j + 1 < p.n) {
             for (; r + FWP_UNROLL <= r1; r += FWP_UNROLL) {
                 double2 a[FWP_UNROLL];
 #pragma unroll
                 for (int q = 0; q < FWP_UNROLL; ++q)
                     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
-                                 : "=d"(a[q].x), "=d"(a[q].y) : "l"(col + (int64_t)(r + q) * ldv));
+                                 : "=d"(a[q].x), "=d"(a[q].y) : "l"(col + (int64_t)(r + q) * p.ldv));
 #pragma unroll
                 for (int q = 0; q < FWP_UNROLL; ++q) {
-                    double uq = us[r - r0 + q];
+                    double uq = us[r + q];
                     s0 += uq * a[q].x;
                     s1 += uq * a[q].y;
                 }
@@ -261,44 +328,44 @@ __global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(const double* __re
             for (; r < r1; ++r) {
                 double2 a;
                 asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
-                             : "=d"(a.x), "=d"(a.y) : "l"(col + (int64_t)r * ldv));
-                double uq = us[r - r0];
+                             : "=d"(a.x), "=d"(a.y) : "l"(col + (int64_t)r * p.ldv));
+                double uq = us[r];
                 s0 += uq * a.x;
                 s1 += uq * a.y;
             }
         } else {
-            const bool two = (j + 1 < n);
+            const bool two = (j + 1 < p.n);
             for (; r < r1; ++r) {
-                double uq = us[r - r0];
-                s0 += uq * __ldcs(col + (int64_t)r * ldv);
-                if (two) s1 += uq * __ldcs(col + (int64_t)r * ldv + 1);
+                double uq = us[r];
+                s0 += uq * __ldcs(col + (int64_t)r * p.ldv);
+                if (two) s1 += uq * __ldcs(col + (int64_t)r * p.ldv + 1);
             }
         }
     }
-    part[2 * threadIdx.x] = s0;
-    part[2 * threadIdx.x + 1] = s1;
-    cluster.sync();
-    if (rank == 0 && j < n) {
-        for (unsigned q = 1; q < nsplit; ++q) {             // fixed order: row chunks 0, 1, 2, ...
-            const double* rp = cluster.map_shared_rank(part, q);
-            s0 += rp[2 * threadIdx.x];
-            s1 += rp[2 * threadIdx.x + 1];
-        }
-        const double cs = ld_cg(&ctrl[C_CS]), den = ld_cg(&ctrl[C_DEN]);
-        const int64_t idx = (int64_t)ld_cg(&ctrl[C_IDX]);
-        const double tsign = ld_cg(&ctrl[C_TSIGN]);
-        w[j] = (w[j] - cs * (s0 * s0)) / den;
-        double xn = x[j] * den;
-        if (j == idx) xn = xn + tsign;
-        x[j] = xn;
-        if (j + 1 < n) {
-            w[j + 1] = (w[j + 1] - cs * (s1 * s1)) / den;
-            xn = x[j + 1] * den;
-            if (j + 1 == idx) xn = xn + tsign;
-            x[j + 1] = xn;
+    part[rg][2 * ct] = s0;
+    part[rg][2 * ct + 1] = s1;
+    __syncthreads();
+    FwCand cd;
+    fw_cand_init(cd);
+    if (rg == 0 && j < p.n) {
+        const double thr = p.away ? 1.0e-8 : 0.0;
+        const int64_t idx = (int64_t)ld_cg(&p.ctrl[C_IDX]);
+        const double tsign = ld_cg(&p.ctrl[C_TSIGN]);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            if (j + e < p.n) {
+                const double pj = ((part[0][2 * ct + e] + part[1][2 * ct + e]) + part[2][2 * ct + e]) + part[3][2 * ct + e];
+                const double wn = (p.w[j + e] - cs * (pj * pj)) / den;
+                double xn = p.x[j + e] * den;
+                if (j + e == idx) xn = xn + tsign;
+                p.w[j + e] = wn;
+                p.x[j + e] = xn;
+                fw_cand_add(cd, wn, xn, j + e, thr);
+            }
         }
     }
-    cluster.sync();                                         // remote shared memory must outlive rank 0's reads
+    if (!p.decide) return;
+    fw_select_tail(p, cd, blk, p.nblk, sh_c, &sh_last, &sh_go, &sh_idx);
 }
 
 // Hinv = Linv^T Linv  (setup only; Linv lower triangular, zero padded, leading dimension mp)
@@ -352,7 +419,8 @@ extern "C" {
 size_t accbpg_fw_workspace_bytes(int m, int64_t n_local) {
     // dopt workspace (gram / factor / Linv / gradient partials) + v and u vectors
     size_t base = accbpg_dopt_workspace_bytes(m, n_local);
-    return base + 2 * (((size_t)m * 8 + 255) / 256 * 256);
+    const size_t nparts = (size_t)((n_local + 127) / 128) + 2048;        // selection candidates, one per selecting CTA
+    return base + 2 * (((size_t)m + 31) / 32 * 32 * 8) + nparts * 40 + 256;
 }
 
 // D_opt_alg.py:39-45 / :123-129:  M = V diag(x0) V^T, Hinv = M^{-1}, w_j = v_j^T Hinv v_j, log det M
@@ -380,7 +448,9 @@ int accbpg_fw_setup(void* ctx, void* stream, const double* V, int m, int64_t n, 
     return ACCBPG_OK;
 }
 
-// run iterations k_start .. k_start+k_count-1 (no-ops after the stop flag is raised)
+// run iterations k_start .. k_start+k_count-1 (no-ops after the stop flag is raised):
+//   select+decide(k_start);  then per iteration  u = Hinv v;  pass (+ rank-one update of Hinv, + decision of k+1)
+// Launches are chained with programmatic dependent launch.
 int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, int64_t ldv, int away, double eps,
                   int k_start, int k_count, void* ws, double* Hinv, double* x, double* w, double* ctrl,
                   double* hist_F, double* hist_SP, double* hist_SN, double* hist_T) {
@@ -389,53 +459,51 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
     if (!c || !V || !ws || !Hinv || !x || !w || !ctrl || !hist_F || !hist_SP || !hist_SN || !hist_T)
         return arg_err("fw_run: NULL pointer");
     if (m < 1 || n < 1 || ldv < n || k_count < 0) return arg_err("fw_run: shape");
+    if (k_count == 0) return ACCBPG_OK;
     size_t base = accbpg_dopt_workspace_bytes(m, n);
     double* v = (double*)((char*)ws + base);
     double* u = v + ((size_t)m + 31) / 32 * 32;
-    const int sel_grid = grid_for(c, n, FW_THREADS, 4, 4);
+    FwCand* parts = (FwCand*)(u + ((size_t)m + 31) / 32 * 32);
+    const int64_t nblk64 = (n + FWP_COLS - 1) / FWP_COLS;
+    if (nblk64 > 2000000000LL) return arg_err("fw_run: n too large");
+    const int nblk = (int)nblk64;
+    const int sel_grid = grid_for(c, n, FW_THREADS, 4, 2);
     const int hv_grid = (m + 7) / 8;
-    const int r1_grid = grid_for(c, (int64_t)m * m, 256, 2, 8);
-    const int64_t pass_grid = (n + 2 * FWP_THREADS - 1) / (2 * FWP_THREADS);
-    if (pass_grid > 2147483647LL) return arg_err("fw_run: n too large");
-    // split the rows over a small cluster when the column blocks alone cannot fill the GPU evenly
-    int nsplit = 1;
-    while (nsplit < FWP_MAXSPLIT && pass_grid * nsplit < (int64_t)c->sm_count * 8 && m / (nsplit * 2) >= 64) nsplit *= 2;
-    const size_t pass_smem = (size_t)((m + nsplit - 1) / nsplit) * sizeof(double);
-    if (pass_smem > 200 * 1024) return arg_err("fw_run: m too large for the shared-memory copy of u");
+    int r1_ctas = c->sm_count / 4;
+    if (r1_ctas < 1) r1_ctas = 1;
+    const size_t pass_smem = (size_t)m * sizeof(double);
+    if (pass_smem > 160 * 1024) return arg_err("fw_run: m too large for the shared-memory copy of u");
     const bool pass_vec = ((reinterpret_cast<uintptr_t>(V) & 15u) == 0) && (ldv % 2 == 0);
     auto pass_fn = pass_vec ? fw_pass_kernel<true> : fw_pass_kernel<false>;
-    if (pass_smem > 48 * 1024)
+    if (pass_smem > 32 * 1024)
         ACCBPG_CUDA(cudaFuncSetAttribute(pass_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
-    cudaLaunchConfig_t pass_cfg = {};
-    pass_cfg.gridDim = dim3((unsigned)pass_grid, (unsigned)nsplit, 1);
-    pass_cfg.blockDim = dim3(FWP_THREADS, 1, 1);
-    pass_cfg.dynamicSmemBytes = pass_smem;
-    pass_cfg.stream = s;
-    cudaLaunchAttribute pass_attr[1];
-    pass_attr[0].id = cudaLaunchAttributeClusterDimension;
-    pass_attr[0].val.clusterDim.x = 1;
-    pass_attr[0].val.clusterDim.y = (unsigned)nsplit;
-    pass_attr[0].val.clusterDim.z = 1;
-    pass_cfg.attrs = pass_attr;
-    pass_cfg.numAttrs = 1;
-    FwDecideParams p;
-    p.n = n; p.ldv = ldv; p.V = V; p.x = x; p.w = w; p.m = m; p.away = away; p.eps = eps;
-    p.ctrl = ctrl; p.v = v; p.hist_F = hist_F; p.hist_SP = hist_SP; p.hist_SN = hist_SN; p.hist_T = hist_T;
-    p.partials = c->d_partials; p.ipartials = c->d_ipartials; p.counter = c->d_counter;
+    FwParams p;
+    p.V = V; p.m = m; p.n = n; p.ldv = ldv; p.x = x; p.w = w; p.Hinv = Hinv; p.u = u; p.v = v; p.ctrl = ctrl;
+    p.hist_F = hist_F; p.hist_SP = hist_SP; p.hist_SN = hist_SN; p.hist_T = hist_T;
+    p.parts = parts; p.counter = c->d_counter; p.away = away; p.eps = eps; p.nblk = nblk; p.nr1 = r1_ctas;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = s;
+    cfg.attrs = attr;
+    // the first decision of the batch
+    p.k = k_start; p.decide = 1; p.reverse = 0;
+    cfg.gridDim = dim3(sel_grid); cfg.blockDim = dim3(FW_THREADS); cfg.dynamicSmemBytes = 0; cfg.numAttrs = 0;
+    ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, fw_select_kernel, p));
+    ACCBPG_LAUNCHED("fw_select_kernel");
     for (int k = k_start; k < k_start + k_count; ++k) {
         ProfScope ps_iter(P_FW_ITER, s);
-        fw_argmax_kernel<<<sel_grid, FW_THREADS, 0, s>>>(n, w, c->d_partials, c->d_ipartials, c->d_counter, ctrl);
-        ACCBPG_LAUNCHED("fw_argmax_kernel");
-        p.k = k;
-        fw_argmin_decide_kernel<<<sel_grid, FW_THREADS, 0, s>>>(p);
-        ACCBPG_LAUNCHED("fw_argmin_decide_kernel");
-        fw_hv_kernel<<<hv_grid, 256, 0, s>>>(Hinv, m, v, u, ctrl);
+        cfg.gridDim = dim3(hv_grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.numAttrs = 1;
+        ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, fw_hv_kernel, (const double*)Hinv, m, (const double*)v, u, (const double*)ctrl));
         ACCBPG_LAUNCHED("fw_hv_kernel");
-        fw_rank1_kernel<<<r1_grid, 256, 0, s>>>(Hinv, m, u, ctrl);
-        ACCBPG_LAUNCHED("fw_rank1_kernel");
+        p.k = k + 1;                                        // the tail decides the next iteration ...
+        p.decide = (k + 1 < k_start + k_count) ? 1 : 0;     // ... except after the last pass of the batch
+        p.reverse = k & 1;
+        cfg.gridDim = dim3(nblk + r1_ctas); cfg.blockDim = dim3(FWP_THREADS); cfg.dynamicSmemBytes = pass_smem;
         {
             ProfScope ps(P_FW_PASS, s);
-            ACCBPG_CUDA(cudaLaunchKernelEx(&pass_cfg, pass_fn, V, m, n, ldv, (const double*)u, x, w, (const double*)ctrl));
+            ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, pass_fn, p));
         }
         ACCBPG_LAUNCHED("fw_pass_kernel");
     }
