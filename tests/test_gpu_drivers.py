@@ -200,3 +200,46 @@ def test_direct_evaluation_mode_matches_too(acc, dopt, golden_traj):
             assert ferr(out[1], golden_traj["kls_gain_F"][:120]) <= FTOL
     finally:
         config.linear_images = old
+
+
+def test_pipelined_and_synchronous_loops_agree(acc, dopt, golden_traj):
+    """config.pipeline: ABPG / ABDA / BPG-without-line-search enqueue iteration k+1 before reading iteration k's scalars.
+    Recorded histories, the stopping iteration and the returned iterate must be those of the synchronous loop."""
+    from accbpg_and_fw_b200 import config
+    f, h, L, x0 = dopt
+    old = config.pipeline
+    res = {}
+    try:
+        for mode in (False, True):
+            config.pipeline = mode
+            res[mode] = (
+                acc.ABPG(f, h, L, x0, gamma=2, maxitrs=200, theta_eq=False, verbose=False),
+                acc.ABDA(f, h, L, x0, gamma=2, maxitrs=200, verbose=False),
+                acc.BPG(f, h, L, x0, maxitrs=200, linesearch=False, verbose=False),
+                # early stop: epsilon large enough that dzz < epsilon fires mid-run
+                acc.ABPG(f, h, L, x0, gamma=2, maxitrs=200, epsilon=1e-3, theta_eq=False, verbose=False),
+                acc.BPG(f, h, L, x0, maxitrs=400, epsilon=1e-4, linesearch=False, verbose=False),
+            )
+    finally:
+        config.pipeline = old
+    for a, b in zip(res[False], res[True]):
+        assert len(a[1]) == len(b[1])                       # same stopping iteration
+        assert np.array_equal(a[1], b[1])                   # F: same kernels on the same data, bit for bit
+        assert np.array_equal(a[2], b[2])
+        assert np.array_equal(a[0], b[0])                   # returned iterate
+        assert np.all(np.diff(b[-1]) >= 0)                  # T stays monotone
+    assert len(res[True][3][1]) < 200 and len(res[True][4][1]) < 400      # the early stops really fired
+    assert ferr(res[True][0][1], golden_traj["abpg_F"][:200]) <= FTOL
+    assert ferr(res[True][1][1], golden_traj["abda_F"][:200]) <= FTOL
+
+
+def test_deferred_reads_round_robin(acc):
+    """accbpg_ctx_read_async / _wait: tickets come back in order, values are those at enqueue time."""
+    import torch
+    rt = acc.Runtime.get()
+    tickets = []
+    for i in range(6):
+        rt.scal[40:43] = torch.tensor([i, 2.0 * i, -1.0 * i], dtype=torch.float64, device=rt.device)
+        tickets.append(rt.read_async(40, 3))
+    for i, t in enumerate(tickets):
+        assert rt.read_wait(t, 3) == [float(i), 2.0 * i, -1.0 * i]
