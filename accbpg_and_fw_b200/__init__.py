@@ -15,7 +15,8 @@ from .bregman import (LegendreFunction, BurgEntropy, BurgEntropyL1, BurgEntropyL
 from .lmo import (lmo_simplex, lmo_matrix_simplex, lmo_l2_ball, lmo_l2_ball_positive_orthant, lmo_linf_ball,
                   lmo_matrix_box)
 from .drivers import BPG, ABPG, ABPG_expo, ABPG_gain, ABDA, solve_theta
-from .drivers_fw import FW_alg_div_step, FW_alg_descent_step
+from .drivers_fw import (FW_alg_div_step, FW_alg_descent_step, FW_alg_L0_L1_shortest_step,
+                         FW_l0l1_log_and_linear_step, FW_l0l1_log_only)
 from .dopt_fw import D_opt_FW, D_opt_FW_away
 from .problems import (D_opt_libsvm, D_opt_design, D_opt_KYinit, Poisson_regrL1, Poisson_regrL2, KL_nonneg_regr,
                        load_libsvm_dense)
@@ -29,7 +30,8 @@ __all__ = [
     "lmo_simplex", "lmo_matrix_simplex", "lmo_l2_ball", "lmo_l2_ball_positive_orthant", "lmo_linf_ball",
     "lmo_matrix_box",
     "BPG", "ABPG", "ABPG_expo", "ABPG_gain", "ABDA", "solve_theta",
-    "FW_alg_div_step", "FW_alg_descent_step", "D_opt_FW", "D_opt_FW_away",
+    "FW_alg_div_step", "FW_alg_descent_step", "FW_alg_L0_L1_shortest_step", "FW_l0l1_log_and_linear_step",
+    "FW_l0l1_log_only", "D_opt_FW", "D_opt_FW_away",
     "D_opt_libsvm", "D_opt_design", "D_opt_KYinit", "Poisson_regrL1", "Poisson_regrL2", "KL_nonneg_regr",
     "load_libsvm_dense", "ColumnShard", "Runtime",
 ]

@@ -98,6 +98,13 @@ struct DotDiffF {
         acc[0] += __dmul_rn(g[i], __dsub_rn(a[i], b[i]));
     }
 };
+struct SqDistF {
+    const double *a, *b;
+    __device__ void operator()(int64_t i, double* acc, uint32_t&) const {
+        const double d = __dsub_rn(a[i], b[i]);
+        acc[0] += __dmul_rn(d, d);
+    }
+};
 struct SumF {
     const double* x;
     __device__ void operator()(int64_t i, double* acc, uint32_t&) const { acc[0] += x[i]; }
@@ -591,6 +598,10 @@ int accbpg_vec_dot_diff(void* ctx, void* stream, int64_t n, const double* g, con
                         double* d_out) {
     CTX_STREAM
     return launch_reduce<1>(c, s, n, DotDiffF{g, a, b}, d_out, "vec_dot_diff");
+}
+int accbpg_vec_sqdist(void* ctx, void* stream, int64_t n, const double* a, const double* b, double* d_out) {
+    CTX_STREAM
+    return launch_reduce<1>(c, s, n, SqDistF{a, b}, d_out, "vec_sqdist");
 }
 int accbpg_vec_sum(void* ctx, void* stream, int64_t n, const double* x, double* d_out) {
     CTX_STREAM

@@ -113,26 +113,47 @@ def KL_nonneg_regr(m, n, noise=0.01, lamdaL1=0, randseed=-1, normalizeA=True, de
     return KLdivRegression(A, b, device=device), ShannonEntropyL1(lamdaL1, device=device), L, 0.5 * np.ones(n)
 
 
-def D_opt_KYinit(V):
+def D_opt_KYinit(V, device=None):
     """Kumar-Yildirim sparse starting point (applications.py:59-95).
 
-    Host-side setup executed once before a solve (m Gram-Schmidt sweeps, each with one q^T V product);
-    it is a SURVEY section 8(f) "next" item for the device path and runs in NumPy here."""
-    V = np.asarray(V.cpu().numpy() if hasattr(V, "cpu") else V)
-    m, n = V.shape
+    m Gram-Schmidt sweeps, each with one product q^T V over all of V (8mn bytes: the whole cost, m passes over the
+    design matrix).  That pass, the arg-max / arg-min over its n results and the gather of the two chosen columns run
+    on the device (K6 `rmatvec`, K14 `argext`); the m x m Gram-Schmidt bookkeeping on m-vectors between the passes is
+    host scalar control in the reference's exact order, and the random directions come from the legacy NumPy stream as
+    in the reference.  Returns a host NumPy vector like the reference."""
+    import torch
+    from . import _native as nat
+    from .runtime import Runtime
+    lib = nat.lib
+    rt = Runtime.get(device)
+    Vd = rt.to_device(V)
+    m, n = int(Vd.shape[0]), int(Vd.shape[1])
     if n <= 2 * m:
         return (1.0 / n) * np.ones(n)
+    ws = rt.workspace(("linreg", m, n), lib.accbpg_linreg_workspace_bytes(m, n))
+    qV = rt.empty(n)
+    host_V = None if isinstance(V, torch.Tensor) else np.asarray(V)
     picked = []
     Q = np.zeros((m, m))
+    s0 = rt.S_TMP
     for i in range(m):
         b = np.random.rand(m)
         q = b.copy()
         for j in range(i):
             q = q - np.dot(Q[:, j], b) * Q[:, j]
-        qV = np.dot(q, V)
-        kmax, kmin = int(np.argmax(qV)), int(np.argmin(qV))
+        qd = rt.to_device(q)
+        nat.check(lib.accbpg_linreg_rmatvec(rt.ctx, rt.stream, Vd.data_ptr(), m, n, Vd.stride(0), qd.data_ptr(),
+                                            ws.data_ptr(), qV.data_ptr()))
+        nat.check(lib.accbpg_vec_argext(rt.ctx, rt.stream, n, qV.data_ptr(), 1, rt.slot(s0)))
+        nat.check(lib.accbpg_vec_argext(rt.ctx, rt.stream, n, qV.data_ptr(), 0, rt.slot(s0 + 2)))
+        vals = rt.read(s0, 4)
+        kmax, kmin = int(vals[1]), int(vals[3])
         picked += [kmax, kmin]
-        v = V[:, kmin] - V[:, kmax]
+        if host_V is not None:
+            v = host_V[:, kmin] - host_V[:, kmax]
+        else:
+            cols = Vd[:, [kmin, kmax]].cpu().numpy()          # 2m doubles back (data movement only)
+            v = cols[:, 0] - cols[:, 1]
         q = v.copy()
         for j in range(i):
             q = q - np.dot(Q[:, j], v) * Q[:, j]

@@ -100,6 +100,8 @@ int accbpg_vec_dot(void* ctx, void* stream, int64_t n, const double* d_x, const 
 /* d_out = dot(g, a - b) without the temporary */
 int accbpg_vec_dot_diff(void* ctx, void* stream, int64_t n, const double* d_g, const double* d_a,
                         const double* d_b, double* d_out);
+/* d_out = sum (a - b)^2: ||s - x||^2 of the (L0,L1) Frank-Wolfe step rules (algorithms_fw.py:297, :396) */
+int accbpg_vec_sqdist(void* ctx, void* stream, int64_t n, const double* d_a, const double* d_b, double* d_out);
 int accbpg_vec_sum(void* ctx, void* stream, int64_t n, const double* d_x, double* d_out);
 /* d_out[0] = min(x), d_out[1] = max(x) */
 int accbpg_vec_minmax(void* ctx, void* stream, int64_t n, const double* d_x, double* d_out);

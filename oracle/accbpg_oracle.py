@@ -701,6 +701,148 @@ def FW_alg_descent_step(f, h, x0, maxitrs, lmo, epsilon=1e-14, verbose=False, ve
     return x, F[:k + 1], T[:k + 1], G[:k + 1]
 
 
+def FW_alg_L0_L1_shortest_step(f, h, L0, L1, x0, maxitrs, gamma, lmo, epsilon=1e-14,
+                               linesearch=True, ls_ratio=2, verbose=False, verbskip=1):
+    """algorithms_fw.py:78-207.  Returns (x, F, Ls, T)."""
+    if ls_ratio < 1:
+        raise ValueError("ls_ratio must be >= 1")
+    if L0 < 0 or L1 < 0:
+        raise ValueError("Initial L must be positive")
+    if epsilon <= 0:
+        raise ValueError("epsilon must be positive")
+    t0 = time.time()
+    F, Ls, T = [], [], []
+    delta = 1e-8                                             # :153
+    x = np.copy(x0)
+    toggle = 0
+    for k in range(maxitrs):
+        fx, g = f.func_grad(x)
+        F.append(fx + h.extra_Psi(x))
+        T.append(time.time() - t0)
+        s = lmo(g)
+        d = s - x
+        div = h.divergence(s, x)
+        if div == 0:
+            div = delta
+        gdp = np.dot(g.ravel(), d.ravel())                   # :167
+        if 0 < gdp <= delta:
+            gdp = 0
+        if gdp > 0:
+            raise ValueError("<grad f(x), d> must be nonpositive (LMO issue).")
+        g_norm = np.linalg.norm(g)
+        a_k = L0 + L1 * g_norm
+        if linesearch:                                       # :176-178
+            L0 /= ls_ratio + L0 / a_k
+            L1 /= ls_ratio + (L1 * g_norm) / a_k
+        while True:
+            a_k = L0 + L1 * g_norm
+            alpha = min((-gdp / (a_k * div * np.e)) ** (1 / (gamma - 1)), 1)      # :184
+            x1 = x + alpha * d
+            if not linesearch:
+                break
+            if f.func_grad(x1, flag=0) <= fx + alpha * gdp + alpha ** gamma * (a_k / 2) * np.e * div:   # :190
+                break
+            if toggle == 0:
+                L0 *= ls_ratio - L0 / a_k
+                toggle = 1
+            else:
+                L1 *= ls_ratio - (L1 * g_norm) / a_k
+                toggle = 0
+        x = x1
+        Ls.append(a_k)
+        if k > 0 and abs(F[k] - F[k - 1]) < epsilon:
+            break
+    return x, np.array(F), np.array(Ls), np.array(T)
+
+
+def _fw_l0l1_log(f, h, L0, L1, x0, maxitrs, lmo, ls_ratio, epsilon, L0_max, L1_max, linesearch, log_only):
+    """Shared body of FW_l0l1_log_and_linear_step (algorithms_fw.py:250-349) and FW_l0l1_log_only (:352-453)."""
+    if ls_ratio < 1:
+        raise ValueError("ls_ratio must be >= 1")
+    if L0 <= 0 or L1 <= 0:
+        raise ValueError("Initial L0 and L1 must be positive")
+    if epsilon <= 0:
+        raise ValueError("epsilon must be positive")
+    t0 = time.time()
+    F, Ls, T, LOG_STEPS = [], [], [], []
+    delta = 1e-8
+    toggle = 0
+    x = np.copy(x0)
+    for k in range(maxitrs):
+        fx, g = f.func_grad(x)
+        gx_norm = np.linalg.norm(g)
+        F.append(fx + h.extra_Psi(x))
+        T.append(time.time() - t0)
+        s = lmo(g)
+        d = s - x
+        d_norm = np.linalg.norm(d)
+        gdp = np.vdot(g, d)
+        if 0 < gdp <= delta:
+            gdp = 0
+        if gdp > 0:
+            raise ValueError("grad_d_prod must be non-positive (we minimize)")
+        if linesearch:
+            L0 /= ls_ratio
+            L1 /= ls_ratio
+        if log_only:
+            L1 = max(math.log(2) / d_norm, L1)               # :401
+        if k == 0:
+            LOG_STEPS.append(0)
+        while True:
+            assert L0 >= 0 and L1 >= 0, "Smoothness parameters must stay positive"
+            a_k = L0 + L1 * gx_norm
+            if log_only:
+                z = L1 * d_norm
+                if z >= math.log(2) - 1e-5:                  # :410
+                    alpha = (1 / (L1 * d_norm)) * math.log(1 - (L1 * gdp) / (a_k * d_norm))
+                    LOG_STEPS.append(LOG_STEPS[-1] + 1)
+                else:
+                    assert False, "No use for the second step!"
+            elif L1 * d_norm >= np.log(2):                   # :312
+                alpha = (1 / (L1 * d_norm)) * np.log(1 - (L1 * gdp) / (a_k * d_norm))
+                LOG_STEPS.append(LOG_STEPS[-1] + 1)
+            else:
+                alpha = L1 * (-gdp) / (a_k * d_norm)
+                LOG_STEPS.append(LOG_STEPS[-1])
+            x1 = x + alpha * d
+            if not linesearch:
+                break
+            fx1 = f.func_grad(x1, flag=0)
+            z = L1 * alpha * d_norm
+            exp_term = np.expm1(z) - z if z < 50 else 0.5 * z ** 2          # :327-330
+            rhs = fx + alpha * gdp + (a_k / L1 ** 2) * exp_term
+            if fx1 <= rhs:
+                break
+            if log_only:
+                if toggle == 0:
+                    L0 = min(L0 * ls_ratio, L0_max) if L0_max else L0 * ls_ratio
+                    toggle = 1
+                else:
+                    L1 = min(L1 * ls_ratio, L1_max) if L1_max else L1 * ls_ratio
+                    toggle = 0
+            else:
+                L0 = min(L0 * ls_ratio, L0_max) if L0_max else L0 * ls_ratio
+                L1 = min(L1 * ls_ratio, L1_max) if L1_max else L1 * ls_ratio
+            a_k = L0 + L1 * gx_norm
+        x = x1
+        Ls.append(a_k)
+        if k > 0 and abs(F[k] - F[k - 1]) < epsilon:
+            break
+    return x, np.array(F), np.array(Ls), np.array(LOG_STEPS), np.array(T)
+
+
+def FW_l0l1_log_and_linear_step(f, h, L0, L1, x0, maxitrs, lmo, ls_ratio, epsilon=1e-14, L0_max=None, L1_max=None,
+                                linesearch=True, verbose=False, verbskip=50):
+    """algorithms_fw.py:250-349.  Returns (x, F, Ls, LOG_STEPS, T)."""
+    return _fw_l0l1_log(f, h, L0, L1, x0, maxitrs, lmo, ls_ratio, epsilon, L0_max, L1_max, linesearch, False)
+
+
+def FW_l0l1_log_only(f, h, L0, L1, x0, maxitrs, lmo, ls_ratio, epsilon=1e-14, L0_max=None, L1_max=None,
+                     linesearch=True, verbose=False, verbskip=50):
+    """algorithms_fw.py:352-453.  Returns (x, F, Ls, LOG_STEPS, T)."""
+    return _fw_l0l1_log(f, h, L0, L1, x0, maxitrs, lmo, ls_ratio, epsilon, L0_max, L1_max, linesearch, True)
+
+
 def _fw_setup(V, x0):
     """D_opt_alg.py:39-45 / :123-129."""
     x = np.copy(x0)

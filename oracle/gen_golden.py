@@ -183,6 +183,13 @@ def main():
     tr["fwdiv_x"], tr["fwdiv_F"], tr["fwdiv_Ls"] = out[0], out[1], out[2]
     out = quiet(ref.FW_alg_descent_step, f, h, x0, maxitrs=300, lmo=ref.lmo_simplex(), verbskip=100)
     tr["fwdesc_x"], tr["fwdesc_F"] = out[0], out[1]
+    out = quiet(ref.FW_alg_L0_L1_shortest_step, f, h, 1.0, 1.0, x0, 200, 2.0, ref.lmo_simplex(), ls_ratio=2,
+                verbskip=1000)
+    tr["fwl0l1s_x"], tr["fwl0l1s_F"], tr["fwl0l1s_Ls"] = out[0], out[1], out[2]
+    out = quiet(ref.FW_l0l1_log_and_linear_step, f, h, 1.0, 1.0, x0, 200, ref.lmo_simplex(), 2, verbskip=1000)
+    tr["fwl0l1ll_x"], tr["fwl0l1ll_F"], tr["fwl0l1ll_Ls"], tr["fwl0l1ll_LOG"] = out[0], out[1], out[2], out[3]
+    out = quiet(ref.FW_l0l1_log_only, f, h, 1.0, 1.0, x0, 200, ref.lmo_simplex(), 2, verbskip=1000)
+    tr["fwl0l1lo_x"], tr["fwl0l1lo_F"], tr["fwl0l1lo_Ls"], tr["fwl0l1lo_LOG"] = out[0], out[1], out[2], out[3]
     out = quiet(ref.D_opt_FW, V, x0, 1e-8, 2000, verbskip=1000)
     tr["dfw_x"], tr["dfw_F"], tr["dfw_SP"], tr["dfw_SN"] = out[:4]
     out = quiet(ref.D_opt_FW_away, V, x0, 1e-8, 2000, verbskip=1000)

@@ -104,14 +104,6 @@ def test_libsvm_parser_edge_cases(tmp_path):
         load_libsvm_dense(str(p))
 
 
-def test_ky_init_matches_oracle(golden_traj):
-    from accbpg_and_fw_b200.problems import D_opt_KYinit
-    np.random.seed(10)
-    H = np.random.randn(80, 200)
-    np.random.seed(77)
-    assert np.array_equal(D_opt_KYinit(H), golden_traj["ky_x0"])
-
-
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[3])

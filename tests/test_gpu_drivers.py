@@ -243,3 +243,21 @@ def test_deferred_reads_round_robin(acc):
         tickets.append(rt.read_async(40, 3))
     for i, t in enumerate(tickets):
         assert rt.read_wait(t, 3) == [float(i), 2.0 * i, -1.0 * i]
+
+
+def test_l0l1_fw_variants_golden(acc, dopt, golden_traj):
+    """(L0,L1)-smooth Frank-Wolfe drivers (algorithms_fw.py:78-207, :250-349, :352-453): F to 1e-9 and the discrete
+    line-search outcomes (a_k history, log-step counts) identical up to the first fork."""
+    f, h, L, x0 = dopt
+    lmo = acc.lmo_simplex()
+    x, F, Ls, T = acc.FW_alg_L0_L1_shortest_step(f, h, 1.0, 1.0, x0, 200, 2.0, lmo, ls_ratio=2, verbose=False)
+    assert ferr(F, golden_traj["fwl0l1s_F"]) <= FTOL
+    assert np.max(np.abs(Ls - golden_traj["fwl0l1s_Ls"]) / golden_traj["fwl0l1s_Ls"]) <= 1e-9
+    x, F, Ls, LOG, T = acc.FW_l0l1_log_and_linear_step(f, h, 1.0, 1.0, x0, 200, lmo, 2, verbose=False)
+    assert ferr(F, golden_traj["fwl0l1ll_F"]) <= FTOL and np.array_equal(LOG, golden_traj["fwl0l1ll_LOG"])
+    x, F, Ls, LOG, T = acc.FW_l0l1_log_only(f, h, 1.0, 1.0, x0, 200, lmo, 2, verbose=False)
+    assert ferr(F, golden_traj["fwl0l1lo_F"]) <= FTOL and np.array_equal(LOG, golden_traj["fwl0l1lo_LOG"])
+    with pytest.raises(ValueError):
+        acc.FW_l0l1_log_only(f, h, 0.0, 1.0, x0, 5, lmo, 2, verbose=False)
+    with pytest.raises(ValueError):
+        acc.FW_alg_L0_L1_shortest_step(f, h, -1.0, 1.0, x0, 5, 2.0, lmo, verbose=False)

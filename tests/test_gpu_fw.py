@@ -1,6 +1,7 @@
 """GPU parity: D_opt_FW / D_opt_FW_away (device-resident loop) against the oracle and the golden runs.
 F_k, the slacks SP/SN and the selected vertex indices; the FW vertex index must be bit-exact."""
 import numpy as np
+import torch
 import pytest
 
 from conftest import relerr
@@ -84,3 +85,18 @@ def test_fw_midsize_vs_oracle(acc):
     a = acc.D_opt_FW_away(V, x0, 1e-8, 300, verbose=False)
     b = orc.D_opt_FW_away(V, x0, 1e-8, 300)
     close(a[1], b[1], 1e-9); close(a[2], b[2], 1e-7); close(a[3], b[3], 1e-7)
+
+
+def test_ky_init_golden(acc, golden_traj):
+    """D_opt_KYinit (applications.py:59-95) with the q^T V passes and the arg-extrema on the device: same support as
+    the reference (x0 is a function of the chosen indices only), from a host matrix and from a CUDA tensor."""
+    np.random.seed(10)
+    H = np.random.randn(80, 200)
+    np.random.seed(77)
+    assert np.array_equal(acc.D_opt_KYinit(H), golden_traj["ky_x0"])
+    np.random.seed(77)
+    assert np.array_equal(acc.D_opt_KYinit(torch.tensor(H, device="cuda")), golden_traj["ky_x0"])
+    assert np.array_equal(acc.D_opt_KYinit(H[:, :150]), np.ones(150) / 150)       # n <= 2m: uniform
+    xa, Fa, SPa, SNa, Ta = acc.D_opt_FW_away(H, golden_traj["ky_x0"], 1e-8, 1000, verbose=False)
+    n = min(len(Fa), len(golden_traj["dfwa_ky_F"]))
+    assert np.max(np.abs(Fa[:n] - golden_traj["dfwa_ky_F"][:n]) / np.abs(golden_traj["dfwa_ky_F"][:n])) <= 1e-9
