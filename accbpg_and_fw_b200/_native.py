@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libaccbpg_b200.so")
 
 _CTYPES = {
     "void*": ctypes.c_void_p,
+    "const void*": ctypes.c_void_p,
     "void**": ctypes.POINTER(ctypes.c_void_p),
     "const double*": ctypes.c_void_p,     # device or host address passed as an integer
     "double*": ctypes.c_void_p,

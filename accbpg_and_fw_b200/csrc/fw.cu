@@ -65,24 +65,31 @@ __device__ __forceinline__ void fw_block_argmin(double& v, long long& i, double*
 //   fmask  first index outside the support -> decides the tie when every support entry equals w_max
 //                                            (then (w - w_max)*[x > thr] is 0 everywhere and np.argmin returns the first index)
 // thr = 1e-8 with away steps (:147), 0 without (:60).
-struct FwCand {
+struct FwCand {                  // 64 bytes; the column-sharded loop all-gathers one per rank
     double amax; long long imax;
-    double smin; long long imin;
-    long long fmask;
+    double smin; long long imin; double xmin;      // support minimum of w, its index, x there
+    long long fmask; double wmask; double xmask;   // first index outside the support, w and x there
 };
 constexpr long long FW_NOIDX = 0x7fffffffffffffffLL;
 __device__ __forceinline__ void fw_cand_init(FwCand& c) {
-    c.amax = FW_INF; c.imax = FW_NOIDX; c.smin = FW_INF; c.imin = FW_NOIDX; c.fmask = FW_NOIDX;
+    c.amax = FW_INF; c.imax = FW_NOIDX; c.smin = FW_INF; c.imin = FW_NOIDX; c.xmin = 0.0;
+    c.fmask = FW_NOIDX; c.wmask = 0.0; c.xmask = 0.0;
+}
+__device__ __forceinline__ void fw_smin_combine(FwCand& c, double v2, long long i2, double x2) {
+    if (v2 < c.smin || (v2 == c.smin && i2 < c.imin)) { c.smin = v2; c.imin = i2; c.xmin = x2; }
+}
+__device__ __forceinline__ void fw_mask_combine(FwCand& c, long long i2, double w2, double x2) {
+    if (i2 < c.fmask) { c.fmask = i2; c.wmask = w2; c.xmask = x2; }
 }
 __device__ __forceinline__ void fw_cand_add(FwCand& c, double wi, double xi, long long i, double thr) {
     fw_arg_combine(c.amax, c.imax, -wi, i);
-    if (xi > thr) fw_arg_combine(c.smin, c.imin, wi, i);
-    else if (i < c.fmask) c.fmask = i;
+    if (xi > thr) fw_smin_combine(c, wi, i, xi);
+    else fw_mask_combine(c, i, wi, xi);
 }
 __device__ __forceinline__ void fw_cand_merge(FwCand& c, const FwCand& o) {
     fw_arg_combine(c.amax, c.imax, o.amax, o.imax);
-    fw_arg_combine(c.smin, c.imin, o.smin, o.imin);
-    if (o.fmask < c.fmask) c.fmask = o.fmask;
+    fw_smin_combine(c, o.smin, o.imin, o.xmin);
+    fw_mask_combine(c, o.fmask, o.wmask, o.xmask);
 }
 __device__ __forceinline__ void fw_cand_warp(FwCand& c) {
 #pragma unroll
@@ -92,7 +99,10 @@ __device__ __forceinline__ void fw_cand_warp(FwCand& c) {
         q.imax = __shfl_xor_sync(0xffffffffu, c.imax, o);
         q.smin = __shfl_xor_sync(0xffffffffu, c.smin, o);
         q.imin = __shfl_xor_sync(0xffffffffu, c.imin, o);
+        q.xmin = __shfl_xor_sync(0xffffffffu, c.xmin, o);
         q.fmask = __shfl_xor_sync(0xffffffffu, c.fmask, o);
+        q.wmask = __shfl_xor_sync(0xffffffffu, c.wmask, o);
+        q.xmask = __shfl_xor_sync(0xffffffffu, c.xmask, o);
         fw_cand_merge(c, q);
     }
 }
@@ -121,7 +131,12 @@ struct FwParams {
     int nblk;                 // column blocks of the pass
     int nr1;                  // leading CTAs that update Hinv instead (they start first, so they read the step's
                               // coefficients long before the tail of the same launch replaces them)
-    int decide;               // pass kernel: take the decision of iteration k in the tail
+    int decide;               // tail of the selecting kernels: 0 nothing, 1 merge + take the decision of iteration k,
+                              // 2 merge only and write the record to cand_out (column-sharded: the ranks' records
+                              // are exchanged before accbpg_fw_decide)
+    FwCand* cand_out;
+    int64_t col_offset;       // global index of local column 0
+    int sharded;              // decide: the chosen column may live on another rank (then v <- 0 here)
     int reverse;              // pass kernel: walk the column blocks from the end
 };
 
@@ -133,17 +148,14 @@ __device__ __forceinline__ void fw_decide(const FwParams& p, const FwCand& cd, i
         const double md = (double)p.m;
         const double wmax = -cd.amax;
         const long long imax = cd.imax;
-        long long jmin;
-        if (p.away) {
-            // argmin((w - w_max) * [x > 1e-8]): the support minimum unless it ties with the zeros of the mask
-            if (cd.imin != FW_NOIDX && cd.smin < wmax) jmin = cd.imin;
-            else jmin = cd.imin < cd.fmask ? cd.imin : cd.fmask;
-        } else {
-            jmin = cd.imin;
+        long long jmin = cd.imin;
+        double wj = cd.smin, xj = cd.xmin;
+        if (p.away && !(cd.imin != FW_NOIDX && cd.smin < wmax) && cd.fmask < cd.imin) {
+            // argmin((w - w_max) * [x > 1e-8]) is the support minimum unless that ties with the zeros of the mask:
+            // then every entry is 0 and np.argmin returns the first index overall
+            jmin = cd.fmask; wj = cd.wmask; xj = cd.xmask;
         }
-        if (jmin == FW_NOIDX) jmin = 0;              // empty support cannot happen for x on the simplex
-        const double wj = p.w[jmin];
-        const double xj = p.x[jmin];
+        if (jmin == FW_NOIDX) { jmin = 0; wj = wmax; xj = 1.0; }      // empty support cannot happen on the simplex
         const double logdet = c[C_LOGDET_HI] + c[C_LOGDET_LO];
         const double eps_pos = wmax / md - 1.0;
         const double eps_neg = 1.0 - wj / md;
@@ -195,8 +207,10 @@ __device__ __forceinline__ void fw_decide(const FwParams& p, const FwCand& cd, i
     }
     __syncthreads();
     if (*sh_go) {
-        const long long col = *sh_idx;
-        for (int r = threadIdx.x; r < p.m; r += blockDim.x) p.v[r] = p.V[(int64_t)r * p.ldv + col];
+        const long long col = *sh_idx - p.col_offset;
+        const bool mine = (col >= 0 && col < p.n);
+        // column-sharded: ranks that do not own the column contribute zeros; the caller sums v over the ranks
+        for (int r = threadIdx.x; r < p.m; r += blockDim.x) p.v[r] = mine ? p.V[(int64_t)r * p.ldv + col] : 0.0;
     }
 }
 
@@ -220,17 +234,36 @@ __device__ __forceinline__ void fw_select_tail(const FwParams& p, FwCand& cd, in
     for (int b = threadIdx.x; b < nparts; b += blockDim.x) {
         FwCand q;
         q.amax = ld_cg(&p.parts[b].amax); q.imax = __ldcg(&p.parts[b].imax);
-        q.smin = ld_cg(&p.parts[b].smin); q.imin = __ldcg(&p.parts[b].imin);
-        q.fmask = __ldcg(&p.parts[b].fmask);
+        q.smin = ld_cg(&p.parts[b].smin); q.imin = __ldcg(&p.parts[b].imin); q.xmin = ld_cg(&p.parts[b].xmin);
+        q.fmask = __ldcg(&p.parts[b].fmask); q.wmask = ld_cg(&p.parts[b].wmask); q.xmask = ld_cg(&p.parts[b].xmask);
         fw_cand_merge(cd, q);
     }
     fw_cand_block(cd, sh_c);
-    if (threadIdx.x < 32) {
-        if (threadIdx.x == 0) sh_c[0] = cd;
-    }
+    if (threadIdx.x == 0) sh_c[0] = cd;
     __syncthreads();
     cd = sh_c[0];
+    if (p.decide == 2) {
+        if (threadIdx.x == 0) *p.cand_out = cd;
+        return;
+    }
     fw_decide(p, cd, sh_go, sh_idx);
+}
+
+// column-sharded decision: merge the ranks' records in rank order, decide, gather the column if it lives here
+__global__ void __launch_bounds__(FW_THREADS) fw_decide_kernel(FwParams p, const FwCand* recs, int world) {
+    __shared__ int sh_go;
+    __shared__ long long sh_idx;
+    if (ld_cg(&p.ctrl[C_STOP]) != 0.0) return;
+    FwCand cd;
+    fw_cand_init(cd);
+    for (int r = 0; r < world; ++r) {
+        FwCand q;
+        q.amax = ld_cg(&recs[r].amax); q.imax = __ldcg(&recs[r].imax);
+        q.smin = ld_cg(&recs[r].smin); q.imin = __ldcg(&recs[r].imin); q.xmin = ld_cg(&recs[r].xmin);
+        q.fmask = __ldcg(&recs[r].fmask); q.wmask = ld_cg(&recs[r].wmask); q.xmask = ld_cg(&recs[r].xmask);
+        fw_cand_merge(cd, q);
+    }
+    fw_decide(p, cd, &sh_go, &sh_idx);
 }
 
 // standalone selection + decision (first iteration of a batch)
@@ -240,13 +273,13 @@ __global__ void __launch_bounds__(FW_THREADS) fw_select_kernel(FwParams p) {
     __shared__ int sh_go;
     __shared__ long long sh_idx;
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (ld_cg(&p.ctrl[C_STOP]) != 0.0) return;
+    if (p.decide != 2 && ld_cg(&p.ctrl[C_STOP]) != 0.0) return;
     const double thr = p.away ? 1.0e-8 : 0.0;
     FwCand cd;
     fw_cand_init(cd);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride)
-        fw_cand_add(cd, p.w[i], p.x[i], i, thr);
+        fw_cand_add(cd, p.w[i], p.x[i], i + p.col_offset, thr);
     fw_select_tail(p, cd, blockIdx.x, gridDim.x, sh_c, &sh_last, &sh_go, &sh_idx);
 }
 
@@ -357,10 +390,10 @@ __global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(FwParams p) {
                 const double pj = ((part[0][2 * ct + e] + part[1][2 * ct + e]) + part[2][2 * ct + e]) + part[3][2 * ct + e];
                 const double wn = (p.w[j + e] - cs * (pj * pj)) / den;
                 double xn = p.x[j + e] * den;
-                if (j + e == idx) xn = xn + tsign;
+                if (j + e + p.col_offset == idx) xn = xn + tsign;
                 p.w[j + e] = wn;
                 p.x[j + e] = xn;
-                fw_cand_add(cd, wn, xn, j + e, thr);
+                fw_cand_add(cd, wn, xn, j + e + p.col_offset, thr);
             }
         }
     }
@@ -420,7 +453,7 @@ size_t accbpg_fw_workspace_bytes(int m, int64_t n_local) {
     // dopt workspace (gram / factor / Linv / gradient partials) + v and u vectors
     size_t base = accbpg_dopt_workspace_bytes(m, n_local);
     const size_t nparts = (size_t)((n_local + 127) / 128) + 2048;        // selection candidates, one per selecting CTA
-    return base + 2 * (((size_t)m + 31) / 32 * 32 * 8) + nparts * 40 + 256;
+    return base + 2 * (((size_t)m + 31) / 32 * 32 * 8) + nparts * 64 + 256;
 }
 
 // D_opt_alg.py:39-45 / :123-129:  M = V diag(x0) V^T, Hinv = M^{-1}, w_j = v_j^T Hinv v_j, log det M
@@ -448,6 +481,42 @@ int accbpg_fw_setup(void* ctx, void* stream, const double* V, int m, int64_t n, 
     return ACCBPG_OK;
 }
 
+struct FwLaunch {
+    FwParams p;
+    int sel_grid, hv_grid, nblk, r1_ctas;
+    size_t pass_smem;
+    bool pass_vec;
+};
+
+static int fw_prepare(Ctx* c, const double* V, int m, int64_t n, int64_t ldv, int away, double eps, void* ws, double* Hinv,
+                      double* x, double* w, double* ctrl, double* hist_F, double* hist_SP, double* hist_SN,
+                      double* hist_T, FwLaunch* L) {
+    if (m < 1 || n < 1 || ldv < n) return arg_err("fw: shape");
+    size_t base = accbpg_dopt_workspace_bytes(m, n);
+    double* v = (double*)((char*)ws + base);
+    double* u = v + ((size_t)m + 31) / 32 * 32;
+    FwCand* parts = (FwCand*)(u + ((size_t)m + 31) / 32 * 32);
+    const int64_t nblk64 = (n + FWP_COLS - 1) / FWP_COLS;
+    if (nblk64 > 2000000000LL) return arg_err("fw: n too large");
+    L->nblk = (int)nblk64;
+    L->sel_grid = grid_for(c, n, FW_THREADS, 4, 2);
+    L->hv_grid = (m + 7) / 8;
+    L->r1_ctas = c->sm_count / 4 < 1 ? 1 : c->sm_count / 4;
+    L->pass_smem = (size_t)m * sizeof(double);
+    if (L->pass_smem > 160 * 1024) return arg_err("fw: m too large for the shared-memory copy of u");
+    L->pass_vec = ((reinterpret_cast<uintptr_t>(V) & 15u) == 0) && (ldv % 2 == 0);
+    if (L->pass_smem > 32 * 1024) {
+        if (L->pass_vec) ACCBPG_CUDA(cudaFuncSetAttribute(fw_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->pass_smem));
+        else ACCBPG_CUDA(cudaFuncSetAttribute(fw_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->pass_smem));
+    }
+    FwParams& p = L->p;
+    p.V = V; p.m = m; p.n = n; p.ldv = ldv; p.x = x; p.w = w; p.Hinv = Hinv; p.u = u; p.v = v; p.ctrl = ctrl;
+    p.hist_F = hist_F; p.hist_SP = hist_SP; p.hist_SN = hist_SN; p.hist_T = hist_T;
+    p.parts = parts; p.counter = c->d_counter; p.away = away; p.eps = eps; p.nblk = L->nblk; p.nr1 = L->r1_ctas;
+    p.k = 0; p.decide = 0; p.reverse = 0; p.cand_out = nullptr; p.col_offset = 0; p.sharded = 0;
+    return ACCBPG_OK;
+}
+
 // run iterations k_start .. k_start+k_count-1 (no-ops after the stop flag is raised):
 //   select+decide(k_start);  then per iteration  u = Hinv v;  pass (+ rank-one update of Hinv, + decision of k+1)
 // Launches are chained with programmatic dependent launch.
@@ -458,29 +527,13 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !V || !ws || !Hinv || !x || !w || !ctrl || !hist_F || !hist_SP || !hist_SN || !hist_T)
         return arg_err("fw_run: NULL pointer");
-    if (m < 1 || n < 1 || ldv < n || k_count < 0) return arg_err("fw_run: shape");
+    if (k_count < 0) return arg_err("fw_run: shape");
     if (k_count == 0) return ACCBPG_OK;
-    size_t base = accbpg_dopt_workspace_bytes(m, n);
-    double* v = (double*)((char*)ws + base);
-    double* u = v + ((size_t)m + 31) / 32 * 32;
-    FwCand* parts = (FwCand*)(u + ((size_t)m + 31) / 32 * 32);
-    const int64_t nblk64 = (n + FWP_COLS - 1) / FWP_COLS;
-    if (nblk64 > 2000000000LL) return arg_err("fw_run: n too large");
-    const int nblk = (int)nblk64;
-    const int sel_grid = grid_for(c, n, FW_THREADS, 4, 2);
-    const int hv_grid = (m + 7) / 8;
-    int r1_ctas = c->sm_count / 4;
-    if (r1_ctas < 1) r1_ctas = 1;
-    const size_t pass_smem = (size_t)m * sizeof(double);
-    if (pass_smem > 160 * 1024) return arg_err("fw_run: m too large for the shared-memory copy of u");
-    const bool pass_vec = ((reinterpret_cast<uintptr_t>(V) & 15u) == 0) && (ldv % 2 == 0);
-    auto pass_fn = pass_vec ? fw_pass_kernel<true> : fw_pass_kernel<false>;
-    if (pass_smem > 32 * 1024)
-        ACCBPG_CUDA(cudaFuncSetAttribute(pass_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem));
-    FwParams p;
-    p.V = V; p.m = m; p.n = n; p.ldv = ldv; p.x = x; p.w = w; p.Hinv = Hinv; p.u = u; p.v = v; p.ctrl = ctrl;
-    p.hist_F = hist_F; p.hist_SP = hist_SP; p.hist_SN = hist_SN; p.hist_T = hist_T;
-    p.parts = parts; p.counter = c->d_counter; p.away = away; p.eps = eps; p.nblk = nblk; p.nr1 = r1_ctas;
+    FwLaunch L;
+    int rc = fw_prepare(c, V, m, n, ldv, away, eps, ws, Hinv, x, w, ctrl, hist_F, hist_SP, hist_SN, hist_T, &L);
+    if (rc) return rc;
+    FwParams& p = L.p;
+    auto pass_fn = L.pass_vec ? fw_pass_kernel<true> : fw_pass_kernel<false>;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -489,24 +542,110 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
     cfg.attrs = attr;
     // the first decision of the batch
     p.k = k_start; p.decide = 1; p.reverse = 0;
-    cfg.gridDim = dim3(sel_grid); cfg.blockDim = dim3(FW_THREADS); cfg.dynamicSmemBytes = 0; cfg.numAttrs = 0;
+    cfg.gridDim = dim3(L.sel_grid); cfg.blockDim = dim3(FW_THREADS); cfg.dynamicSmemBytes = 0; cfg.numAttrs = 0;
     ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, fw_select_kernel, p));
     ACCBPG_LAUNCHED("fw_select_kernel");
     for (int k = k_start; k < k_start + k_count; ++k) {
         ProfScope ps_iter(P_FW_ITER, s);
-        cfg.gridDim = dim3(hv_grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.numAttrs = 1;
-        ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, fw_hv_kernel, (const double*)Hinv, m, (const double*)v, u, (const double*)ctrl));
+        cfg.gridDim = dim3(L.hv_grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.numAttrs = 1;
+        ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, fw_hv_kernel, (const double*)Hinv, m, (const double*)p.v, p.u, (const double*)ctrl));
         ACCBPG_LAUNCHED("fw_hv_kernel");
         p.k = k + 1;                                        // the tail decides the next iteration ...
         p.decide = (k + 1 < k_start + k_count) ? 1 : 0;     // ... except after the last pass of the batch
         p.reverse = k & 1;
-        cfg.gridDim = dim3(nblk + r1_ctas); cfg.blockDim = dim3(FWP_THREADS); cfg.dynamicSmemBytes = pass_smem;
+        cfg.gridDim = dim3(L.nblk + L.r1_ctas); cfg.blockDim = dim3(FWP_THREADS); cfg.dynamicSmemBytes = L.pass_smem;
         {
             ProfScope ps(P_FW_PASS, s);
             ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, pass_fn, p));
         }
         ACCBPG_LAUNCHED("fw_pass_kernel");
     }
+    return ACCBPG_OK;
+}
+
+// ---- column-sharded building blocks (one rank's slab of V and slices of x, w; Hinv, ctrl and the histories replicated).
+// Per iteration the caller runs:  accbpg_fw_decide(k, records of all ranks) -> sum v over the ranks ->
+// accbpg_fw_step(k) [u = Hinv v; local pass + rank-one update; local record of the updated slice] -> all-gather records.
+size_t accbpg_fw_record_bytes(void) { return sizeof(FwCand); }
+
+int accbpg_fw_select_local(void* ctx, void* stream, int64_t n_local, int64_t col_offset, int away, const double* x,
+                           const double* w, void* ws, int m, void* d_record_out) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !x || !w || !ws || !d_record_out) return arg_err("fw_select_local: NULL pointer");
+    FwLaunch L;
+    int rc = fw_prepare(c, x /* any aligned pointer: V is not read */, m, n_local, n_local, away, 0.0, ws, nullptr,
+                        (double*)x, (double*)w, nullptr, nullptr, nullptr, nullptr, nullptr, &L);
+    if (rc) return rc;
+    L.p.decide = 2; L.p.cand_out = (FwCand*)d_record_out; L.p.col_offset = col_offset;
+    fw_select_kernel<<<L.sel_grid, FW_THREADS, 0, s>>>(L.p);
+    ACCBPG_LAUNCHED("fw_select_kernel");
+    return ACCBPG_OK;
+}
+
+int accbpg_fw_decide(void* ctx, void* stream, const double* V, int m, int64_t n_local, int64_t ldv, int64_t col_offset,
+                     int away, double eps, int k, const void* d_records, int world, void* ws, double* ctrl,
+                     double* hist_F, double* hist_SP, double* hist_SN, double* hist_T, double* d_vcol) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !V || !d_records || !ws || !ctrl || !hist_F || !hist_SP || !hist_SN || !hist_T || !d_vcol)
+        return arg_err("fw_decide: NULL pointer");
+    if (world < 1) return arg_err("fw_decide: world");
+    FwLaunch L;
+    int rc = fw_prepare(c, V, m, n_local, ldv, away, eps, ws, nullptr, nullptr, nullptr, ctrl, hist_F, hist_SP, hist_SN,
+                        hist_T, &L);
+    if (rc) return rc;
+    L.p.k = k; L.p.decide = 1; L.p.col_offset = col_offset; L.p.sharded = 1; L.p.v = d_vcol;
+    fw_decide_kernel<<<1, FW_THREADS, 0, s>>>(L.p, (const FwCand*)d_records, world);
+    ACCBPG_LAUNCHED("fw_decide_kernel");
+    return ACCBPG_OK;
+}
+
+int accbpg_fw_step(void* ctx, void* stream, const double* V, int m, int64_t n_local, int64_t ldv, int64_t col_offset,
+                   int away, int k, void* ws, double* Hinv, const double* d_vcol, double* x, double* w, double* ctrl,
+                   void* d_record_out) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !V || !ws || !Hinv || !d_vcol || !x || !w || !ctrl || !d_record_out) return arg_err("fw_step: NULL pointer");
+    FwLaunch L;
+    int rc = fw_prepare(c, V, m, n_local, ldv, away, 0.0, ws, Hinv, x, w, ctrl, nullptr, nullptr, nullptr, nullptr, &L);
+    if (rc) return rc;
+    FwParams& p = L.p;
+    fw_hv_kernel<<<L.hv_grid, 256, 0, s>>>(Hinv, m, d_vcol, p.u, ctrl);
+    ACCBPG_LAUNCHED("fw_hv_kernel");
+    p.k = k + 1; p.decide = 2; p.reverse = k & 1; p.cand_out = (FwCand*)d_record_out; p.col_offset = col_offset;
+    auto pass_fn = L.pass_vec ? fw_pass_kernel<true> : fw_pass_kernel<false>;
+    {
+        ProfScope ps(P_FW_PASS, s);
+        pass_fn<<<L.nblk + L.r1_ctas, FWP_THREADS, L.pass_smem, s>>>(p);
+    }
+    ACCBPG_LAUNCHED("fw_pass_kernel");
+    return ACCBPG_OK;
+}
+
+// setup from an already summed Gram matrix M = V diag(x0) V^T (column-sharded: the caller all-reduces it):
+// Hinv = M^{-1}, w_j = v_j^T Hinv v_j for the local columns, ctrl <- {log det M, not stopped}
+int accbpg_fw_setup_from_gram(void* ctx, void* stream, const double* V, int m, int64_t n_local, int64_t ldv,
+                              const double* M, void* ws, double* Hinv, double* w, double* ctrl) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !V || !M || !ws || !Hinv || !w || !ctrl) return arg_err("fw_setup_from_gram: NULL pointer");
+    double* slot = c->d_slots + 247;
+    int rc = accbpg_dopt_factor(ctx, stream, m, M, nullptr, 1, ws, slot);
+    if (rc) return rc;
+    rc = accbpg_dopt_grad(ctx, stream, V, m, n_local, ldv, ws, w);
+    if (rc) return rc;
+    int g = grid_for(c, n_local, 256, 2, 8);
+    negate_kernel<<<g, 256, 0, s>>>(n_local, w);
+    ACCBPG_LAUNCHED("negate_kernel");
+    fw_ctrl_init_from_slot_kernel<<<1, 32, 0, s>>>(ctrl, slot);
+    ACCBPG_LAUNCHED("fw_ctrl_init");
+    int mp = 0;
+    size_t off = dopt_linv_offset(m, n_local, c->sm_count, &mp);
+    const double* Linv = (const double*)((const char*)ws + off);
+    dim3 grid((m + 31) / 32, (m + 31) / 32);
+    fw_hinv_kernel<<<grid, 256, 0, s>>>(Linv, m, mp, Hinv);
+    ACCBPG_LAUNCHED("fw_hinv_kernel");
     return ACCBPG_OK;
 }
 

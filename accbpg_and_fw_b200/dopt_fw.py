@@ -78,11 +78,86 @@ def _run(V, x0, eps, maxitrs, away, verbose, verbskip, batch, device, index_log)
     return like_input(x, host), F, SP, SN, T
 
 
-def D_opt_FW(V, x0, eps, maxitrs, verbose=True, verbskip=1, batch=64, device=None, index_log=None):
-    """Frank-Wolfe for D-optimal design.   accbpg/D_opt_alg.py:9-88.   Returns (x, F, SP, SN, T)."""
+def _run_sharded(V, x0, eps, maxitrs, away, verbose, verbskip, batch, device, index_log, shard):
+    """Column-sharded loop: V is this rank's column slab, x0 its slice; Hinv, the control block and the histories are
+    replicated.  Per iteration: decision from all ranks' selection records, all-reduce of the chosen column (only its
+    owner contributes), u = Hinv v + local pass + rank-one update, all-gather of the new records.  No host round trip
+    except one read of the control block per batch."""
+    import torch.distributed as dist
+    rt = Runtime.get(device)
+    t_start = time.time()
+    host = is_host(x0)
+    Vd = rt.to_device(V)
+    m, n = int(Vd.shape[0]), int(Vd.shape[1])
+    assert n == shard.n_local, "V must be this rank's column slab (ColumnShard.cols)"
+    x = rt.to_device(x0).clone()
+    assert x.numel() == n, "x0 must be this rank's slice (ColumnShard.part)"
+    dev = rt.device
+    ws = rt.workspace(("fw", m, n), lib.accbpg_fw_workspace_bytes(m, n))
+    Hinv = torch.empty(m, m, dtype=torch.float64, device=dev)
+    M = torch.empty(m, m, dtype=torch.float64, device=dev)
+    w = torch.empty(n, dtype=torch.float64, device=dev)
+    vcol = torch.zeros(m, dtype=torch.float64, device=dev)
+    ctrl = torch.zeros(NCTRL, dtype=torch.float64, device=dev)
+    hist = torch.zeros(4, max(int(maxitrs), 1), dtype=torch.float64, device=dev)
+    rec_doubles = lib.accbpg_fw_record_bytes() // 8
+    rec = torch.zeros(rec_doubles, dtype=torch.float64, device=dev)
+    recs = torch.zeros(shard.world * rec_doubles, dtype=torch.float64, device=dev)
+    st = Vd.stride(0)
+    nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, Vd.data_ptr(), m, n, st, x.data_ptr(), ws.data_ptr(), M.data_ptr()))
+    shard.sum_(M)
+    nat.check(lib.accbpg_fw_setup_from_gram(rt.ctx, rt.stream, Vd.data_ptr(), m, n, st, M.data_ptr(), ws.data_ptr(),
+                                            Hinv.data_ptr(), w.data_ptr(), ctrl.data_ptr()))
+    rt.read(0, 0)
+    nat.check(lib.accbpg_fw_select_local(rt.ctx, rt.stream, n, shard.lo, int(away), x.data_ptr(), w.data_ptr(),
+                                         ws.data_ptr(), m, rec.data_ptr()))
+    shard.all_gather_equal(recs, rec)
+    if verbose and shard.rank == 0:
+        print("\nSolving D-opt design problem using Frank-Wolfe method" + (" with away steps" if away else ""))
+        print("     k      F(x)     pos_slack   neg_slack    time")
+    t_setup = time.time() - t_start
+    k = 0
+    done = 0
+    while k < maxitrs:
+        cnt = 1 if index_log is not None else min(batch, maxitrs - k)
+        for kk in range(k, k + cnt):
+            nat.check(lib.accbpg_fw_decide(rt.ctx, rt.stream, Vd.data_ptr(), m, n, st, shard.lo, int(away), float(eps), kk,
+                                           recs.data_ptr(), shard.world, ws.data_ptr(), ctrl.data_ptr(),
+                                           hist[0].data_ptr(), hist[1].data_ptr(), hist[2].data_ptr(), hist[3].data_ptr(),
+                                           vcol.data_ptr()))
+            shard.sum_(vcol)
+            nat.check(lib.accbpg_fw_step(rt.ctx, rt.stream, Vd.data_ptr(), m, n, st, shard.lo, int(away), kk, ws.data_ptr(),
+                                         Hinv.data_ptr(), vcol.data_ptr(), x.data_ptr(), w.data_ptr(), ctrl.data_ptr(),
+                                         rec.data_ptr()))
+            shard.all_gather_equal(recs, rec)
+        c = ctrl.cpu().numpy()
+        done = int(c[C_NITER])
+        if index_log is not None and done == k + 1:
+            index_log.append((int(c[C_IMAX]), int(c[C_JMIN]), None if c[C_STOP] != 0 else int(c[C_MODE])))
+        if verbose and shard.rank == 0 and done > k:
+            hb = hist[:, k:done].cpu().numpy()
+            for q in range(k, done):
+                if q % verbskip == 0:
+                    print("{0:6d}  {1:10.3e}  {2:10.3e}  {3:10.3e}".format(q, hb[0, q - k], hb[1, q - k], hb[2, q - k]))
+        k += cnt
+        if c[C_STOP] != 0:
+            break
+    hh = hist[:, :done].cpu().numpy()
+    F, SP, SN = hh[0].copy(), hh[1].copy(), hh[2].copy()
+    T = t_setup + (hh[3] - hh[3][0]) * 1e-9 if done > 0 else np.zeros(0)
+    return like_input(x, host), F, SP, SN, T
+
+
+def D_opt_FW(V, x0, eps, maxitrs, verbose=True, verbskip=1, batch=64, device=None, index_log=None, shard=None):
+    """Frank-Wolfe for D-optimal design.   accbpg/D_opt_alg.py:9-88.   Returns (x, F, SP, SN, T).
+    shard: a ColumnShard when V / x0 are this rank's column slab / slice (the returned x is the local slice)."""
+    if shard is not None and shard.world > 1:
+        return _run_sharded(V, x0, eps, maxitrs, 0, verbose, verbskip, batch, device, index_log, shard)
     return _run(V, x0, eps, maxitrs, 0, verbose, verbskip, batch, device, index_log)
 
 
-def D_opt_FW_away(V, x0, eps, maxitrs, verbose=True, verbskip=1, batch=64, device=None, index_log=None):
+def D_opt_FW_away(V, x0, eps, maxitrs, verbose=True, verbskip=1, batch=64, device=None, index_log=None, shard=None):
     """Frank-Wolfe with away steps (Wolfe-Atwood).   accbpg/D_opt_alg.py:91-185.   Returns (x, F, SP, SN, T)."""
+    if shard is not None and shard.world > 1:
+        return _run_sharded(V, x0, eps, maxitrs, 1, verbose, verbskip, batch, device, index_log, shard)
     return _run(V, x0, eps, maxitrs, 1, verbose, verbskip, batch, device, index_log)

@@ -239,6 +239,28 @@ int accbpg_fw_run(void* ctx, void* stream, const double* d_V, int m, int64_t n, 
                   int k_start, int k_count, void* d_ws, double* d_Hinv, double* d_x, double* d_w, double* d_ctrl,
                   double* d_hist_F, double* d_hist_SP, double* d_hist_SN, double* d_hist_T);
 
+
+/* Column-sharded building blocks of the same loop (D_opt_alg.py:9-185 with V split by columns over the ranks;
+ * Hinv, the control block and the histories are replicated).  A selection record (accbpg_fw_record_bytes() bytes)
+ * carries a rank's arg-max, support arg-min and first off-support entry with their GLOBAL indices and the w / x values
+ * the step rule needs.  Per iteration k the caller runs
+ *   accbpg_fw_decide(k, all ranks' records)  ->  all-reduce(sum) of d_vcol (only the owner of the chosen column
+ *   contributes non-zeros)  ->  accbpg_fw_step(k): u = Hinv v, the local pass over V, the rank-one update of Hinv and
+ *   the record of the updated local slice  ->  all-gather of the records.
+ * The decision merges the records in rank order with the lowest-index tie-break, so the vertex sequence does not
+ * depend on the number of ranks. */
+size_t accbpg_fw_record_bytes(void);
+int accbpg_fw_setup_from_gram(void* ctx, void* stream, const double* d_V, int m, int64_t n_local, int64_t ldv,
+                              const double* d_M, void* d_ws, double* d_Hinv, double* d_w, double* d_ctrl);
+int accbpg_fw_select_local(void* ctx, void* stream, int64_t n_local, int64_t col_offset, int away, const double* d_x,
+                           const double* d_w, void* d_ws, int m, void* d_record_out);
+int accbpg_fw_decide(void* ctx, void* stream, const double* d_V, int m, int64_t n_local, int64_t ldv, int64_t col_offset,
+                     int away, double eps, int k, const void* d_records, int world, void* d_ws, double* d_ctrl,
+                     double* d_hist_F, double* d_hist_SP, double* d_hist_SN, double* d_hist_T, double* d_vcol);
+int accbpg_fw_step(void* ctx, void* stream, const double* d_V, int m, int64_t n_local, int64_t ldv, int64_t col_offset,
+                   int away, int k, void* d_ws, double* d_Hinv, const double* d_vcol, double* d_x, double* d_w,
+                   double* d_ctrl, void* d_record_out);
+
 #ifdef __cplusplus
 }
 #endif

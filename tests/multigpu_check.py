@@ -63,7 +63,19 @@ def main():
         xs, Fs, Lss, Ts = acc.FW_alg_div_step(f, h, Lo, sh.part(x0), maxitrs=min(its, 60), gamma=2.0, lmo=lmo, verbose=False)
         xr, Fr, Lsr, Tr = orc.FW_alg_div_step(fo, ho, Lo, x0, min(its, 60), 2.0, orc.make_lmo_simplex(), vertex_log=log_o)
         assert ferr(Fs, Fr) <= 1e-9 and np.array_equal(Lss, Lsr)
-        report[f"dopt_{m}x{n}"] = (ferr(F, Fo), ferr(out[1], outo[1]), ferr(Fs, Fr))
+        # D_opt_FW / D_opt_FW_away with V column-sharded: owner-contributed column, replicated Hinv
+        for away, fn_g, fn_o in ((1, acc.D_opt_FW_away, orc.D_opt_FW_away), (0, acc.D_opt_FW, orc.D_opt_FW)):
+            glog, olog = [], []
+            xa, Fa, SPa, SNa, Ta = fn_g(sh.cols(fo.H), sh.part(x0), 1e-8, min(its, 80), verbose=False, shard=sh,
+                                        index_log=glog)
+            xb, Fb, SPb, SNb, Tb = fn_o(fo.H, x0, 1e-8, min(its, 80), index_log=olog)
+            assert len(Fa) == len(Fb) and ferr(Fa, Fb) <= 1e-9, (len(Fa), len(Fb))
+            assert [(a, b) for a, b, *_ in glog[:len(olog) - 1]] == [(a, b) for a, b, *_ in olog[:len(olog) - 1]]
+            assert np.max(np.abs(gathered(sh, xa) - xb)) <= 1e-9
+        xa, Fa, SPa, SNa, Ta = acc.D_opt_FW_away(sh.cols(fo.H), sh.part(x0), 1e-8, its, verbose=False, shard=sh)   # batched
+        xb, Fb, SPb, SNb, Tb = orc.D_opt_FW_away(fo.H, x0, 1e-8, its)
+        assert len(Fa) == len(Fb) and ferr(Fa, Fb) <= 1e-9
+        report[f"dopt_{m}x{n}"] = (ferr(F, Fo), ferr(out[1], outo[1]), ferr(Fs, Fr), ferr(Fa, Fb))
     # LMO tie across ranks: lowest global index wins
     n = 1000
     sh = acc.ColumnShard(n)

@@ -100,3 +100,75 @@ def test_ky_init_golden(acc, golden_traj):
     xa, Fa, SPa, SNa, Ta = acc.D_opt_FW_away(H, golden_traj["ky_x0"], 1e-8, 1000, verbose=False)
     n = min(len(Fa), len(golden_traj["dfwa_ky_F"]))
     assert np.max(np.abs(Fa[:n] - golden_traj["dfwa_ky_F"][:n]) / np.abs(golden_traj["dfwa_ky_F"][:n])) <= 1e-9
+
+
+@pytest.mark.parametrize("away,world", [(1, 2), (0, 3), (1, 4)])
+def test_sharded_fw_building_blocks_on_one_gpu(acc, away, world):
+    """The column-sharded Frank-Wolfe loop emulated on one GPU: `world` slabs processed one after the other, records
+    and the chosen column exchanged by hand exactly as the collectives would.  F, slacks and the vertex sequence must
+    be those of the single-slab device loop (and of the oracle): the decision does not depend on the sharding."""
+    from accbpg_and_fw_b200 import _native as nat
+    from accbpg_and_fw_b200.dopt_fw import NCTRL, C_IMAX, C_JMIN, C_STOP, C_NITER
+    lib = nat.lib
+    rt = acc.Runtime.get()
+    m, n, its = 12, 203, 60
+    rng = np.random.RandomState(5)
+    V = rng.randn(m, n)
+    x0 = np.ones(n) / n
+    offs = acc.ColumnShard.partition(n, world)
+    dev = "cuda"
+    Vs = [torch.tensor(np.ascontiguousarray(V[:, offs[r]:offs[r + 1]]), device=dev) for r in range(world)]
+    xs = [torch.tensor(x0[offs[r]:offs[r + 1]].copy(), device=dev) for r in range(world)]
+    nl = [offs[r + 1] - offs[r] for r in range(world)]
+    wss = [torch.empty(lib.accbpg_fw_workspace_bytes(m, nl[r]), dtype=torch.uint8, device=dev) for r in range(world)]
+    M = torch.zeros(m, m, dtype=torch.float64, device=dev)
+    Mr = torch.empty(m, m, dtype=torch.float64, device=dev)
+    for r in range(world):
+        nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, Vs[r].data_ptr(), m, nl[r], nl[r], xs[r].data_ptr(),
+                                       wss[r].data_ptr(), Mr.data_ptr()))
+        M += Mr
+    Hinv = [torch.empty(m, m, dtype=torch.float64, device=dev) for _ in range(world)]
+    ws_ = [torch.empty(nl[r], dtype=torch.float64, device=dev) for r in range(world)]
+    ctrl = [torch.zeros(NCTRL, dtype=torch.float64, device=dev) for _ in range(world)]
+    hist = [torch.zeros(4, its, dtype=torch.float64, device=dev) for _ in range(world)]
+    rd = lib.accbpg_fw_record_bytes() // 8
+    recs = torch.zeros(world * rd, dtype=torch.float64, device=dev)
+    vcols = [torch.zeros(m, dtype=torch.float64, device=dev) for _ in range(world)]
+    for r in range(world):
+        nat.check(lib.accbpg_fw_setup_from_gram(rt.ctx, rt.stream, Vs[r].data_ptr(), m, nl[r], nl[r], M.data_ptr(),
+                                                wss[r].data_ptr(), Hinv[r].data_ptr(), ws_[r].data_ptr(), ctrl[r].data_ptr()))
+        nat.check(lib.accbpg_fw_select_local(rt.ctx, rt.stream, nl[r], offs[r], away, xs[r].data_ptr(), ws_[r].data_ptr(),
+                                             wss[r].data_ptr(), m, recs[r * rd:].data_ptr()))
+    log = []
+    for k in range(its):
+        for r in range(world):
+            h = hist[r]
+            nat.check(lib.accbpg_fw_decide(rt.ctx, rt.stream, Vs[r].data_ptr(), m, nl[r], nl[r], offs[r], away, 1e-9, k,
+                                           recs.data_ptr(), world, wss[r].data_ptr(), ctrl[r].data_ptr(), h[0].data_ptr(),
+                                           h[1].data_ptr(), h[2].data_ptr(), h[3].data_ptr(), vcols[r].data_ptr()))
+        vsum = sum(vcols)                                   # the all-reduce
+        c0 = ctrl[0].cpu().numpy()
+        if c0[C_STOP] != 0:
+            break
+        log.append((int(c0[C_IMAX]), int(c0[C_JMIN])))
+        new = torch.zeros_like(recs)
+        for r in range(world):
+            vr = vsum.clone()
+            nat.check(lib.accbpg_fw_step(rt.ctx, rt.stream, Vs[r].data_ptr(), m, nl[r], nl[r], offs[r], away, k,
+                                         wss[r].data_ptr(), Hinv[r].data_ptr(), vr.data_ptr(), xs[r].data_ptr(),
+                                         ws_[r].data_ptr(), ctrl[r].data_ptr(), new[r * rd:].data_ptr()))
+        torch.cuda.synchronize()
+        recs = new                                          # the all-gather
+    done = int(ctrl[0].cpu().numpy()[C_NITER])
+    F = hist[0][0, :done].cpu().numpy()
+    fn = orc.D_opt_FW_away if away else orc.D_opt_FW
+    olog = []
+    xo, Fo, SPo, SNo, To = fn(V, x0, 1e-9, its, index_log=olog)
+    nn = min(len(F), len(Fo))
+    assert nn >= its - 1
+    assert np.max(np.abs(F[:nn] - Fo[:nn]) / np.maximum(np.abs(Fo[:nn]), 1e-3)) <= 1e-9
+    assert [(a, b) for a, b in log[:nn - 1]] == [(a, b) for a, b, *_ in olog[:nn - 1]]
+    xfull = np.concatenate([t.cpu().numpy() for t in xs])
+    assert np.max(np.abs(xfull - xo)) <= 1e-9
+    for r in range(1, world):                               # replicated state stays identical
+        assert torch.equal(ctrl[r][:15], ctrl[0][:15]) and torch.equal(Hinv[r], Hinv[0])
