@@ -606,6 +606,141 @@ trmm_tma_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ K4, persistent
+// One CTA per SM walks a list of (row block, column panel) tiles fetched from a device counter, heaviest row blocks
+// first, and the TMA ring keeps running across tile boundaries: the pipeline fill of a tile hides under the DMMAs of
+// the previous one (a tile is only 8-32 k-slabs long at m = 500).  Each stage carries a small descriptor (row block,
+// panel, k-slab, last-slab flag) written by the producer next to the data.  `first_tile` / `tile_limit` restrict a launch
+// to part of the list, `grid` to part of the SMs.
+struct TrmmTileMeta { int ib, panel, slab, flags; };      // flags: 1 = last slab of its tile, 2 = no more tiles
+constexpr int TRP_SMEM = TRT_STAGES * TRT_STAGE_BYTES + 1024 + 256 + 4 * BN * 8 + TRT_STAGES * 16;
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, int* tile_counter, int tile_limit) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem0 = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
+    unsigned char* smem_gen = smem_raw + (smem0 - (uint32_t)__cvta_generic_to_shared(smem_raw));
+    const uint32_t bars = smem0 + TRT_STAGES * TRT_STAGE_BYTES;
+    double* colx = reinterpret_cast<double*>(smem_gen + TRT_STAGES * TRT_STAGE_BYTES + 256);      // [4][128]
+    TrmmTileMeta* meta = reinterpret_cast<TrmmTileMeta*>(colx + 4 * BN);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int64_t npanels = (p.n + BN - 1) / BN;
+    const int m16 = (p.m + BK - 1) / BK * BK;
+
+    for (int st = 0; st < TRT_STAGES; ++st) {
+        double* bz = reinterpret_cast<double*>(smem_gen + st * TRT_STAGE_BYTES + TRT_A_BYTES);
+        for (int e = tid; e < BK * BT_LD; e += GEMM_THREADS) bz[e] = 0.0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < TRT_STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (TRT_STAGES + s), GEMM_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    // ---- producer state (thread 0 only)
+    int pr_ib = 0, pr_panel = 0, pr_slab = 0, pr_KT = 0;      // current tile being issued (pr_slab == pr_KT: need a new one)
+    int issued = 0;                                           // stages issued so far (data or the final marker)
+    bool pr_done = false;
+    auto produce_one = [&]() {
+        const int st = issued % TRT_STAGES;
+        if (issued >= TRT_STAGES) mbar_wait(bars + 8 * (TRT_STAGES + st), ((issued / TRT_STAGES) + 1) & 1);
+        const uint32_t full = bars + 8 * st;
+        if (pr_slab == pr_KT) {                               // fetch the next tile
+            const int tile = atomicAdd(tile_counter, 1);
+            if (tile >= tile_limit) {
+                meta[st].flags = 2;
+                mbar_arrive(full);
+                pr_done = true;
+                ++issued;
+                return;
+            }
+            pr_ib = p.nib - 1 - (int)(tile / npanels);        // heaviest row blocks first
+            pr_panel = (int)(tile % npanels);
+            int kmax = (pr_ib + 1) * BM;
+            if (kmax > m16) kmax = m16;
+            pr_KT = kmax / BK;
+            pr_slab = 0;
+        }
+        const uint32_t base = smem0 + st * TRT_STAGE_BYTES;
+        const int k0 = pr_slab * BK;
+        const int64_t j0 = (int64_t)pr_panel * BN;
+        int64_t ncols = p.n - j0;
+        if (ncols > BN) ncols = BN;
+        const uint32_t row_bytes = (uint32_t)ncols * 8;
+        int rows = p.m - k0;
+        rows = rows > BK ? BK : rows;
+        meta[st].ib = pr_ib; meta[st].panel = pr_panel; meta[st].slab = pr_slab;
+        meta[st].flags = (pr_slab + 1 == pr_KT) ? 1 : 0;
+        mbar_arrive_expect_tx(full, TRT_A_BYTES + (uint32_t)rows * row_bytes);
+        tma_load_2d(base, &tmL, k0, pr_ib * BM, full);
+        const double* src = p.H + (int64_t)k0 * p.ldh + j0;
+        for (int r = 0; r < rows; ++r)
+            bulk_load_1d(base + TRT_A_BYTES + r * BT_LD * 8, src + (int64_t)r * p.ldh, row_bytes, full);
+        ++pr_slab;
+        ++issued;
+    };
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    uint32_t offA[2];
+#pragma unroll
+    for (int pq = 0; pq < 2; ++pq) {
+        const int ra = wm * 32 + 2 * g + pq;
+        offA[pq] = ra * 128 + ((((t >> 1) ^ (ra & 7))) << 4) + (t & 1) * 8;
+    }
+    const uint32_t offB = TRT_A_BYTES + (t * BT_LD + wn * 32 + g) * 8;
+
+    for (int gs = 0;; ++gs) {
+        if (tid == 0)
+            while (!pr_done && issued < gs + 1 + TRT_PREFETCH) produce_one();
+        const int st = gs % TRT_STAGES;
+        mbar_wait(bars + 8 * st, (gs / TRT_STAGES) & 1);
+        const TrmmTileMeta mt = meta[st];
+        if (mt.flags & 2) break;
+        const uint32_t base = smem0 + st * TRT_STAGE_BYTES;
+        int k4 = (mt.ib * BM + wm * 32 + 32 - mt.slab * BK) >> 2;      // this warp's rows end at its own diagonal
+        k4 = k4 < 0 ? 0 : (k4 > BK / 4 ? BK / 4 : k4);
+        if (k4 == BK / 4) trmm_tma_slab<BK / 4>(acc, base, offA, offB);
+        else if (k4 == 3) trmm_tma_slab<3>(acc, base, offA, offB);
+        else if (k4 == 2) trmm_tma_slab<2>(acc, base, offA, offB);
+        else if (k4 == 1) trmm_tma_slab<1>(acc, base, offA, offB);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * (TRT_STAGES + st));
+        if (mt.flags & 1) {                                   // tile finished: column sums of squares, fixed order
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double sq = 0.0;
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) { sq = fma(acc[i][j][e], acc[i][j][e], sq); acc[i][j][e] = 0.0; }
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+                    if (g == 0) colx[wm * BN + wn * 32 + j * 8 + 2 * t + e] = sq;
+                }
+            }
+            __syncthreads();
+            if (tid < BN) {
+                const int64_t col = (int64_t)mt.panel * BN + tid;
+                if (col < p.n)
+                    p.part[(size_t)mt.ib * p.npad + col] =
+                        ((colx[tid] + colx[BN + tid]) + colx[2 * BN + tid]) + colx[3 * BN + tid];
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) grad_finalize_kernel(const double* part, int nib, int64_t npad, int64_t n,
                                                             double* g) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -706,6 +841,7 @@ static int ensure_smem_attrs() {
     ACCBPG_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMAJOR_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(trmm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRT_SMEM));
+    ACCBPG_CUDA(cudaFuncSetAttribute(trmm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRP_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(trmm_colnorm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(trmm_colnorm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
     g_attr_done = true;
@@ -866,8 +1002,19 @@ int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r1 == CUDA_SUCCESS) {
-            ProfScope ps(P_TRMM, s);
-            trmm_tma_kernel<<<grid, GEMM_THREADS, TRT_SMEM, s>>>(p, tmL);
+            const int64_t ntiles = (int64_t)pl.nib * npanels;
+            static int persistent = -1;
+            if (persistent < 0) { const char* e = getenv("ACCBPG_TRMM_PERSISTENT"); persistent = (e && e[0] == '0') ? 0 : 1; }
+            if (persistent && ntiles < (1LL << 30)) {
+                int* counter = (int*)(c->d_counter + 8);      // a second ticket word of the context
+                ACCBPG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
+                const int pgrid = (int)(ntiles < c->sm_count ? ntiles : c->sm_count);
+                ProfScope ps(P_TRMM, s);
+                trmm_persistent_kernel<<<pgrid, GEMM_THREADS, TRP_SMEM, s>>>(p, tmL, counter, (int)ntiles);
+            } else {
+                ProfScope ps(P_TRMM, s);
+                trmm_tma_kernel<<<grid, GEMM_THREADS, TRT_SMEM, s>>>(p, tmL);
+            }
             launched = true;
         }
     }

@@ -45,6 +45,30 @@ __global__ void __launch_bounds__(512, 1) probe(double* out, const double* gsrc,
         const double* Xs = Bs + 128 * A_LD;
         const double* ap = As + (wm * (MI * 8) + g) * A_LD + t;
         const double* bp = Bs + (wn * (NI * 8) + g) * A_LD + t;
+        if (FLAGS & 16) {      // register double buffering of the fragments (8-warp configuration of round 1)
+            double a2[2][MI], b2[2][NI];
+            const double xv0 = (FLAGS & 2) ? Xs[t] : 1.0;
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a2[0][i] = ap[i * 8 * A_LD];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) b2[0][j] = bp[j * 8 * A_LD] * xv0;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int cur = kk & 1, nxt = cur ^ 1;
+                if (kk + 1 < 4) {
+                    const double xv = (FLAGS & 2) ? Xs[(kk + 1) * 4 + t] : 1.0;
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) a2[nxt][i] = ap[i * 8 * A_LD + (kk + 1) * 4];
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) b2[nxt][j] = bp[j * 8 * A_LD + (kk + 1) * 4] * xv;
+                }
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma(acc[i][j][0], acc[i][j][1], a2[cur][i], b2[cur][j]);
+            }
+            continue;
+        }
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             if (FLAGS & 1) {
@@ -95,8 +119,9 @@ int main() {
     double* gsrc; cudaMalloc(&gsrc, (size_t)sms * 65536 * 8 + (1 << 20)); cudaMemset(gsrc, 0, (size_t)sms * 65536 * 8 + (1 << 20));
     run<8, 4, 0>(256, sms, d, gsrc);  run<8, 4, 1>(256, sms, d, gsrc);  run<8, 4, 3>(256, sms, d, gsrc);
     run<8, 4, 7>(256, sms, d, gsrc);  run<8, 4, 15>(256, sms, d, gsrc); run<8, 4, 13>(256, sms, d, gsrc);
+    run<8, 4, 17>(256, sms, d, gsrc); run<8, 4, 19>(256, sms, d, gsrc); run<8, 4, 23>(256, sms, d, gsrc); run<8, 4, 31>(256, sms, d, gsrc);
+    run<4, 4, 17>(512, sms, d, gsrc); run<4, 4, 19>(512, sms, d, gsrc);
     run<4, 4, 0>(512, sms, d, gsrc);  run<4, 4, 1>(512, sms, d, gsrc);  run<4, 4, 3>(512, sms, d, gsrc);
     run<4, 4, 7>(512, sms, d, gsrc);  run<4, 4, 15>(512, sms, d, gsrc); run<4, 4, 13>(512, sms, d, gsrc);
-    run<8, 8, 1>(128, sms, d, gsrc);  run<8, 8, 15>(128, sms, d, gsrc);
     return 0;
 }
