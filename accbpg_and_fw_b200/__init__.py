@@ -11,9 +11,9 @@ not been built; there is no CPU fallback.
 from . import _native                                         # noqa: F401  (raises if the library is missing)
 from .objectives import RSmoothFunction, DOptimalObj, PoissonRegression, KLdivRegression
 from .bregman import (LegendreFunction, BurgEntropy, BurgEntropyL1, BurgEntropyL2, BurgEntropySimplex,
-                      ShannonEntropy, ShannonEntropyL1, ShannonEntropySimplex)
+                      ShannonEntropy, ShannonEntropyL1, ShannonEntropySimplex, SquaredL2Norm)
 from .lmo import (lmo_simplex, lmo_matrix_simplex, lmo_l2_ball, lmo_l2_ball_positive_orthant, lmo_linf_ball,
-                  lmo_matrix_box)
+                  lmo_matrix_box, lmo_nuclear_norm_ball)
 from .drivers import BPG, ABPG, ABPG_expo, ABPG_gain, ABDA, solve_theta
 from .drivers_fw import (FW_alg_div_step, FW_alg_descent_step, FW_alg_L0_L1_shortest_step,
                          FW_l0l1_log_and_linear_step, FW_l0l1_log_only)
@@ -26,9 +26,9 @@ from .runtime import Runtime
 __all__ = [
     "RSmoothFunction", "DOptimalObj", "PoissonRegression", "KLdivRegression",
     "LegendreFunction", "BurgEntropy", "BurgEntropyL1", "BurgEntropyL2", "BurgEntropySimplex",
-    "ShannonEntropy", "ShannonEntropyL1", "ShannonEntropySimplex",
+    "ShannonEntropy", "ShannonEntropyL1", "ShannonEntropySimplex", "SquaredL2Norm",
     "lmo_simplex", "lmo_matrix_simplex", "lmo_l2_ball", "lmo_l2_ball_positive_orthant", "lmo_linf_ball",
-    "lmo_matrix_box",
+    "lmo_matrix_box", "lmo_nuclear_norm_ball",
     "BPG", "ABPG", "ABPG_expo", "ABPG_gain", "ABDA", "solve_theta",
     "FW_alg_div_step", "FW_alg_descent_step", "FW_alg_L0_L1_shortest_step", "FW_l0l1_log_and_linear_step",
     "FW_l0l1_log_only", "D_opt_FW", "D_opt_FW_away",

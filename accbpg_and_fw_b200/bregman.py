@@ -290,3 +290,41 @@ class ShannonEntropyL1(ShannonEntropy):
 class ShannonEntropySimplex(ShannonEntropy):
     """Shannon kernel on the unit simplex (normalised multiplicative update).   functions.py:469-490."""
     _normalize = 1
+
+
+# ------------------------------------------------------------------------------------------------
+class SquaredL2Norm(LegendreFunction):
+    """h(x) = (1/2)||x||_2^2.   accbpg/functions.py:738-759 (the kernel the Euclidean Frank-Wolfe examples pass)."""
+
+    def __init__(self, shard=None, device=None):
+        self._setup(shard, device)
+
+    def _enq_value(self, xd, slot):
+        rt = self.rt
+        nat.check(lib.accbpg_vec_dot(rt.ctx, rt.stream, xd.numel(), xd.data_ptr(), xd.data_ptr(), rt.slot(slot)))
+        self._reduce(slot)
+        rt.scal[slot:slot + 1].mul_(0.5)
+
+    def gradient(self, x):
+        return x if is_host(x) else x.clone()
+
+    def _enq_gradient(self, xd, out):
+        out.copy_(xd)
+
+    def _enq_divergence(self, xd, yd, slot):
+        rt = self.rt
+        nat.check(lib.accbpg_vec_sqdist(rt.ctx, rt.stream, xd.numel(), xd.data_ptr(), yd.data_ptr(), rt.slot(slot)))
+        self._reduce(slot)
+        rt.scal[slot:slot + 1].mul_(0.5)
+
+    def _enq_prox(self, gd, L, out):                 # -(1/L) g
+        assert L > 0, "SquaredL2Norm: L should be positive."
+        rt = self.rt
+        nat.check(lib.accbpg_vec_axpby(rt.ctx, rt.stream, gd.numel(), -(1 / L), gd.data_ptr(), 0.0, gd.data_ptr(),
+                                       out.data_ptr()))
+
+    def _enq_div_prox(self, yd, gd, L, out):         # y - (1/L) g
+        assert L > 0, "Vectors y and g not same shape."
+        rt = self.rt
+        nat.check(lib.accbpg_vec_axpby(rt.ctx, rt.stream, gd.numel(), 1.0, yd.data_ptr(), -(1 / L), gd.data_ptr(),
+                                       out.data_ptr()))

@@ -599,6 +599,25 @@ int accbpg_vec_dot_diff(void* ctx, void* stream, int64_t n, const double* g, con
     CTX_STREAM
     return launch_reduce<1>(c, s, n, DotDiffF{g, a, b}, d_out, "vec_dot_diff");
 }
+// out[i][j] = u[i] * v[j]   (p x q, row-major)
+__global__ void __launch_bounds__(256) outer_kernel(const double* __restrict__ u, int64_t p, const double* __restrict__ v,
+                                                    int64_t q, double* __restrict__ out) {
+    const int64_t total = p * q, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t i = e / q, j = e - i * q;
+        out[e] = u[i] * v[j];
+    }
+}
+int accbpg_mat_outer(void* ctx, void* stream, int64_t p, const double* u, int64_t q, const double* v, double* out) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !u || !v || !out) return arg_err("mat_outer: NULL pointer");
+    if (p < 1 || q < 1) return arg_err("mat_outer: shape");
+    int grid = grid_for(c, p * q, 256, 2, 8);
+    outer_kernel<<<grid, 256, 0, s>>>(u, p, v, q, out);
+    ACCBPG_LAUNCHED("outer_kernel");
+    return ACCBPG_OK;
+}
 int accbpg_vec_sqdist(void* ctx, void* stream, int64_t n, const double* a, const double* b, double* d_out) {
     CTX_STREAM
     return launch_reduce<1>(c, s, n, SqDistF{a, b}, d_out, "vec_sqdist");

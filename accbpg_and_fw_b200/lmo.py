@@ -3,8 +3,8 @@
 Each factory returns a callable g -> s, exactly like the reference.  The returned callables
 accept NumPy arrays (NumPy out) or CUDA tensors (CUDA out).  `lmo_simplex` is the one the
 benchmark configurations use; its callable also exposes `.last_index(sync)` and an
-asynchronous `_enq(gd, out, slot)` form for the drivers.  `lmo_nuclear_norm_ball` (full SVD)
-is outside the hot path and is not provided.
+asynchronous `_enq(gd, out, slot)` form for the drivers.  `lmo_nuclear_norm_ball` replaces the
+reference's full SVD by a power iteration for the leading singular pair (two GEMVs per step).
 """
 import numpy as np
 import torch
@@ -152,3 +152,52 @@ def lmo_l2_ball_positive_orthant(radius, center=None, epsilon=0.0, device=None):
         res = torch.clamp(out, min=float(epsilon))
         return like_input(res, host).reshape(g.shape)
     return f
+
+
+def lmo_nuclear_norm_ball(device=None, tol=1e-14, maxit=50000):
+    """Rank-one vertex u1 v1^T of the leading singular pair of g.   functions_lmo.py:4-13 (which takes a full SVD and
+    returns np.outer(U[:, 0], Vh[0]) -- no sign flip, no radius; mirrored as is).
+
+    Here: power iteration v <- A^T(A v)/||.|| on the device (K5/K6 GEMV kernels), stopped when ||v_new - v||^2 <= tol^2
+    (the host reads two scalars per step), then u = A v/||A v||.  u v^T does not depend on the sign of the pair, so it
+    matches the SVD's answer whenever sigma_1 is simple; convergence is geometric with ratio (sigma_2/sigma_1)^2."""
+    def f(G):
+        rt = Runtime.get(device)
+        host = is_host(G)
+        A = rt.to_device(G)
+        assert A.dim() == 2, "lmo_nuclear_norm_ball takes a matrix"
+        p, q = int(A.shape[0]), int(A.shape[1])
+        ws = rt.workspace(("linreg", p, q), lib.accbpg_linreg_workspace_bytes(p, q))
+        # deterministic start with components along every right singular vector
+        v = torch.tensor(1.0 + 0.37 * np.cos(1.7 * np.arange(q)), dtype=torch.float64, device=rt.device)
+        v /= float(np.sqrt(float((v * v).sum().item())))
+        u = rt.empty(p)
+        v2 = rt.empty(q)
+        s0 = rt.S_TMP
+        for it in range(maxit):
+            nat.check(lib.accbpg_linreg_matvec(rt.ctx, rt.stream, A.data_ptr(), p, q, A.stride(0), v.data_ptr(),
+                                               ws.data_ptr(), u.data_ptr()))
+            nat.check(lib.accbpg_linreg_rmatvec(rt.ctx, rt.stream, A.data_ptr(), p, q, A.stride(0), u.data_ptr(),
+                                                ws.data_ptr(), v2.data_ptr()))
+            nat.check(lib.accbpg_vec_dot(rt.ctx, rt.stream, q, v2.data_ptr(), v2.data_ptr(), rt.slot(s0)))
+            nrm = float(np.sqrt(rt.read(s0, 1)[0]))
+            if nrm == 0.0:
+                break
+            vn = rt.empty(q)
+            nat.check(lib.accbpg_vec_divide(rt.ctx, rt.stream, q, v2.data_ptr(), nrm, vn.data_ptr()))
+            nat.check(lib.accbpg_vec_sqdist(rt.ctx, rt.stream, q, vn.data_ptr(), v.data_ptr(), rt.slot(s0)))
+            diff2 = rt.read(s0, 1)[0]
+            v = vn
+            if diff2 <= tol * tol:
+                break
+        nat.check(lib.accbpg_linreg_matvec(rt.ctx, rt.stream, A.data_ptr(), p, q, A.stride(0), v.data_ptr(),
+                                           ws.data_ptr(), u.data_ptr()))
+        nat.check(lib.accbpg_vec_dot(rt.ctx, rt.stream, p, u.data_ptr(), u.data_ptr(), rt.slot(s0)))
+        un = float(np.sqrt(rt.read(s0, 1)[0]))
+        uu = rt.empty(p)
+        nat.check(lib.accbpg_vec_divide(rt.ctx, rt.stream, p, u.data_ptr(), un if un > 0 else 1.0, uu.data_ptr()))
+        out = torch.empty(p, q, dtype=torch.float64, device=rt.device)
+        nat.check(lib.accbpg_mat_outer(rt.ctx, rt.stream, p, uu.data_ptr(), q, v.data_ptr(), out.data_ptr()))
+        return like_input(out, host)
+
+    return lambda g: f(g)

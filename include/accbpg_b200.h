@@ -108,6 +108,9 @@ int accbpg_vec_minmax(void* ctx, void* stream, int64_t n, const double* d_x, dou
 /* d_out[0] = value, d_out[1] = (double) first index attaining it; want_max = 0 argmin, 1 argmax */
 int accbpg_vec_argext(void* ctx, void* stream, int64_t n, const double* d_x, int want_max, double* d_out);
 
+/* out (p x q, row-major) = u v^T: the rank-one vertex of lmo_nuclear_norm_ball (functions_lmo.py:4-13) */
+int accbpg_mat_outer(void* ctx, void* stream, int64_t p, const double* d_u, int64_t q, const double* d_v, double* d_out);
+
 /* ---- Burg entropy kernels  h(x) = -sum log x   (accbpg/functions.py:238-356) */
 #define ACCBPG_BURG_PLAIN   0   /* BurgEntropy.prox_map        functions.py:255-262 */
 #define ACCBPG_BURG_L1      1   /* BurgEntropyL1.prox_map      functions.py:290-298 */

@@ -370,3 +370,30 @@ def test_lmo_simplex_large_ties(acc):
     lmo = acc.lmo_simplex()
     s = lmo(g)
     assert lmo.last_index() == 5 and s[5] == 1.0 and s[4] == 1e-15 and s.sum() == orc.lmo_simplex_eval(g).sum()
+
+
+def test_squared_l2_norm_kernel(acc):
+    """SquaredL2Norm (functions.py:738-759) against its NumPy definition."""
+    rng = np.random.RandomState(3)
+    x, y, g = rng.randn(1001), rng.randn(1001), rng.randn(1001)
+    h = acc.SquaredL2Norm()
+    assert abs(h(x) - 0.5 * np.vdot(x, x)) <= 1e-12 * np.vdot(x, x)
+    assert np.array_equal(h.gradient(x), x)
+    assert abs(h.divergence(x, y) - 0.5 * np.vdot(x - y, x - y)) <= 1e-12 * np.vdot(x - y, x - y)
+    assert np.array_equal(h.prox_map(g, 0.7), -(1 / 0.7) * g)
+    assert np.array_equal(h.div_prox_map(y, g, 0.7), y - (1 / 0.7) * g)
+    assert h.extra_Psi(x) == 0
+
+
+def test_lmo_nuclear_norm_ball(acc):
+    """Leading singular pair by power iteration on the device against np.linalg.svd (functions_lmo.py:4-13)."""
+    rng = np.random.RandomState(11)
+    for p, q in [(60, 40), (33, 120), (7, 7)]:
+        G = rng.randn(p, q) + 3.0 * np.outer(rng.randn(p), rng.randn(q)) / np.sqrt(p * q) * 4
+        U, S, Vh = np.linalg.svd(G, full_matrices=False)
+        ref = np.outer(U[:, 0], Vh[0])
+        out = acc.lmo_nuclear_norm_ball()(G)
+        assert out.shape == (p, q)
+        assert np.max(np.abs(out - ref)) <= 1e-9
+        outd = acc.lmo_nuclear_norm_ball()(torch.tensor(G, device="cuda"))
+        assert outd.is_cuda and np.max(np.abs(outd.cpu().numpy() - ref)) <= 1e-9
