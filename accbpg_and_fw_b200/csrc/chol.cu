@@ -14,6 +14,7 @@
 // so when the last launch retires both L and L^{-1} are complete: the triangular inverse costs no launch of its own
 // and no serial chain beyond the factorisation's.  Tiles are written by exactly one CTA and the block column J that a
 // launch reads is never written in it, so the trailing matrix is updated in place.
+#include <functional>
 #include "dmma.cuh"
 
 namespace accbpg {
@@ -544,7 +545,7 @@ static int ensure_attrs() {
 // Launches are chained with programmatic dependent launch: launch J+1 is resident and past its prologue when
 // launch J retires, so the ~4 us launch gap drops out of the critical path.
 int chol_factor_inv(Ctx* c, cudaStream_t s, int m, int mp, const double* M, double* L, int want_inv, double* Linv,
-                    double* W, double* Y, double* acc, double* d_out) {
+                    double* W, double* Y, double* acc, double* d_out, const std::function<int(int)>* after_step) {
     int rc = ensure_attrs();
     if (rc) return rc;
     if (L) ACCBPG_CUDA(cudaMemsetAsync(L, 0, (size_t)m * m * sizeof(double), s));
@@ -567,6 +568,7 @@ int chol_factor_inv(Ctx* c, cudaStream_t s, int m, int mp, const double* M, doub
     cfg.dynamicSmemBytes = CHOL_SMEM;
     cfg.stream = s;
     cfg.attrs = attr;
+    bool hooked = false;
     for (int J = 0; J < p.nblk; ++J) {
         const int below = p.nblk - 1 - J;
         p.J = J;
@@ -577,10 +579,16 @@ int chol_factor_inv(Ctx* c, cudaStream_t s, int m, int mp, const double* M, doub
         int grid = p.nT + p.nI + p.nF;
         if (grid < 1) grid = 1;
         cfg.gridDim = dim3(grid, 1, 1);
-        cfg.numAttrs = (J > 0) ? 1 : 0;          // the first launch follows memsets / other work: plain ordering
+        cfg.numAttrs = (J > 0 && !hooked) ? 1 : 0;      // plain ordering after memsets / event records / other work
         if (al16) ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, chol_inv_step_kernel<true>, p));
         else      ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, chol_inv_step_kernel<false>, p));
         ACCBPG_LAUNCHED("chol_inv_step_kernel");
+        hooked = false;
+        if (after_step) {                        // rows of block column J of L^{-1} are final from here on
+            int hr = (*after_step)(J);
+            if (hr < 0) return -hr;
+            hooked = hr > 0;                     // the hook put something on the stream: the next launch is not programmatic
+        }
     }
     return ACCBPG_OK;
 }

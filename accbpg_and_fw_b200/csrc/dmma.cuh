@@ -3,6 +3,7 @@
 // mma.sync.m8n8k4 tiles, k-slabs of 16 staged through a 4-deep cp.async pipeline into padded (bank-conflict-free)
 // shared memory.
 #pragma once
+#include <functional>
 #include "common.cuh"
 
 namespace accbpg {
@@ -133,6 +134,6 @@ __device__ __forceinline__ void mma_nn_slab(double (&acc)[MI][NI][2], const doub
 
 // defined in chol.cu (host side, stream ordered)
 int chol_factor_inv(Ctx* c, cudaStream_t s, int m, int mp, const double* M, double* L, int want_inv, double* Linv,
-                    double* W, double* Y, double* acc, double* d_out);
+                    double* W, double* Y, double* acc, double* d_out, const std::function<int(int)>* after_step = nullptr);
 
 }  // namespace accbpg

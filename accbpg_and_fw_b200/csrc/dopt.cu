@@ -616,7 +616,8 @@ struct TrmmTileMeta { int ib, panel, slab, flags; };      // flags: 1 = last sla
 constexpr int TRP_SMEM = TRT_STAGES * TRT_STAGE_BYTES + 1024 + 256 + 4 * BN * 8 + TRT_STAGES * 16;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, int* tile_counter, int tile_limit) {
+trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, int* tile_counter, int first_tile,
+                       int tile_limit) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem0 = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem_gen = smem_raw + (smem0 - (uint32_t)__cvta_generic_to_shared(smem_raw));
@@ -652,7 +653,7 @@ trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, in
         if (issued >= TRT_STAGES) mbar_wait(bars + 8 * (TRT_STAGES + st), ((issued / TRT_STAGES) + 1) & 1);
         const uint32_t full = bars + 8 * st;
         if (pr_slab == pr_KT) {                               // fetch the next tile
-            const int tile = atomicAdd(tile_counter, 1);
+            const int tile = first_tile + atomicAdd(tile_counter, 1);
             if (tile >= tile_limit) {
                 meta[st].flags = 2;
                 mbar_arrive(full);
@@ -1010,7 +1011,7 @@ int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n,
                 ACCBPG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
                 const int pgrid = (int)(ntiles < c->sm_count ? ntiles : c->sm_count);
                 ProfScope ps(P_TRMM, s);
-                trmm_persistent_kernel<<<pgrid, GEMM_THREADS, TRP_SMEM, s>>>(p, tmL, counter, (int)ntiles);
+                trmm_persistent_kernel<<<pgrid, GEMM_THREADS, TRP_SMEM, s>>>(p, tmL, counter, 0, (int)ntiles);
             } else {
                 ProfScope ps(P_TRMM, s);
                 trmm_tma_kernel<<<grid, GEMM_THREADS, TRT_SMEM, s>>>(p, tmL);
@@ -1033,6 +1034,88 @@ int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n,
     return ACCBPG_OK;
 }
 
+// Factor M (with the inverse) and form the gradient, with the triangular GEMM started before the Cholesky chain has
+// finished: the rows of row block ib of L^{-1} are final once block column 2ib+1 has retired, and the chain keeps at
+// most ~36 SMs busy, so the persistent triangular GEMM is launched per row block on a second stream as its rows
+// become final (on sm_count - 52 SMs), lowest row blocks first; the remaining row blocks follow on the main stream
+// after the chain, heaviest first, on all SMs.  Same results as accbpg_dopt_factor + accbpg_dopt_grad.
+static int overlap_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ACCBPG_OVERLAP"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
+static int dopt_factor_grad(Ctx* c, cudaStream_t s, const double* H, int m, int64_t n, int64_t ldh, const double* M,
+                            void* ws, double* d_f_out, double* g) {
+    DoptPlan pl = make_plan(m, n, c->sm_count);
+    const int64_t npanels = (n + BN - 1) / BN;
+    const int64_t ntiles = (int64_t)pl.nib * npanels;
+    const bool al = aligned16(H) && (ldh % 2 == 0) && (n % 2 == 0);
+    const int n_early = pl.nib / 2 < 4 ? pl.nib / 2 : 4;      // row blocks 0 .. n_early-1 start under the chain
+    if (!overlap_enabled() || !al || !syrk_tma_enabled() || !encode_tiled_fn() || n_early < 1 || ntiles >= (1LL << 30)) {
+        int rc = accbpg_dopt_factor(c, s, m, M, nullptr, 1, ws, d_f_out);
+        if (rc) return rc;
+        return accbpg_dopt_grad(c, s, H, m, n, ldh, ws, g);
+    }
+    int rc = ensure_smem_attrs();
+    if (rc) return rc;
+    double* Linv = (double*)((char*)ws + pl.off_Linv);
+    double* part = (double*)((char*)ws + pl.off_part);
+    CUtensorMap tmL;
+    cuuint64_t dimL[2] = {(cuuint64_t)pl.mp, (cuuint64_t)pl.mp};
+    cuuint64_t strL[1] = {(cuuint64_t)pl.mp * 8};
+    cuuint32_t boxL[2] = {BK, BM};
+    cuuint32_t one[2] = {1, 1};
+    if (encode_tiled_fn()(&tmL, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)Linv, dimL, strL, boxL, one,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        rc = accbpg_dopt_factor(c, s, m, M, nullptr, 1, ws, d_f_out);
+        if (rc) return rc;
+        return accbpg_dopt_grad(c, s, H, m, n, ldh, ws, g);
+    }
+    TrmmParams p;
+    p.Linv = Linv; p.H = H; p.part = part; p.m = m; p.mp = pl.mp; p.nib = pl.nib; p.n = n; p.ldh = ldh; p.npad = pl.npad;
+    int* counters = (int*)(c->d_counter + 8);                 // words 8 .. 13 of the context's ticket block
+    ACCBPG_CUDA(cudaMemsetAsync(counters, 0, 6 * sizeof(int), s));
+    static int reserve = -1;                                  // SMs left to the Cholesky chains while they run
+    if (reserve < 0) { const char* e = getenv("ACCBPG_CHAIN_SMS"); reserve = e ? atoi(e) : 52; }
+    int early_grid = c->sm_count - reserve;
+    if (early_grid < 1) early_grid = 1;
+    if ((int64_t)early_grid > npanels) early_grid = (int)npanels;
+    // side2 must not start before the main stream has reached this point (Linv memset, counters, earlier readers of part)
+    ACCBPG_CUDA(cudaEventRecord(c->ev_fork, s));
+    ACCBPG_CUDA(cudaStreamWaitEvent(c->side2, c->ev_fork, 0));
+    ProfScope ps_all(P_TRINV, s);                             // chain + triangular GEMM as one interval
+    std::function<int(int)> hook = [&](int J) -> int {
+        if ((J & 1) == 0) return 0;
+        const int ib = J >> 1;                                // rows of row block ib are final
+        if (ib >= n_early) return 0;
+        if (cudaEventRecord(c->ev_rows[ib], s) != cudaSuccess) return -ACCBPG_E_CUDA;
+        if (cudaStreamWaitEvent(c->side2, c->ev_rows[ib], 0) != cudaSuccess) return -ACCBPG_E_CUDA;
+        // LPT numbering: row block ib owns tiles [(nib-1-ib) npanels, (nib-ib) npanels)
+        const int first = (int)((pl.nib - 1 - ib) * npanels), limit = (int)((pl.nib - ib) * npanels);
+        trmm_persistent_kernel<<<early_grid, GEMM_THREADS, TRP_SMEM, c->side2>>>(p, tmL, counters + 1 + ib, first, limit);
+        ++g_launches;
+        if (cudaGetLastError() != cudaSuccess) return -ACCBPG_E_CUDA;
+        return 1;
+    };
+    rc = chol_factor_inv(c, s, m, pl.mp, M, nullptr, 1, Linv, (double*)((char*)ws + pl.off_W),
+                         (double*)((char*)ws + pl.off_Y), c->d_slots + 248, d_f_out, &hook);
+    if (rc) return rc;
+    ACCBPG_CUDA(cudaEventRecord(c->ev_early_done, c->side2));
+    {   // the late row blocks, heaviest first, on every SM that is free
+        const int limit = (int)((pl.nib - n_early) * npanels);
+        const int pgrid = (int)((int64_t)c->sm_count < (int64_t)limit ? c->sm_count : limit);
+        trmm_persistent_kernel<<<pgrid, GEMM_THREADS, TRP_SMEM, s>>>(p, tmL, counters, 0, limit);
+        ACCBPG_LAUNCHED("trmm_persistent_kernel");
+    }
+    ACCBPG_CUDA(cudaStreamWaitEvent(s, c->ev_early_done, 0));
+    int fg = grid_for(c, n, 256, 2, 8);
+    grad_finalize_kernel<<<fg, 256, 0, s>>>(part, pl.nib, pl.npad, n, g);
+    ACCBPG_LAUNCHED("grad_finalize_kernel");
+    return ACCBPG_OK;
+}
+
 int accbpg_dopt_func_grad(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh, const double* x,
                           int flag, void* ws, double* d_f_out, double* g) {
     Ctx* c = (Ctx*)ctx;
@@ -1043,10 +1126,8 @@ int accbpg_dopt_func_grad(void* ctx, void* stream, const double* H, int m, int64
     double* M = (double*)((char*)ws + pl.off_M);
     int rc = accbpg_dopt_gram(ctx, stream, H, m, n, ldh, x, ws, M);
     if (rc) return rc;
-    rc = accbpg_dopt_factor(ctx, stream, m, M, NULL, flag >= 1, ws, d_f_out ? d_f_out : (c->d_slots + 249));
-    if (rc) return rc;
-    if (flag >= 1) rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, ws, g);
-    return rc;
+    if (flag >= 1) return dopt_factor_grad(c, (cudaStream_t)stream, H, m, n, ldh, M, ws, d_f_out ? d_f_out : (c->d_slots + 249), g);
+    return accbpg_dopt_factor(ctx, stream, m, M, NULL, 0, ws, d_f_out ? d_f_out : (c->d_slots + 249));
 }
 
 // f(xf) and (f(yg), grad f(yg)) in one call: the two Gram matrices are formed back to back on the main stream, then
@@ -1071,9 +1152,7 @@ int accbpg_dopt_pair(void* ctx, void* stream, const double* H, int m, int64_t n,
     ACCBPG_CUDA(cudaEventRecord(c->ev_join, c->side));
     rc = accbpg_dopt_gram(ctx, stream, H, m, n, ldh, yg, ws, M1);
     if (rc) return rc;
-    rc = accbpg_dopt_factor(ctx, stream, m, M1, NULL, 1, ws, d_fy_out ? d_fy_out : (c->d_slots + 249));
-    if (rc) return rc;
-    rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, ws, g);
+    rc = dopt_factor_grad(c, s, H, m, n, ldh, M1, ws, d_fy_out ? d_fy_out : (c->d_slots + 249), g);
     if (rc) return rc;
     ACCBPG_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
     return ACCBPG_OK;
@@ -1099,12 +1178,9 @@ int accbpg_dopt_pair_from_gram(void* ctx, void* stream, const double* H, int m, 
         if (rc) return rc;
         ACCBPG_CUDA(cudaEventRecord(c->ev_join, c->side));
     }
-    rc = accbpg_dopt_factor(ctx, stream, m, My, NULL, flag_y >= 1, ws, d_fy_out ? d_fy_out : (c->d_slots + 249));
+    if (flag_y >= 1) rc = dopt_factor_grad(c, s, H, m, n, ldh, My, ws, d_fy_out ? d_fy_out : (c->d_slots + 249), g);
+    else rc = accbpg_dopt_factor(ctx, stream, m, My, NULL, 0, ws, d_fy_out ? d_fy_out : (c->d_slots + 249));
     if (rc) return rc;
-    if (flag_y >= 1) {
-        rc = accbpg_dopt_grad(ctx, stream, H, m, n, ldh, ws, g);
-        if (rc) return rc;
-    }
     if (Mx) ACCBPG_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
     return ACCBPG_OK;
 }

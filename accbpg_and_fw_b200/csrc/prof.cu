@@ -11,7 +11,7 @@ static std::vector<EvPair> g_prof_live[P_COUNT];
 static std::vector<EvPair> g_prof_pool;
 
 static const char* kProfNames[P_COUNT] = {
-    "syrk_dmma_kernel", "syrk_reduce_kernel", "chol_inv_step_kernel(all block columns)", "unused",
+    "syrk_dmma_kernel", "syrk_reduce_kernel", "chol_inv_step_kernel(all block columns)", "factor+gradient interval (chain with overlapped triangular GEMM)",
     "trmm_colnorm_kernel", "grad_finalize_kernel", "burg_simplex_kernel", "matvec_kernel", "rmatvec_kernel",
     "fw_pass_kernel", "fw_iteration(5 kernels)"};
 

@@ -498,6 +498,9 @@ int accbpg_ctx_create(void** out) {
     ACCBPG_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     ACCBPG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     ACCBPG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    ACCBPG_CUDA(cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) ACCBPG_CUDA(cudaEventCreateWithFlags(&c->ev_rows[i], cudaEventDisableTiming));
+    ACCBPG_CUDA(cudaEventCreateWithFlags(&c->ev_early_done, cudaEventDisableTiming));
     int per_sm = 0;
     ACCBPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, burg_simplex_kernel, kBurgThreads, 0));
     if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "burg_simplex_kernel cannot be made resident"); return ACCBPG_E_CUDA; }
@@ -516,6 +519,8 @@ int accbpg_ctx_destroy(void* ctx) {
     cudaFree(c->d_ipartials); cudaFree(c->d_counter);
     cudaFreeHost(c->h_slots); cudaFreeHost(c->h_status);
     cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->side2); cudaEventDestroy(c->ev_early_done);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(c->ev_rows[i]);
     delete c;
     return ACCBPG_OK;
 }
