@@ -64,6 +64,7 @@ class Runtime:
         self._hstat = ctypes.c_uint32(0)
         self._ws = {}
         self.dist = None            # set by dist.ColumnShard when the problem is column-sharded
+        self._pin = {}              # numel -> (ring of pinned staging buffers, next index) for host-vector uploads
 
     # ---- streams / pointers ------------------------------------------------------------
     @property
@@ -128,6 +129,22 @@ class Runtime:
                 return a
             return a.to(device=self.device, dtype=F64).contiguous()
         arr = np.ascontiguousarray(a, dtype=np.float64)
+        if arr.ndim == 1 and 0 < arr.size <= (1 << 24):
+            # host vectors go through a small ring of pinned staging buffers: one CPU memcpy, then an asynchronous DMA
+            # on the current stream (a pageable cudaMemcpy would block and stage through the driver's own buffer).
+            # Every public operator call ends with a synchronising read, so a ring of 8 cannot be overrun.
+            ring = self._pin.get(arr.size)
+            if ring is None:
+                ring = [[torch.empty(arr.size, dtype=F64).pin_memory() for _ in range(8)], 0]
+                self._pin[arr.size] = ring
+            buf = ring[0][ring[1]]
+            ring[1] = (ring[1] + 1) % 8
+            buf.numpy()[:] = arr
+            out = torch.empty(arr.size, dtype=F64, device=self.device)
+            out.copy_(buf, non_blocking=True)
+            return out
+        if not arr.flags.writeable:
+            arr = arr.copy()
         return torch.from_numpy(arr).to(self.device)
 
 
