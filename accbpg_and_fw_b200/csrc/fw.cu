@@ -129,6 +129,7 @@ struct FwParams {
     int away; double eps;
     int k;                    // iteration whose decision the tail of this kernel takes
     int nblk;                 // column blocks of the pass
+    int width;                // columns per block (even, <= 128): chosen so that the blocks fill whole waves of SMs
     int nr1;                  // leading CTAs that update Hinv instead (they start first, so they read the step's
                               // coefficients long before the tail of the same launch replaces them)
     int decide;               // tail of the selecting kernels: 0 nothing, 1 merge + take the decision of iteration k,
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(256) fw_hv_kernel(const double* __restrict__ H
 // pass read last -- still resident in the 126 MB L2 -- is read first.
 constexpr int FWP_THREADS = 256;
 constexpr int FWP_COLS = 128;
-constexpr int FWP_UNROLL = 8;        // rows in flight per thread (8 x 16 B)
+constexpr int FWP_UNROLL = 16;       // rows in flight per thread (16 x 16 B)
 
 template <bool VEC2>
 __global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(FwParams p) {
@@ -339,9 +340,10 @@ __global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(FwParams p) {
     const int rg = threadIdx.x >> 6, ct = threadIdx.x & 63;
     const int rows_per = (m + 3) / 4;
     const int r0 = rg * rows_per, r1 = min(m, r0 + rows_per);
-    const int64_t j = ((int64_t)cb * 64 + ct) * 2;
+    const int64_t j = (int64_t)cb * p.width + ct * 2;
+    const bool owns = (ct * 2 < p.width) && (j < p.n);
     double s0 = 0.0, s1 = 0.0;
-    if (j < p.n) {
+    if (owns) {
         const double* col = p.V + j;
         int r = r0;
         if (VEC2 && j + 1 < p.n) {
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(FwParams p) {
     __syncthreads();
     FwCand cd;
     fw_cand_init(cd);
-    if (rg == 0 && j < p.n) {
+    if (rg == 0 && owns) {
         const double thr = p.away ? 1.0e-8 : 0.0;
         const int64_t idx = (int64_t)ld_cg(&p.ctrl[C_IDX]);
         const double tsign = ld_cg(&p.ctrl[C_TSIGN]);
@@ -452,7 +454,7 @@ extern "C" {
 size_t accbpg_fw_workspace_bytes(int m, int64_t n_local) {
     // dopt workspace (gram / factor / Linv / gradient partials) + v and u vectors
     size_t base = accbpg_dopt_workspace_bytes(m, n_local);
-    const size_t nparts = (size_t)((n_local + 127) / 128) + 2048;        // selection candidates, one per selecting CTA
+    const size_t nparts = (size_t)((n_local + 127) / 128) + 4096;        // selection candidates, one per selecting CTA
     return base + 2 * (((size_t)m + 31) / 32 * 32 * 8) + nparts * 64 + 256;
 }
 
@@ -496,9 +498,17 @@ static int fw_prepare(Ctx* c, const double* V, int m, int64_t n, int64_t ldv, in
     double* v = (double*)((char*)ws + base);
     double* u = v + ((size_t)m + 31) / 32 * 32;
     FwCand* parts = (FwCand*)(u + ((size_t)m + 31) / 32 * 32);
-    const int64_t nblk64 = (n + FWP_COLS - 1) / FWP_COLS;
+    // block width: the smallest number of whole waves of (3 CTAs per SM) that covers n with <= 128 columns per CTA
+    int64_t per_wave = (int64_t)c->sm_count * 3;
+    int64_t waves = (n + per_wave * FWP_COLS - 1) / (per_wave * FWP_COLS);
+    int64_t width = (n + waves * per_wave - 1) / (waves * per_wave);
+    width = (width + 1) / 2 * 2;
+    if (width < 16) width = 16;
+    if (width > FWP_COLS) width = FWP_COLS;
+    const int64_t nblk64 = (n + width - 1) / width;
     if (nblk64 > 2000000000LL) return arg_err("fw: n too large");
     L->nblk = (int)nblk64;
+    L->p.width = (int)width;
     L->sel_grid = grid_for(c, n, FW_THREADS, 4, 2);
     L->hv_grid = (m + 7) / 8;
     L->r1_ctas = c->sm_count / 4 < 1 ? 1 : c->sm_count / 4;
