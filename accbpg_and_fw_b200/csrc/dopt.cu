@@ -21,9 +21,10 @@ namespace accbpg {
 
 // ------------------------------------------------------------------------------------------ K1: SYRK
 // Lower 128x128 tiles only.  Off-diagonal tiles use all 16 warps; in a diagonal tile the six warp tiles strictly above
-// the diagonal are skipped and the ten that remain are numbered so that the four SM sub-partitions carry 3/3/2/2 of
-// them: a diagonal tile costs 3/4 of a full one (and stages its 128 rows of H once, as both operands).  The column
-// range is split differently for the two kinds of tile so that every CTA carries about the same work.
+// the diagonal are skipped, the four on the diagonal also skip their own strictly-upper 16x16 quarter (TMA kernel), and
+// the ten that remain are numbered so that the four SM sub-partitions carry equal-ish DMMA counts (table below): a
+// diagonal tile costs 5/8 of a full one (and stages its 128 rows of H once, as both operands).  The column range is
+// split differently for the two kinds of tile so that every CTA carries about the same work.
 struct SyrkParams {
     const double* H;
     const double* x;
@@ -36,8 +37,12 @@ struct SyrkParams {
     uint32_t* status;
 };
 
-__constant__ signed char kDiagWm[16] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, -1, -1, -1, -1, -1, -1};
-__constant__ signed char kDiagWn[16] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, -1, -1, -1, -1, -1, -1};
+// Warp -> warp tile of a diagonal CTA tile.  Warp id mod 4 is the SM sub-partition.  The six tiles below the diagonal
+// cost 16 DMMAs per k-step, the four on it 12 (their strictly-upper 16x16 quarter is skipped), so sub-partitions 0 and 1
+// get one full + two diagonal tiles (40) and sub-partitions 2 and 3 two full ones (32): a diagonal CTA tile costs
+// 40/64 of a full one.
+__constant__ signed char kDiagWm[16] = {1, 2, 2, 3, 0, 2, 3, 3, 1, 3, -1, -1, -1, -1, -1, -1};
+__constant__ signed char kDiagWn[16] = {0, 0, 1, 1, 0, 2, 0, 2, 1, 3, -1, -1, -1, -1, -1, -1};
 
 template <bool ALIGNED16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_dmma_kernel(SyrkParams p) {
@@ -265,6 +270,7 @@ syrk_tma_kernel(SyrkParams p, const __grid_constant__ CUtensorMap tmH, const __g
     if (diag) { wm = kDiagWm[warp]; wn = kDiagWn[warp]; }
     const bool active = wm >= 0;
     const int n_active = diag ? 10 : 16;
+    const bool diag_warp = diag && active && (wm == wn);
 
     const int64_t k_begin = (int64_t)split * kchunk;             // multiple of BK: chunk edges fall on slab edges
     int64_t k_end = k_begin + kchunk;
@@ -325,19 +331,38 @@ syrk_tma_kernel(SyrkParams p, const __grid_constant__ CUtensorMap tmH, const __g
         if (active) {
             mbar_wait(bars + 8 * st, (s / TMA_STAGES) & 1);
             const uint32_t xs = base + 2 * BM * BK * 8 + t * 8;
+            if (diag_warp) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 4; ++kk) {
-                const double xv = lds_f64(xs + kk * 32);
-                neg |= (xv < 0.0);
-                double a[MI], bq[NI];
+                for (int kk = 0; kk < BK / 4; ++kk) {
+                    const double xv = lds_f64(xs + kk * 32);
+                    neg |= (xv < 0.0);
+                    double a[MI], bq[NI];
 #pragma unroll
-                for (int i = 0; i < MI; ++i) a[i] = lds_f64(base + ((offA[i & 1] ^ (kk << 5)) + (i >> 1) * 16 * 128));
+                    for (int i = 0; i < MI; ++i) a[i] = lds_f64(base + ((offA[i & 1] ^ (kk << 5)) + (i >> 1) * 16 * 128));
 #pragma unroll
-                for (int j = 0; j < NI; ++j) bq[j] = lds_f64(base + ((offB[j & 1] ^ (kk << 5)) + (j >> 1) * 16 * 128)) * xv;
+                    for (int j = 0; j < NI; ++j) bq[j] = lds_f64(base + ((offB[j & 1] ^ (kk << 5)) + (j >> 1) * 16 * 128)) * xv;
 #pragma unroll
-                for (int i = 0; i < MI; ++i)
+                    for (int i = 0; i < MI; ++i)
 #pragma unroll
-                    for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bq[j]);
+                        for (int j = 0; j < NI; ++j)
+                            if (!(i < 2 && j >= 2))      // rows 0..15 x columns 16..31 of the tile lie above the diagonal
+                                dmma884(acc[i][j][0], acc[i][j][1], a[i], bq[j]);
+                }
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < BK / 4; ++kk) {
+                    const double xv = lds_f64(xs + kk * 32);
+                    neg |= (xv < 0.0);
+                    double a[MI], bq[NI];
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) a[i] = lds_f64(base + ((offA[i & 1] ^ (kk << 5)) + (i >> 1) * 16 * 128));
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) bq[j] = lds_f64(base + ((offB[j & 1] ^ (kk << 5)) + (j >> 1) * 16 * 128)) * xv;
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bq[j]);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + 8 * (TMA_STAGES + st));
@@ -760,9 +785,17 @@ struct DoptPlan {
     size_t off_P, off_Linv, off_Y, off_part, off_M, off_L, off_W, off_M2, off_W2, total;
 };
 
+// Relative cost of a diagonal tile: 40/64 by DMMA count; its sub-partitions host only 2-3 active warps instead of 4,
+// which hides less latency, so the effective figure is a little higher (calibrated on B200; ACCBPG_DIAG_COST overrides).
+static double syrk_diag_cost() {
+    static double v = -1.0;
+    if (v < 0.0) { const char* e = getenv("ACCBPG_DIAG_COST"); v = e ? atof(e) : 0.625; }
+    return v;
+}
+
 // Makespan (in k-slab units) of the SYRK grid under in-order dispatch onto `sms` single-CTA SMs.
 static double syrk_makespan(int n_off, int nt, int64_t ktiles, int s_off, int s_diag, int sms, int* diag_first) {
-    const double ovh = 2.0, diag_cost = 0.75;
+    const double ovh = 2.0, diag_cost = syrk_diag_cost();
     const double d_off = n_off ? (double)((ktiles + s_off - 1) / s_off) + ovh : 0.0;
     const double d_diag = (double)((ktiles + s_diag - 1) / s_diag) * diag_cost + ovh;
     const int c_off = n_off * s_off, c_diag = nt * s_diag;
@@ -802,7 +835,7 @@ static DoptPlan make_plan(int m, int64_t n, int sm_count) {
     pl.s_off = pl.s_diag = 1; pl.diag_first = 0;
     for (int so = 1; so <= max_splits; ++so) {
         for (int d = -2; d <= 2; ++d) {
-            int sd = (int)(0.75 * so + 0.5) + d;
+            int sd = (int)(syrk_diag_cost() * so + 0.5) + d;
             if (sd < 1 || sd > max_splits) continue;
             if ((int64_t)(pl.n_off * so + pl.nt * sd) > 6LL * sm_count) continue;
             int df = 0;
