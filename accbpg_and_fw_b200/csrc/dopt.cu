@@ -639,8 +639,9 @@ trmm_tma_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL) {
 // to part of the list, `grid` to part of the SMs.
 struct TrmmTileMeta { int ib, panel, slab, flags; };      // flags: 1 = last slab of its tile, 2 = no more tiles
 constexpr int TRP_SMEM = TRT_STAGES * TRT_STAGE_BYTES + 1024 + 256 + 4 * BN * 8 + TRT_STAGES * 16;
+constexpr int TRP_THREADS = GEMM_THREADS + 32;          // 16 consuming warps + one producer warp
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(TRP_THREADS, 1)
 trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, int* tile_counter, int first_tile,
                        int tile_limit) {
     extern __shared__ unsigned char smem_raw[];
@@ -657,7 +658,7 @@ trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, in
 
     for (int st = 0; st < TRT_STAGES; ++st) {
         double* bz = reinterpret_cast<double*>(smem_gen + st * TRT_STAGE_BYTES + TRT_A_BYTES);
-        for (int e = tid; e < BK * BT_LD; e += GEMM_THREADS) bz[e] = 0.0;
+        for (int e = tid; e < BK * BT_LD; e += TRP_THREADS) bz[e] = 0.0;
     }
     if (tid == 0) {
         for (int s = 0; s < TRT_STAGES; ++s) {
@@ -712,6 +713,12 @@ trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, in
         ++issued;
     };
 
+    if (warp == GEMM_THREADS / 32) {                          // the producer warp: one lane feeds the ring and leaves
+        if (lane == 0)
+            while (!pr_done) produce_one();
+        return;
+    }
+
     double acc[MI][NI][2];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
@@ -726,8 +733,6 @@ trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, in
     const uint32_t offB = TRT_A_BYTES + (t * BT_LD + wn * 32 + g) * 8;
 
     for (int gs = 0;; ++gs) {
-        if (tid == 0)
-            while (!pr_done && issued < gs + 1 + TRT_PREFETCH) produce_one();
         const int st = gs % TRT_STAGES;
         mbar_wait(bars + 8 * st, (gs / TRT_STAGES) & 1);
         const TrmmTileMeta mt = meta[st];
@@ -755,14 +760,14 @@ trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, in
                     if (g == 0) colx[wm * BN + wn * 32 + j * 8 + 2 * t + e] = sq;
                 }
             }
-            __syncthreads();
+            asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS) : "memory");       // the 16 consuming warps only
             if (tid < BN) {
                 const int64_t col = (int64_t)mt.panel * BN + tid;
                 if (col < p.n)
                     p.part[(size_t)mt.ib * p.npad + col] =
                         ((colx[tid] + colx[BN + tid]) + colx[2 * BN + tid]) + colx[3 * BN + tid];
             }
-            __syncthreads();
+            asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS) : "memory");
         }
     }
 }
@@ -1044,7 +1049,7 @@ int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n,
                 ACCBPG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
                 const int pgrid = (int)(ntiles < c->sm_count ? ntiles : c->sm_count);
                 ProfScope ps(P_TRMM, s);
-                trmm_persistent_kernel<<<pgrid, GEMM_THREADS, TRP_SMEM, s>>>(p, tmL, counter, 0, (int)ntiles);
+                trmm_persistent_kernel<<<pgrid, TRP_THREADS, TRP_SMEM, s>>>(p, tmL, counter, 0, (int)ntiles);
             } else {
                 ProfScope ps(P_TRMM, s);
                 trmm_tma_kernel<<<grid, GEMM_THREADS, TRT_SMEM, s>>>(p, tmL);
@@ -1127,7 +1132,7 @@ static int dopt_factor_grad(Ctx* c, cudaStream_t s, const double* H, int m, int6
         if (cudaStreamWaitEvent(c->side2, c->ev_rows[ib], 0) != cudaSuccess) return -ACCBPG_E_CUDA;
         // LPT numbering: row block ib owns tiles [(nib-1-ib) npanels, (nib-ib) npanels)
         const int first = (int)((pl.nib - 1 - ib) * npanels), limit = (int)((pl.nib - ib) * npanels);
-        trmm_persistent_kernel<<<early_grid, GEMM_THREADS, TRP_SMEM, c->side2>>>(p, tmL, counters + 1 + ib, first, limit);
+        trmm_persistent_kernel<<<early_grid, TRP_THREADS, TRP_SMEM, c->side2>>>(p, tmL, counters + 1 + ib, first, limit);
         ++g_launches;
         if (cudaGetLastError() != cudaSuccess) return -ACCBPG_E_CUDA;
         return 1;
@@ -1139,7 +1144,7 @@ static int dopt_factor_grad(Ctx* c, cudaStream_t s, const double* H, int m, int6
     {   // the late row blocks, heaviest first, on every SM that is free
         const int limit = (int)((pl.nib - n_early) * npanels);
         const int pgrid = (int)((int64_t)c->sm_count < (int64_t)limit ? c->sm_count : limit);
-        trmm_persistent_kernel<<<pgrid, GEMM_THREADS, TRP_SMEM, s>>>(p, tmL, counters, 0, limit);
+        trmm_persistent_kernel<<<pgrid, TRP_THREADS, TRP_SMEM, s>>>(p, tmL, counters, 0, limit);
         ACCBPG_LAUNCHED("trmm_persistent_kernel");
     }
     ACCBPG_CUDA(cudaStreamWaitEvent(s, c->ev_early_done, 0));
