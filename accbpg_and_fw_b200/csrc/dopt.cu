@@ -1077,10 +1077,9 @@ int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n,
 // most ~36 SMs busy, so the persistent triangular GEMM is launched per row block on a second stream as its rows
 // become final (on sm_count - 52 SMs), lowest row blocks first; the remaining row blocks follow on the main stream
 // after the chain, heaviest first, on all SMs.  Same results as accbpg_dopt_factor + accbpg_dopt_grad.
-static int overlap_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("ACCBPG_OVERLAP"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v;
+static int overlap_enabled() {          // read on every call: tools/bench_configs.py times the kernels one by one with it off
+    const char* e = getenv("ACCBPG_OVERLAP");
+    return (e && e[0] == '0') ? 0 : 1;
 }
 
 static int dopt_factor_grad(Ctx* c, cudaStream_t s, const double* H, int m, int64_t n, int64_t ldh, const double* M,
