@@ -217,7 +217,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 // bounded wait: a protocol error traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
-    for (int spin = 0; spin < (1 << 24); ++spin) {
+    for (int spin = 0; spin < (1 << 21); ++spin) {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;

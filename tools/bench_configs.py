@@ -24,7 +24,7 @@ from accbpg_and_fw_b200 import _native as nat         # noqa: E402
 
 lib = nat.lib
 dev = torch.device("cuda")
-which = set(sys.argv[1:]) or {"c1", "c3", "c4", "c5"}
+which = set(sys.argv[1:]) or {"c1", "c2", "c3", "c4", "c5"}
 out = {}
 
 
@@ -72,6 +72,25 @@ if "c1" in which:
     out["c1_dopt_80x200_bpg_ls"] = {"iterations": len(F), "it_per_s": (len(T) - 1) / (T[-1] - T[0]), "wall_s": wall,
                                     "F_last": float(F[-1])}
     print("c1", out["c1_dopt_80x200_bpg_ls"], flush=True)
+
+if "c2" in which:
+    f, h, L, x0 = acc.D_opt_design(500, 50000, randseed=1)
+    x0d = torch.tensor(x0, device=dev)
+    res = {}
+    for name, fn in [("ABPG_gain", lambda k: acc.ABPG_gain(f, h, L, x0d, gamma=2, maxitrs=k, verbose=False)),
+                     ("ABPG_expo", lambda k: acc.ABPG_expo(f, h, L, x0d, gamma0=3, maxitrs=k, verbose=False)),
+                     ("ABPG", lambda k: acc.ABPG(f, h, L, x0d, gamma=2, maxitrs=k, verbose=False)),
+                     ("ABDA", lambda k: acc.ABDA(f, h, L, x0d, gamma=2, maxitrs=k, verbose=False)),
+                     ("BPG_LS", lambda k: acc.BPG(f, h, L, x0d, maxitrs=k, verbose=False)),
+                     ("FW_alg_div_step", lambda k: acc.FW_alg_div_step(f, h, L, x0d, k, 2.0, acc.lmo_simplex(), verbose=False))]:
+        fn(5)
+        (out_, ms) = timed(lambda: fn(60))
+        res[name] = {"iterations": len(out_[1]), "ms_per_iteration": ms / len(out_[1]), "it_per_s": len(out_[1]) / (ms * 1e-3),
+                     "F_last": float(out_[1][-1])}
+    out["c2_dopt_500x50000_drivers"] = res
+    print("c2", res, flush=True)
+    del f
+    torch.cuda.empty_cache()
 
 if "c5" in which:
     m, n = 2000, 1000000
