@@ -205,28 +205,43 @@ def BPG(f, h, L, x0, maxitrs, epsilon=1e-14, linesearch=True, ls_ratio=1.2,
             T[pk] = lp.now()
             stop = pk
         return lp.result(x), F[0:stop + 1], Ls[0:stop + 1], T[0:stop + 1]
+    # Line search: f(x_{k+1}) is what the accepted trial already evaluated, and so is the objective's linear image
+    # (M(x) / A x) of the accepted point, so from the second iteration on the gradient comes from the carried image
+    # (no second pass over H / A) and there is no host round trip before the first trial.
+    Ix = lp.img(x)
+    fx_known = None
     for k in range(maxitrs):
-        g = lp.enq_fg(x, rt.S_F)
+        g = lp.enq_start(None, None, None, x, Ix, 2, rt.S_F)
         lp.enq_psi(x)
-        vals = lp.fetch()
-        fx = vals[rt.S_F]
-        F[k] = fx + lp.psi(vals)
         T[k] = lp.now()
+        if fx_known is None or not linesearch:
+            vals = lp.fetch()
+            fx = vals[rt.S_F]
+            F[k] = fx + lp.psi(vals)
+        else:
+            fx = fx_known
+            F[k] = np.nan                                 # completed by the first trial's fetch (Psi rides along)
         if linesearch:
             L = L / ls_ratio
             while True:
                 x1 = lp.div_prox(x, g, L)
-                lp.enq_f(x1, rt.S_F2)
+                Ix1 = lp.img(x1)
+                lp.enq_f_img(x1, Ix1, rt.S_F2)
                 lp.enq_dot_diff(g, x1, x)
                 lp.enq_div(x1, x, rt.S_DXY)
                 vals = lp.fetch()
+                if np.isnan(F[k]):
+                    F[k] = fx + lp.psi(vals)
                 if vals[rt.S_F2] > fx + vals[rt.S_DOT] + L * vals[rt.S_DXY]:      # algorithms.py:53
                     L = L * ls_ratio
                 else:
                     break
             x = x1
+            Ix = Ix1
+            fx_known = vals[rt.S_F2]
         else:
             x = lp.div_prox(x, g, L)
+            Ix = lp.img(x)
         Ls[k] = L
         if verbose and k % verbskip == 0:
             print("{0:6d}  {1:10.3e}  {2:10.3e}  {3:6.1f}".format(k, F[k], L, T[k]))
