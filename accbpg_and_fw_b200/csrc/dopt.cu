@@ -782,6 +782,25 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(const double* part, 
     }
 }
 
+// Gram matrix of a simplex vertex s (s = fill everywhere, s[i] = radius; functions_lmo.py:153-158) without a pass over H:
+//   H diag(s) H^T = fill * (H H^T) + (radius - fill) * h_i h_i^T
+// G = H H^T of the local columns is formed once per solve; the column index comes from the device slot the LMO wrote.
+__global__ void __launch_bounds__(256) vertex_gram_kernel(const double* __restrict__ H, int m, int64_t n, int64_t ldh,
+                                                          const double* __restrict__ G, double fill,
+                                                          const double* __restrict__ d_idx, int64_t col_offset,
+                                                          double radius, double* __restrict__ out) {
+    const int64_t col = (int64_t)(*d_idx) - col_offset;
+    const bool mine = (col >= 0 && col < n);
+    const double w = radius - fill;
+    const int64_t total = (int64_t)m * m, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int r = (int)(e / m), c = (int)(e - (int64_t)r * m);
+        double v = fill * G[e];
+        if (mine) v = fma(w * __ldg(H + (int64_t)r * ldh + col), __ldg(H + (int64_t)c * ldh + col), v);
+        out[e] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side plan
 struct DoptPlan {
     int mp, nt, n_off, nib;
@@ -995,6 +1014,18 @@ int accbpg_dopt_gram(void* ctx, void* stream, const double* H, int m, int64_t n,
         syrk_reduce_kernel<<<rg, 256, 0, s>>>(p.P, pl.s_off, pl.s_diag, m, pl.mp, M);
     }
     ACCBPG_LAUNCHED("syrk_reduce_kernel");
+    return ACCBPG_OK;
+}
+
+int accbpg_dopt_vertex_gram(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh, const double* G,
+                            double fill, const double* d_idx, int64_t col_offset, double radius, double* out) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !H || !G || !d_idx || !out) return arg_err("dopt_vertex_gram: NULL pointer");
+    if (m < 1 || n < 1 || ldh < n) return arg_err("dopt_vertex_gram: shape");
+    int grid = grid_for(c, (int64_t)m * m, 256, 2, 8);
+    vertex_gram_kernel<<<grid, 256, 0, s>>>(H, m, n, ldh, G, fill, d_idx, col_offset, radius, out);
+    ACCBPG_LAUNCHED("vertex_gram_kernel");
     return ACCBPG_OK;
 }
 

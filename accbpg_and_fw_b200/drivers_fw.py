@@ -54,10 +54,19 @@ def FW_alg_div_step(f, h, L, x0, maxitrs, gamma, lmo,
     F, Ls, T = [], [], []
     delta = 1e-6
     x = lp.x0
+    # With config.linear_images the objective's image of every trial point x + alpha (s - x) is the combination
+    # (1 - alpha) I(x) + alpha I(s): one image of s per iteration instead of one pass over H / A per trial.  For the
+    # simplex LMO over a D-optimal objective I(s) itself needs no pass either (DOptimalObj._img_vertex).
+    Ix = lp.img(x)
+    fast_vertex = lp.lin and hasattr(lmo, "_enq") and hasattr(f, "_img_vertex")
     for k in range(maxitrs):
-        g = lp.enq_fg(x, rt.S_F)
+        g = lp.enq_start(None, None, None, x, Ix, 2, rt.S_F)
         lp.enq_psi(x)
         s = _call_lmo(lp, lmo, g)
+        if fast_vertex:
+            Is = f._img_vertex(rt.S_AUX0 + 1, 1e-15, lmo.radius)       # the LMO left (min g, index) in S_AUX0, S_AUX0+1
+        else:
+            Is = lp.img(s)
         lp.enq_div(s, x, rt.S_DXY)
         lp.enq_dot_diff(g, s, x)                     # <g, s - x>
         vals = lp.fetch()
@@ -77,13 +86,15 @@ def FW_alg_div_step(f, h, L, x0, maxitrs, gamma, lmo,
         while True:
             alpha = min((-gdp / (2 * L * div)) ** (1 / (gamma - 1)), 1.0)
             x1 = _step(lp, x, s, alpha)
+            Ix1 = lp.img_combo(1 - alpha, Ix, alpha, Is)
             if not linesearch:
                 break
             assert not math.isinf(L), "L is infinite"
-            lp.enq_f(x1, rt.S_F2)
+            lp.enq_f_img(x1, Ix1, rt.S_F2)
             if lp.fetch()[rt.S_F2] <= fx + alpha * gdp + alpha ** gamma * L * div:     # algorithms_fw.py:61
                 break
             L = L * ls_ratio
+        Ix = lp.img_refresh(k, x1, Ix1)
         x = x1
         Ls.append(L)
         if verbose and k % verbskip == 0:

@@ -81,6 +81,25 @@ class DOptimalObj(RSmoothFunction):
                                        Ib.data_ptr(), out.data_ptr()))
         return out
 
+    def _img_vertex(self, idx_slot, fill, radius):
+        """M(s) for the simplex vertex s (fill everywhere, radius at the column whose global index sits in the device
+        slot idx_slot) from H H^T of the local columns: no pass over H (accbpg_dopt_vertex_gram)."""
+        rt = self.rt
+        H = self._Hd
+        if getattr(self, "_G1", None) is None:
+            ones = torch.ones(self.n_local, dtype=torch.float64, device=rt.device)
+            self._G1 = torch.empty(self.m, self.m, dtype=torch.float64, device=rt.device)
+            nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
+                                           ones.data_ptr(), self._ws.data_ptr(), self._G1.data_ptr()))
+        M = torch.empty(self.m, self.m, dtype=torch.float64, device=rt.device)
+        off = self.shard.lo if self.shard is not None else 0
+        nat.check(lib.accbpg_dopt_vertex_gram(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
+                                              self._G1.data_ptr(), float(fill), rt.slot(idx_slot), off, float(radius),
+                                              M.data_ptr()))
+        if self.shard is not None and self.shard.world > 1:
+            self.shard.sum_(M)
+        return M
+
     def _enqueue_img_pair(self, Ix, slot_x, Iy, flag_y, slot_y, g):
         """f from M(x) -> slot_x (skipped when Ix is None) and (f, grad f) from M(y) -> (slot_y, g): K2-K4 only."""
         rt = self.rt

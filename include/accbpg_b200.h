@@ -180,6 +180,13 @@ size_t accbpg_dopt_workspace_bytes(int m, int64_t n_local);
  * as a full symmetric m x m matrix with leading dimension m.  Sets ST_X_NEGATIVE if some x < 0. */
 int accbpg_dopt_gram(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
                      const double* d_x, void* d_ws, double* d_M);
+/* Gram matrix of a simplex vertex s (s = fill everywhere, s[i] = radius: lmo_simplex, functions_lmo.py:153-158) from
+ * d_G = H H^T of the local columns:  fill*G + (radius - fill) h_i h_i^T.  d_idx: device double holding the GLOBAL column
+ * index the LMO chose (accbpg_lmo_simplex's d_out[1]); columns outside [col_offset, col_offset + n_local) add nothing.
+ * Lets FW_alg_div_step (algorithms_fw.py:6-75) form M(x + alpha(s - x)) = (1-alpha) M(x) + alpha M(s) without a SYRK. */
+int accbpg_dopt_vertex_gram(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
+                            const double* d_G, double fill, const double* d_idx, int64_t col_offset, double radius,
+                            double* d_out);
 /* K2 (+K3): blocked Cholesky M = L L^T, out of place (d_M symmetric m x m is only read); d_out[0] = -log det M =
  * -sum log(pivot).  d_L (m x m, may be NULL) receives the lower factor, zero above the diagonal.  want_inverse != 0
  * also leaves L^{-1} in the workspace for accbpg_dopt_grad: the block forward substitution rides in the same launches
