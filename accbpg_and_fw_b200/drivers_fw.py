@@ -27,6 +27,14 @@ def _call_lmo(lp, lmo, g):
     return rt.to_device(lmo(g))
 
 
+def _vertex_image(lp, f, lmo, s):
+    """Objective image of the LMO's answer: for the simplex LMO over a D-optimal objective from H H^T and the chosen
+    column (DOptimalObj._img_vertex; the LMO left the index in S_AUX0 + 1), otherwise one pass (None when images are off)."""
+    if lp.lin and hasattr(lmo, "_enq") and hasattr(f, "_img_vertex"):
+        return f._img_vertex(lp.rt.S_AUX0 + 1, 1e-15, lmo.radius)
+    return lp.img(s)
+
+
 def _step(lp, x, s, alpha):
     """x + alpha*(s - x)   (algorithms_fw.py:34,54 / :227-231)."""
     rt = lp.rt
@@ -58,15 +66,11 @@ def FW_alg_div_step(f, h, L, x0, maxitrs, gamma, lmo,
     # (1 - alpha) I(x) + alpha I(s): one image of s per iteration instead of one pass over H / A per trial.  For the
     # simplex LMO over a D-optimal objective I(s) itself needs no pass either (DOptimalObj._img_vertex).
     Ix = lp.img(x)
-    fast_vertex = lp.lin and hasattr(lmo, "_enq") and hasattr(f, "_img_vertex")
     for k in range(maxitrs):
         g = lp.enq_start(None, None, None, x, Ix, 2, rt.S_F)
         lp.enq_psi(x)
         s = _call_lmo(lp, lmo, g)
-        if fast_vertex:
-            Is = f._img_vertex(rt.S_AUX0 + 1, 1e-15, lmo.radius)       # the LMO left (min g, index) in S_AUX0, S_AUX0+1
-        else:
-            Is = lp.img(s)
+        Is = _vertex_image(lp, f, lmo, s)
         lp.enq_div(s, x, rt.S_DXY)
         lp.enq_dot_diff(g, s, x)                     # <g, s - x>
         vals = lp.fetch()
@@ -115,7 +119,8 @@ def FW_alg_descent_step(f, h, x0, maxitrs, lmo, epsilon=1e-14, verbose=True, ver
     G = np.zeros(maxitrs)
     T = np.zeros(maxitrs)
     x = lp.x0
-    g = lp.enq_fg(x, rt.S_F)
+    Ix = lp.img(x)
+    g = lp.enq_start(None, None, None, x, Ix, 2, rt.S_F)
     lp.enq_psi(x)
     vals = lp.fetch()
     F[0] = vals[rt.S_F] + lp.psi(vals)
@@ -123,9 +128,11 @@ def FW_alg_descent_step(f, h, x0, maxitrs, lmo, epsilon=1e-14, verbose=True, ver
     k = 0
     for k in range(1, maxitrs):
         s = _call_lmo(lp, lmo, g)
+        Is = _vertex_image(lp, f, lmo, s)
         alpha = 2 / (k + 2)
         x = _step(lp, x, s, alpha)
-        g = lp.enq_fg(x, rt.S_F)
+        Ix = lp.img_refresh(k, x, lp.img_combo(1 - alpha, Ix, alpha, Is))
+        g = lp.enq_start(None, None, None, x, Ix, 2, rt.S_F)
         lp.enq_psi(x)
         nat.check(lib.accbpg_vec_dot(rt.ctx, rt.stream, lp.n, g.data_ptr(), g.data_ptr(), rt.slot(rt.S_DOT)))
         vals = lp.fetch()                                # sharded: the partial slots are summed over the ranks here
@@ -168,11 +175,13 @@ def FW_alg_L0_L1_shortest_step(f, h, L0, L1, x0, maxitrs, gamma, lmo, epsilon=1e
     F, Ls, T = [], [], []
     delta = 1e-8
     x = lp.x0
+    Ix = lp.img(x)
     toggle = 0
     for k in range(maxitrs):
-        g = lp.enq_fg(x, rt.S_F)
+        g = lp.enq_start(None, None, None, x, Ix, 2, rt.S_F)
         lp.enq_psi(x)
         s = _call_lmo(lp, lmo, g)
+        Is = _vertex_image(lp, f, lmo, s)
         lp.enq_dot_diff(g, s, x)                     # <g, s - x>
         lp.enq_div(s, x, rt.S_DXY)
         _enq_gnorm2(lp, g, rt.S_DZZ)
@@ -194,9 +203,10 @@ def FW_alg_L0_L1_shortest_step(f, h, L0, L1, x0, maxitrs, gamma, lmo, epsilon=1e
             a_k = L0 + L1 * g_norm
             alpha_k = min((-gdp / (a_k * div * np.e)) ** (1 / (gamma - 1)), 1)
             x1 = _step(lp, x, s, alpha_k)
+            Ix1 = lp.img_combo(1 - alpha_k, Ix, alpha_k, Is)
             if not linesearch:
                 break
-            lp.enq_f(x1, rt.S_F2)
+            lp.enq_f_img(x1, Ix1, rt.S_F2)
             if lp.fetch()[rt.S_F2] <= fx + alpha_k * gdp + alpha_k ** gamma * (a_k / 2) * np.e * div:
                 break
             if toggle == 0:
@@ -206,6 +216,7 @@ def FW_alg_L0_L1_shortest_step(f, h, L0, L1, x0, maxitrs, gamma, lmo, epsilon=1e
                 L1 *= ls_ratio - (L1 * g_norm) / a_k
                 toggle = 0
         x = x1
+        Ix = lp.img_refresh(k, x1, Ix1)
         Ls.append(a_k)
         if verbose and k % verbskip == 0:
             print(f"{k:6d}   {F[k]:10.3e}   {Ls[k]:10.3e}   {L0:10.3e}   {L1:10.3e}   {alpha_k:10.3e}   {T[k]:6.1f}")
@@ -231,10 +242,12 @@ def _fw_l0l1_log(f, h, L0, L1, x0, maxitrs, lmo, ls_ratio, epsilon, L0_max, L1_m
     delta = 1e-8
     toggle = 0
     x = lp.x0
+    Ix = lp.img(x)
     for k in range(maxitrs):
-        g = lp.enq_fg(x, rt.S_F)
+        g = lp.enq_start(None, None, None, x, Ix, 2, rt.S_F)
         lp.enq_psi(x)
         s = _call_lmo(lp, lmo, g)
+        Is = _vertex_image(lp, f, lmo, s)
         lp.enq_dot_diff(g, s, x)
         _enq_gnorm2(lp, g, rt.S_DXY)
         _enq_dnorm2(lp, s, x, rt.S_DZZ)
@@ -271,9 +284,10 @@ def _fw_l0l1_log(f, h, L0, L1, x0, maxitrs, lmo, ls_ratio, epsilon, L0_max, L1_m
                 alpha_k = L1 * (-gdp) / (a_k * d_norm)
                 LOG_STEPS.append(LOG_STEPS[-1])
             x1 = _step(lp, x, s, alpha_k)
+            Ix1 = lp.img_combo(1 - alpha_k, Ix, alpha_k, Is)
             if not linesearch:
                 break
-            lp.enq_f(x1, rt.S_F2)
+            lp.enq_f_img(x1, Ix1, rt.S_F2)
             fx1 = lp.fetch()[rt.S_F2]
             z = L1 * alpha_k * d_norm
             exp_term = np.expm1(z) - z if z < 50 else 0.5 * z ** 2
@@ -292,6 +306,7 @@ def _fw_l0l1_log(f, h, L0, L1, x0, maxitrs, lmo, ls_ratio, epsilon, L0_max, L1_m
                 L1 = min(L1 * ls_ratio, L1_max) if L1_max else L1 * ls_ratio
             a_k = L0 + L1 * gx_norm
         x = x1
+        Ix = lp.img_refresh(k, x1, Ix1)
         Ls.append(a_k)
         if verbose and k % verbskip == 0:
             print(f"{k:6d}   {F[k]:10.3e}   {Ls[k]:10.3e}   {L0:10.3e}   {L1:10.3e}   {LOG_STEPS[k]:6d}      {T[k]:6.1f}")
