@@ -198,6 +198,15 @@ def test_direct_evaluation_mode_matches_too(acc, dopt, golden_traj):
             hk = acc.ShannonEntropySimplex()
             out = acc.ABPG_gain(fk, hk, 1.0, np.ones(400) / 400, gamma=2.0, maxitrs=120, verbose=False)
             assert ferr(out[1], golden_traj["kls_gain_F"][:120]) <= FTOL
+            # line-search drivers carry the accepted trial's image / the vertex image
+            x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=300, linesearch=True, ls_ratio=1.2, verbose=False)
+            assert ferr(F, golden_traj["bpg_ls_F"][:300]) <= FTOL and np.array_equal(Ls, golden_traj["bpg_ls_Ls"][:300])
+            x, F, Ls, T = acc.FW_alg_div_step(f, h, L, x0, 300, 2.0, acc.lmo_simplex(), ls_ratio=2, verbose=False)
+            assert ferr(F, golden_traj["fwdiv_F"]) <= FTOL and np.array_equal(Ls, golden_traj["fwdiv_Ls"])
+            out = acc.FW_alg_div_step(fk, hk, 1.0, np.ones(400) / 400, 100, 2.0, acc.lmo_simplex(), verbose=False)
+            assert ferr(out[1], golden_traj["kls_fw_F"]) <= FTOL
+            x, F, T, G = acc.FW_alg_descent_step(f, h, x0, 300, acc.lmo_simplex(), verbose=False)
+            assert ferr(F, golden_traj["fwdesc_F"]) <= FTOL
     finally:
         config.linear_images = old
 
