@@ -440,6 +440,7 @@ __global__ void fw_ctrl_init_from_slot_kernel(double* ctrl, const double* neg_lo
     __syncthreads();
     if (threadIdx.x == 0) ctrl[C_LOGDET_HI] = -neg_logdet_slot[0];
 }
+__global__ void fw_zero_lo_kernel(double* ctrl) { ctrl[C_LOGDET_LO] = 0.0; }
 __global__ void __launch_bounds__(256) negate_kernel(int64_t n, double* x) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = -x[i];
@@ -550,6 +551,15 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
     cudaLaunchConfig_t cfg = {};
     cfg.stream = s;
     cfg.attrs = attr;
+    if (away && k_start > 0) {
+        // D_opt_FW_away records log det of the *updated, rounded* Hinv by a fresh LU every iteration (D_opt_alg.py:136);
+        // the determinant-lemma accumulator follows the exact update instead, so it is re-anchored on the actual Hinv
+        // at every batch boundary (value-only Cholesky: -log det(Hinv) = log det(V X V^T))
+        rc = accbpg_dopt_factor(ctx, stream, m, Hinv, nullptr, 0, ws, ctrl + C_LOGDET_HI);
+        if (rc) return rc;
+        fw_zero_lo_kernel<<<1, 1, 0, s>>>(ctrl);
+        ACCBPG_LAUNCHED("fw_zero_lo_kernel");
+    }
     // the first decision of the batch
     p.k = k_start; p.decide = 1; p.reverse = 0;
     cfg.gridDim = dim3(L.sel_grid); cfg.blockDim = dim3(FW_THREADS); cfg.dynamicSmemBytes = 0; cfg.numAttrs = 0;
