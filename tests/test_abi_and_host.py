@@ -123,6 +123,11 @@ li = int(torch.argmin(gl)); pair = torch.tensor([float(gl[li]), float(li + sh.lo
 sh.argmin_(pair); assert pair.tolist() == [0.25, 3.0], pair
 m = torch.tensor([float(gl.min())], dtype=torch.float64); sh.min_(m); assert m.item() == 0.25
 assert sh.owner(3) == 0 and sh.owner(8) == 1
+# equal-length gather used by the sharded Burg-simplex root-find and the FW selection records: padding = +inf
+pad = torch.full((sh.width,), float("inf"), dtype=torch.float64); pad[: loc.numel()] = loc
+allv = torch.empty(sh.width * world, dtype=torch.float64); sh.all_gather_equal(allv, pad)
+got = torch.cat([allv[r * sh.width: r * sh.width + (sh.offsets[r + 1] - sh.offsets[r])] for r in range(world)])
+assert torch.equal(got, full) and torch.isinf(allv).sum().item() == sh.width * world - 11
 dist.destroy_process_group()
 print("ok", rank)
 '''
