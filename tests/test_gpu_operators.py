@@ -399,3 +399,26 @@ def test_lmo_nuclear_norm_ball(acc):
         assert np.max(np.abs(out - ref)) <= 1e-9
         outd = acc.lmo_nuclear_norm_ball()(torch.tensor(G, device="cuda"))
         assert outd.is_cuda and np.max(np.abs(outd.cpu().numpy() - ref)) <= 1e-9
+
+
+def test_vertex_gram_matches_the_syrk_of_the_vertex(acc):
+    """accbpg_dopt_vertex_gram: fill*HH^T + (radius - fill) h_i h_i^T against the SYRK of the LMO's vertex vector."""
+    from accbpg_and_fw_b200 import _native as nat
+    lib = nat.lib
+    rt = acc.Runtime.get()
+    for m, n in [(30, 1000), (129, 520)]:
+        f, h, L, x0 = acc.D_opt_design(m, n, randseed=4)
+        rng = np.random.RandomState(m)
+        g = rng.randn(n)
+        g[[7, 311]] = g.min() - 1.0                      # exact tie: the first index wins
+        lmo = acc.lmo_simplex(radius=2.0)
+        s = lmo(g)
+        assert lmo.last_index() == 7
+        gd = torch.tensor(g, device="cuda")
+        sd = torch.empty(n, dtype=torch.float64, device="cuda")
+        lmo._enq(gd, sd, rt.S_AUX0)
+        Mv = f._img_vertex(rt.S_AUX0 + 1, 1e-15, 2.0).cpu().numpy()
+        Ms = f._img_compute(sd).cpu().numpy()
+        ref = (f.H * s) @ f.H.T
+        assert np.max(np.abs(Mv - ref)) <= 1e-12 * np.max(np.abs(ref))
+        assert np.max(np.abs(Ms - ref)) <= 1e-12 * np.max(np.abs(ref))
