@@ -23,7 +23,7 @@ namespace accbpg {
 // Lower 128x128 tiles only.  Off-diagonal tiles use all 16 warps; in a diagonal tile the six warp tiles strictly above
 // the diagonal are skipped, the four on the diagonal also skip their own strictly-upper 16x16 quarter (TMA kernel), and
 // the ten that remain are numbered so that the four SM sub-partitions carry equal-ish DMMA counts (table below): a
-// diagonal tile costs 5/8 of a full one (and stages its 128 rows of H once, as both operands).  The column range is
+// diagonal tile costs 9/16 of a full one (and stages its 128 rows of H once, as both operands).  The column range is
 // split differently for the two kinds of tile so that every CTA carries about the same work.
 struct SyrkParams {
     const double* H;
@@ -38,9 +38,9 @@ struct SyrkParams {
 };
 
 // Warp -> warp tile of a diagonal CTA tile.  Warp id mod 4 is the SM sub-partition.  The six tiles below the diagonal
-// cost 16 DMMAs per k-step, the four on it 12 (their strictly-upper 16x16 quarter is skipped), so sub-partitions 0 and 1
-// get one full + two diagonal tiles (40) and sub-partitions 2 and 3 two full ones (32): a diagonal CTA tile costs
-// 40/64 of a full one.
+// cost 16 DMMAs per k-step, the four on it 10 (their strictly-upper 8x8 mma tiles are skipped; 12 in the cp.async
+// fallback), so sub-partitions 0 and 1 get one full + two diagonal tiles (36) and sub-partitions 2 and 3 two full ones
+// (32): a diagonal CTA tile costs 36/64 of a full one.
 __constant__ signed char kDiagWm[16] = {1, 2, 2, 3, 0, 2, 3, 3, 1, 3, -1, -1, -1, -1, -1, -1};
 __constant__ signed char kDiagWn[16] = {0, 0, 1, 1, 0, 2, 0, 2, 1, 3, -1, -1, -1, -1, -1, -1};
 
@@ -198,8 +198,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_dmma_kernel(SyrkParams p
 // completion is signalled on per-stage mbarriers (full / empty), and there is no CTA-wide barrier in the main loop.
 // With the 128-byte swizzle the 16-byte chunk index of (row, k) is (k/2) ^ (row & 7).  A DMMA fragment read touches
 // rows g = 0..3 and 32 contiguous bytes per row in a half warp, which would be a 2-way conflict under the natural row
-// order; mma row g of tile i is therefore mapped to tile row 16*(i/2) + 2g + (i&1) (and the same for the columns of
-// the output), which makes the half warp's eight (row, chunk) pairs land on eight distinct chunks.
+// order; mma row g of tile i is therefore mapped to row 8i + 2(g&3) + (g>>2) of the warp tile (and the same for the
+// columns of the output): a half warp then touches rows 0,2,4,6 (or 1,3,5,7) of an 8-row group and its eight
+// (row, chunk) pairs land on eight distinct chunks, while every mma tile still covers 8 consecutive rows, so the
+// diagonal warp tiles can drop their strictly-upper 8x8 mma tiles.
 constexpr int TMA_STAGES = 6;
 constexpr int TMA_PREFETCH = 4;                          // slabs in flight ahead of the consumers
 constexpr int TMA_STAGE_BYTES = 2 * BM * BK * 8 + 1024;  // A box, B box, x slab (padded to keep 1024-byte alignment)
@@ -307,15 +309,12 @@ syrk_tma_kernel(SyrkParams p, const __grid_constant__ CUtensorMap tmH, const __g
 #pragma unroll
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // per-thread byte offsets inside a stage: tile row of mma row g for even / odd tiles, with the swizzle term folded in
+    // per-thread byte offset inside a stage, with the swizzle term folded in
     //   element (row, k = 4kk + t):  row*128 + ((2kk + t/2) ^ (row & 7))*16 + (t & 1)*8 = base ^ (kk << 5)
-    uint32_t offA[2], offB[2];
-#pragma unroll
-    for (int pq = 0; pq < 2; ++pq) {
-        const int ra = (active ? wm : 0) * 32 + 2 * g + pq, rb = (active ? wn : 0) * 32 + 2 * g + pq;
-        offA[pq] = ra * 128 + ((((t >> 1) ^ (ra & 7))) << 4) + (t & 1) * 8;
-        offB[pq] = rb * 128 + ((((t >> 1) ^ (rb & 7))) << 4) + (t & 1) * 8 + (diag ? 0 : BM * BK * 8);
-    }
+    const int pg = 2 * (g & 3) + (g >> 2);                        // mma row g -> row pg of its 8-row group
+    const int ra = (active ? wm : 0) * 32 + pg, rb = (active ? wn : 0) * 32 + pg;
+    const uint32_t offA = ra * 128 + ((((t >> 1) ^ pg)) << 4) + (t & 1) * 8;
+    const uint32_t offB = rb * 128 + ((((t >> 1) ^ pg)) << 4) + (t & 1) * 8 + (diag ? 0 : BM * BK * 8);
 
     bool neg = false;
     for (int s = 0; s < KT; ++s) {
@@ -338,14 +337,14 @@ syrk_tma_kernel(SyrkParams p, const __grid_constant__ CUtensorMap tmH, const __g
                     neg |= (xv < 0.0);
                     double a[MI], bq[NI];
 #pragma unroll
-                    for (int i = 0; i < MI; ++i) a[i] = lds_f64(base + ((offA[i & 1] ^ (kk << 5)) + (i >> 1) * 16 * 128));
+                    for (int i = 0; i < MI; ++i) a[i] = lds_f64(base + ((offA ^ (kk << 5)) + i * 8 * 128));
 #pragma unroll
-                    for (int j = 0; j < NI; ++j) bq[j] = lds_f64(base + ((offB[j & 1] ^ (kk << 5)) + (j >> 1) * 16 * 128)) * xv;
+                    for (int j = 0; j < NI; ++j) bq[j] = lds_f64(base + ((offB ^ (kk << 5)) + j * 8 * 128)) * xv;
 #pragma unroll
                     for (int i = 0; i < MI; ++i)
 #pragma unroll
                         for (int j = 0; j < NI; ++j)
-                            if (!(i < 2 && j >= 2))      // rows 0..15 x columns 16..31 of the tile lie above the diagonal
+                            if (i >= j)                  // 8x8 mma tiles strictly above the diagonal are never read
                                 dmma884(acc[i][j][0], acc[i][j][1], a[i], bq[j]);
                 }
             } else {
@@ -355,9 +354,9 @@ syrk_tma_kernel(SyrkParams p, const __grid_constant__ CUtensorMap tmH, const __g
                     neg |= (xv < 0.0);
                     double a[MI], bq[NI];
 #pragma unroll
-                    for (int i = 0; i < MI; ++i) a[i] = lds_f64(base + ((offA[i & 1] ^ (kk << 5)) + (i >> 1) * 16 * 128));
+                    for (int i = 0; i < MI; ++i) a[i] = lds_f64(base + ((offA ^ (kk << 5)) + i * 8 * 128));
 #pragma unroll
-                    for (int j = 0; j < NI; ++j) bq[j] = lds_f64(base + ((offB[j & 1] ^ (kk << 5)) + (j >> 1) * 16 * 128)) * xv;
+                    for (int j = 0; j < NI; ++j) bq[j] = lds_f64(base + ((offB ^ (kk << 5)) + j * 8 * 128)) * xv;
 #pragma unroll
                     for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -375,12 +374,13 @@ syrk_tma_kernel(SyrkParams p, const __grid_constant__ CUtensorMap tmH, const __g
     double* P = p.P + (size_t)split * p.mp * p.mp;
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
-        const int row = bi * BM + wm * 32 + 16 * (i >> 1) + 2 * g + (i & 1);
+        const int row = bi * BM + wm * 32 + 8 * i + pg;
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int col = bj * BN + wn * 32 + 16 * (j >> 1) + 2 * (2 * t + e) + (j & 1);
+                const int nn = 2 * t + e;
+                const int col = bj * BN + wn * 32 + 8 * j + 2 * (nn & 3) + (nn >> 2);
                 P[(size_t)row * p.mp + col] = acc[i][j][e];
             }
         }
@@ -809,11 +809,11 @@ struct DoptPlan {
     size_t off_P, off_Linv, off_Y, off_part, off_M, off_L, off_W, off_M2, off_W2, total;
 };
 
-// Relative cost of a diagonal tile: 40/64 by DMMA count; its sub-partitions host only 2-3 active warps instead of 4,
+// Relative cost of a diagonal tile: 36/64 by DMMA count; its sub-partitions host only 2-3 active warps instead of 4,
 // which hides less latency, so the effective figure is a little higher (calibrated on B200; ACCBPG_DIAG_COST overrides).
 static double syrk_diag_cost() {
     static double v = -1.0;
-    if (v < 0.0) { const char* e = getenv("ACCBPG_DIAG_COST"); v = e ? atof(e) : 0.625; }
+    if (v < 0.0) { const char* e = getenv("ACCBPG_DIAG_COST"); v = e ? atof(e) : 0.5625; }
     return v;
 }
 
