@@ -213,6 +213,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// consumer release of a stage it has only read: the reads are complete once the DMMAs that use them have issued, so no
+// release fence is needed in front of the arrival (a release arrive shows up as membar stalls, one per warp and slab)
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -317,6 +322,7 @@ syrk_tma_kernel(SyrkParams p, const __grid_constant__ CUtensorMap tmH, const __g
     const uint32_t offB = rb * 128 + ((((t >> 1) ^ pg)) << 4) + (t & 1) * 8 + (diag ? 0 : BM * BK * 8);
 
     bool neg = false;
+    const bool check_x = (warp == 0);      // one warp sees every x of the chunk; the sign test stays off the FP64 pipe
     for (int s = 0; s < KT; ++s) {
         const int st = s % TMA_STAGES;
         const uint32_t base = smem0 + st * TMA_STAGE_BYTES;
@@ -334,7 +340,7 @@ syrk_tma_kernel(SyrkParams p, const __grid_constant__ CUtensorMap tmH, const __g
 #pragma unroll
                 for (int kk = 0; kk < BK / 4; ++kk) {
                     const double xv = lds_f64(xs + kk * 32);
-                    neg |= (xv < 0.0);
+                    if (check_x) neg |= (__double2hiint(xv) < 0) & (((__double2hiint(xv) & 0x7fffffff) | __double2loint(xv)) != 0);
                     double a[MI], bq[NI];
 #pragma unroll
                     for (int i = 0; i < MI; ++i) a[i] = lds_f64(base + ((offA ^ (kk << 5)) + i * 8 * 128));
@@ -351,7 +357,7 @@ syrk_tma_kernel(SyrkParams p, const __grid_constant__ CUtensorMap tmH, const __g
 #pragma unroll
                 for (int kk = 0; kk < BK / 4; ++kk) {
                     const double xv = lds_f64(xs + kk * 32);
-                    neg |= (xv < 0.0);
+                    if (check_x) neg |= (__double2hiint(xv) < 0) & (((__double2hiint(xv) & 0x7fffffff) | __double2loint(xv)) != 0);
                     double a[MI], bq[NI];
 #pragma unroll
                     for (int i = 0; i < MI; ++i) a[i] = lds_f64(base + ((offA ^ (kk << 5)) + i * 8 * 128));
@@ -364,7 +370,7 @@ syrk_tma_kernel(SyrkParams p, const __grid_constant__ CUtensorMap tmH, const __g
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bars + 8 * (TMA_STAGES + st));
+            if (lane == 0) mbar_arrive_relaxed(bars + 8 * (TMA_STAGES + st));
         }
     }
     if (neg) atomicOr(p.status, ACCBPG_ST_X_NEGATIVE);
