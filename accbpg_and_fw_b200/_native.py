@@ -17,6 +17,7 @@ _CTYPES = {
     "void*": ctypes.c_void_p,
     "const void*": ctypes.c_void_p,
     "void**": ctypes.POINTER(ctypes.c_void_p),
+    "void* const*": ctypes.POINTER(ctypes.c_void_p),
     "const double*": ctypes.c_void_p,     # device or host address passed as an integer
     "double*": ctypes.c_void_p,
     "uint32_t*": ctypes.POINTER(ctypes.c_uint32),

@@ -15,7 +15,13 @@ pipeline
     accbpg_ctx_read_async): the GPU never idles between iterations.  Recorded values and the returned iterate are
     those of the synchronous loop; when the stopping test fires, the one iteration enqueued beyond it is discarded.
     Switched off automatically with verbose=True or restart=True.
+
+peer_allreduce
+    Column-sharded D-optimal objective: sum the ranks' Gram matrices through NVLink peer memory in kernels of this
+    library (accbpg_dopt_gram_allreduce, buffers from torch.distributed._symmetric_memory) instead of an NCCL all-reduce
+    after the SYRK.  Falls back to NCCL when symmetric memory cannot be set up.
 """
 linear_images = True
 reanchor_every = 64
 pipeline = True
+peer_allreduce = __import__('os').environ.get('ACCBPG_PEER_ALLREDUCE', '1') != '0'

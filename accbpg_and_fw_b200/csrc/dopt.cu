@@ -407,6 +407,92 @@ __global__ void __launch_bounds__(256) syrk_reduce_kernel(const double* P, int s
     M[(size_t)j * m + i] = s;
 }
 
+// ------------------------------------------------------------------------------------------ K1 + cross-GPU sum
+// Column-sharded runs: the Gram matrix is the sum of the ranks' local ones.  Instead of an NCCL all-reduce after the
+// split reduction, the reduction itself continues across the GPUs through NVLink peer memory (buffers from
+// torch.distributed._symmetric_memory, every rank's mapped into every other rank's address space):
+//   A  syrk_reduce_push_kernel: split sums stored into slot `rank` of every rank's receive buffer (remote stores);
+//      the last CTA raises this rank's flag word on every rank
+//   B  gram_sum_received_kernel: wait for the `world` flags, sum the received lower triangles in rank order -> M
+// Every rank sums the same numbers in the same order: all ranks hold the same bits.  Flags carry a call counter (epoch),
+// so nothing is ever reset; the receive buffer is double-buffered on the epoch's parity (a rank can be one call ahead of
+// a peer that is still summing, never two); waits are bounded and trap on a protocol error.
+
+constexpr int kMaxPeers = 16;
+struct PeerGram {
+    double* recv[kMaxPeers];                    // every rank's receive buffer: [2 (epoch parity)][world (sender)][m*m]
+    unsigned long long* flags[kMaxPeers];       // every rank's flag words: [world (sender)], last epoch received
+    int rank, world;
+    unsigned long long epoch;
+    int64_t total;                              // m*m
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Split reduction of the SYRK partials with the result pushed over NVLink: every thread sums the partial tiles of one
+// lower-triangle element and stores it into slot `rank` of EVERY rank's receive buffer (posted remote stores, 256-byte
+// runs along j); the last CTA to finish raises this rank's flag word on every rank.
+__global__ void __launch_bounds__(256) syrk_reduce_push_kernel(const double* P, int s_off, int s_diag, int m, int mp,
+                                                               PeerGram g, unsigned int* counter) {
+    __shared__ bool sh_last;
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (i < m && j <= i) {
+        const int splits = ((i >> 7) == (j >> 7)) ? s_diag : s_off;
+        const size_t off = (size_t)i * mp + j, sz = (size_t)mp * mp;
+        double s = 0.0;
+        for (int k = 0; k < splits; ++k) s += __ldcg(P + k * sz + off);
+        const size_t dst = ((size_t)(g.epoch & 1) * g.world + g.rank) * g.total + (size_t)i * m + j;
+        for (int r = 0; r < g.world; ++r) {
+            int q = g.rank + r;                    // start with the own buffer, then round-robin over the peers
+            if (q >= g.world) q -= g.world;
+            g.recv[q][dst] = s;
+        }
+    }
+    __threadfence_system();                        // this CTA's remote stores are performed before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        sh_last = (t == gridDim.x * gridDim.y - 1);
+        if (sh_last) *counter = 0u;
+    }
+    __syncthreads();
+    if (sh_last) {
+        __threadfence_system();
+        if (threadIdx.x < g.world) st_release_sys(g.flags[threadIdx.x] + g.rank, g.epoch);
+    }
+}
+
+// Waits until every rank's matrix of this epoch has arrived in the local receive buffer, then sums the `world` lower
+// triangles in rank order (all ranks form bit-identical sums) and writes M with its mirror.
+__global__ void __launch_bounds__(256) gram_sum_received_kernel(PeerGram g, int m, double* M) {
+    if (threadIdx.x < g.world) {
+        const unsigned long long* f = g.flags[g.rank] + threadIdx.x;
+        int spin = 0;
+        while (ld_acquire_sys(f) < g.epoch) {
+            if (++spin > (1 << 26)) __trap();
+            __nanosleep(20);
+        }
+    }
+    __syncthreads();
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (i < m && j <= i) {
+        const double* src = g.recv[g.rank] + (size_t)(g.epoch & 1) * g.world * g.total + (size_t)i * m + j;
+        double s = 0.0;
+        for (int r = 0; r < g.world; ++r) s += __ldcg(src + (size_t)r * g.total);   // L2: the slots are rewritten by peers
+        M[(size_t)i * m + j] = s;
+        M[(size_t)j * m + i] = s;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K4: gradient
 struct TrmmParams {
     const double* Linv;   // [mp][mp], zero above the diagonal
@@ -959,11 +1045,8 @@ size_t accbpg_dopt_workspace_bytes(int m, int64_t n_local) {
     return make_plan(m, n_local, device_sm_count()).total;
 }
 
-int accbpg_dopt_gram(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh, const double* x,
-                     void* ws, double* M) {
-    Ctx* c = (Ctx*)ctx;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (!c || !H || !x || !ws || !M) return arg_err("dopt_gram: NULL pointer");
+// the SYRK proper: partial tiles of every column split into the workspace
+static int syrk_partials(Ctx* c, cudaStream_t s, const double* H, int m, int64_t n, int64_t ldh, const double* x, void* ws) {
     if (m < 1 || n < 1 || ldh < n) return arg_err("dopt_gram: shape");
     int rc = ensure_smem_attrs();
     if (rc) return rc;
@@ -1014,12 +1097,56 @@ int accbpg_dopt_gram(void* ctx, void* stream, const double* H, int m, int64_t n,
         else    syrk_dmma_kernel<false><<<grid, GEMM_THREADS, KMAJOR_SMEM, s>>>(p);
     }
     ACCBPG_LAUNCHED("syrk_dmma_kernel");
+    return ACCBPG_OK;
+}
+
+int accbpg_dopt_gram(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh, const double* x,
+                     void* ws, double* M) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !H || !x || !ws || !M) return arg_err("dopt_gram: NULL pointer");
+    int rc = syrk_partials(c, s, H, m, n, ldh, x, ws);
+    if (rc) return rc;
+    DoptPlan pl = make_plan(m, n, c->sm_count);
+    const double* Pp = (const double*)((char*)ws + pl.off_P);
     dim3 rg((m + 31) / 32, (m + 7) / 8);
     {
         ProfScope ps(P_SYRK_REDUCE, s);
-        syrk_reduce_kernel<<<rg, 256, 0, s>>>(p.P, pl.s_off, pl.s_diag, m, pl.mp, M);
+        syrk_reduce_kernel<<<rg, 256, 0, s>>>(Pp, pl.s_off, pl.s_diag, m, pl.mp, M);
     }
     ACCBPG_LAUNCHED("syrk_reduce_kernel");
+    return ACCBPG_OK;
+}
+
+int accbpg_dopt_gram_allreduce(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh, const double* x,
+                               void* ws, int rank, int world, void* const* peer_recv, void* const* peer_flags,
+                               uint64_t epoch, double* M) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !H || !x || !ws || !M || !peer_recv || !peer_flags) return arg_err("dopt_gram_allreduce: NULL pointer");
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return arg_err("dopt_gram_allreduce: rank / world");
+    if (m < 1 || n < 1 || ldh < n || epoch < 1) return arg_err("dopt_gram_allreduce: shape / epoch");
+    PeerGram g;
+    for (int r = 0; r < world; ++r) {
+        g.recv[r] = (double*)peer_recv[r];
+        g.flags[r] = (unsigned long long*)peer_flags[r];
+        if (!g.recv[r] || !g.flags[r]) return arg_err("dopt_gram_allreduce: NULL peer pointer");
+    }
+    g.rank = rank; g.world = world; g.epoch = epoch;
+    g.total = (int64_t)m * m;
+    // the SYRK itself: partial tiles into the workspace (the pushing split reduction replaces syrk_reduce_kernel)
+    int rc = syrk_partials(c, s, H, m, n, ldh, x, ws);
+    if (rc) return rc;
+    DoptPlan pl = make_plan(m, n, c->sm_count);
+    const double* P = (const double*)((char*)ws + pl.off_P);
+    dim3 rg((m + 31) / 32, (m + 7) / 8);
+    {
+        ProfScope ps(P_SYRK_REDUCE, s);
+        syrk_reduce_push_kernel<<<rg, 256, 0, s>>>(P, pl.s_off, pl.s_diag, m, pl.mp, g, c->d_counter + 16);
+        ACCBPG_LAUNCHED("syrk_reduce_push_kernel");
+        gram_sum_received_kernel<<<rg, 256, 0, s>>>(g, m, M);
+        ACCBPG_LAUNCHED("gram_sum_received_kernel");
+    }
     return ACCBPG_OK;
 }
 

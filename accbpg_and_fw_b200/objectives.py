@@ -57,8 +57,58 @@ class DOptimalObj(RSmoothFunction):
         assert self.m < self.n, "DOptimalObj: need m < n"
         self._ws = self.rt.workspace(("dopt", self.m, self.n_local),
                                      lib.accbpg_dopt_workspace_bytes(self.m, self.n_local))
+        self._peer = None
         if shard is not None and shard.world > 1:
             self._M = torch.empty(self.m, self.m, dtype=torch.float64, device=self.rt.device)
+            self._setup_peer_memory()
+
+    # ---- peer-memory all-reduce of the Gram matrix (config.peer_allreduce) ------------------------------------
+    def _setup_peer_memory(self):
+        """Symmetric buffers for accbpg_dopt_gram_allreduce: the receive slots for every rank's Gram matrix and the flag
+        words, mapped into every peer (collective call: every rank constructs the objective)."""
+        from . import config
+        self._peer = None
+        sh = self.shard
+        if not config.peer_allreduce or sh.world > 16 or not torch.distributed.is_initialized():
+            return
+        if torch.distributed.get_backend(sh.group) != "nccl":
+            return
+        try:
+            import ctypes
+            import torch.distributed._symmetric_memory as symm
+            grp = sh.group if sh.group is not None else torch.distributed.group.WORLD
+            mm = self.m * self.m
+            dev = self.rt.device
+            bufs = [symm.empty(2 * sh.world * mm, dtype=torch.float64, device=dev),
+                    symm.empty(sh.world, dtype=torch.int64, device=dev)]
+            bufs[1].zero_()
+            hdls = [symm.rendezvous(b, grp) for b in bufs]
+            arrs = []
+            for hd in hdls:
+                arr = (ctypes.c_void_p * sh.world)(*[int(p) for p in hd.buffer_ptrs])
+                arrs.append(arr)
+            torch.cuda.synchronize()
+            torch.distributed.barrier(grp)              # flags are zero everywhere before the first call
+            self._peer = {"bufs": bufs, "hdls": hdls, "arrs": arrs, "epoch": 0}
+        except Exception as exc:                          # no symmetric memory on this system: NCCL all-reduce
+            import warnings
+            warnings.warn(f"peer-memory all-reduce unavailable ({exc!r}); using NCCL")
+            self._peer = None
+
+    def _gram_sharded(self, xd, M):
+        """M <- sum over ranks of H_r diag(x_r) H_r^T."""
+        rt = self.rt
+        H = self._Hd
+        if self._peer is not None:
+            pr = self._peer
+            pr["epoch"] += 1
+            nat.check(lib.accbpg_dopt_gram_allreduce(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
+                                                     xd.data_ptr(), self._ws.data_ptr(), self.shard.rank, self.shard.world,
+                                                     pr["arrs"][0], pr["arrs"][1], pr["epoch"], M.data_ptr()))
+            return
+        nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
+                                       xd.data_ptr(), self._ws.data_ptr(), M.data_ptr()))
+        self.shard.sum_(M)
 
     # ---- linear image M(x) = H diag(x) H^T (config.linear_images) ------------------------------------------
     _lin_capable = True
@@ -68,10 +118,11 @@ class DOptimalObj(RSmoothFunction):
         rt = self.rt
         H = self._Hd
         M = torch.empty(self.m, self.m, dtype=torch.float64, device=rt.device)
+        if self.shard is not None and self.shard.world > 1:
+            self._gram_sharded(xd, M)
+            return M
         nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
                                        xd.data_ptr(), self._ws.data_ptr(), M.data_ptr()))
-        if self.shard is not None and self.shard.world > 1:
-            self.shard.sum_(M)
         return M
 
     def _img_axpby(self, a, Ia, b, Ib):
@@ -131,9 +182,7 @@ class DOptimalObj(RSmoothFunction):
                                                 xd.data_ptr(), flag, self._ws.data_ptr(), rt.slot(slot), gp))
             return
         ws = self._ws.data_ptr()
-        nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
-                                       xd.data_ptr(), ws, self._M.data_ptr()))
-        self.shard.sum_(self._M)
+        self._gram_sharded(xd, self._M)
         nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, self.m, self._M.data_ptr(), None, int(flag >= 1), ws,
                                          rt.slot(slot)))
         if flag >= 1:

@@ -180,6 +180,18 @@ size_t accbpg_dopt_workspace_bytes(int m, int64_t n_local);
  * as a full symmetric m x m matrix with leading dimension m.  Sets ST_X_NEGATIVE if some x < 0. */
 int accbpg_dopt_gram(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
                      const double* d_x, void* d_ws, double* d_M);
+/* Column-sharded form of K1 with the cross-GPU sum fused behind the SYRK over NVLink peer memory instead of an NCCL
+ * all-reduce (reference: the same HXHT, accbpg/functions.py:153, when H's columns live on several GPUs).  The split
+ * reduction that ends the SYRK stores each summed lower-triangle element straight into slot `rank` of EVERY rank's
+ * receive buffer (remote stores), the last CTA raises this rank's flag word on every rank; a second kernel waits for the
+ * `world` flags and sums the received matrices in rank order into d_M (full, mirrored) - all ranks end with bit-identical
+ * M.  peer_recv / peer_flags: host arrays of `world` device pointers to every rank's symmetric buffers
+ * (2*world*m*m doubles - double-buffered on epoch parity - and `world` uint64 flag words, zero-initialised once; e.g.
+ * torch.distributed._symmetric_memory buffer_ptrs); epoch: 1, 2, 3, ..., one per call on these buffers, the same on
+ * every rank.  world <= 16.  A rank that waits longer than ~1 min for a peer traps. */
+int accbpg_dopt_gram_allreduce(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
+                               const double* d_x, void* d_ws, int rank, int world, void* const* peer_recv,
+                               void* const* peer_flags, uint64_t epoch, double* d_M);
 /* Gram matrix of a simplex vertex s (s = fill everywhere, s[i] = radius: lmo_simplex, functions_lmo.py:153-158) from
  * d_G = H H^T of the local columns:  fill*G + (radius - fill) h_i h_i^T.  d_idx: device double holding the GLOBAL column
  * index the LMO chose (accbpg_lmo_simplex's d_out[1]); columns outside [col_offset, col_offset + n_local) add nothing.

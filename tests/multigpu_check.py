@@ -76,6 +76,20 @@ def main():
         xb, Fb, SPb, SNb, Tb = orc.D_opt_FW_away(fo.H, x0, 1e-8, its)
         assert len(Fa) == len(Fb) and ferr(Fa, Fb) <= 1e-9
         report[f"dopt_{m}x{n}"] = (ferr(F, Fo), ferr(out[1], outo[1]), ferr(Fs, Fr), ferr(Fa, Fb))
+        # Gram all-reduce through NVLink peer memory (the default) against the NCCL all-reduce of the same matrices
+        from accbpg_and_fw_b200 import config
+        report[f"peer_allreduce_{m}"] = f._peer is not None
+        if f._peer is not None:
+            config.peer_allreduce = False
+            f_nccl = acc.DOptimalObj(sh.cols(fo.H), shard=sh)
+            config.peer_allreduce = True
+            assert f_nccl._peer is None
+            for rep in range(20):                      # repeated calls: flag epochs and buffer reuse
+                xt = sh.part(x0 * (1.0 + 0.01 * rep))
+                a, ga = f.func_grad(xt)
+                b, gb = f_nccl.func_grad(xt)
+                assert abs(a - b) <= 1e-13 * abs(b), (rep, a, b)
+                assert np.max(np.abs(ga - gb) / np.abs(gb)) <= 1e-11, rep
     # LMO tie across ranks: lowest global index wins
     n = 1000
     sh = acc.ColumnShard(n)
