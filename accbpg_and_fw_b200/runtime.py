@@ -130,6 +130,14 @@ class Runtime:
             return a.to(device=self.device, dtype=F64).contiguous()
         arr = np.ascontiguousarray(a, dtype=np.float64)
         if arr.ndim == 1 and 0 < arr.size <= (1 << 24):
+            base = arr.base
+            if isinstance(base, torch.Tensor) and base.is_pinned() and arr.flags.writeable:
+                # a vector this package returned (like_input) and the caller passes back unchanged in type: its memory
+                # is page-locked already, so the DMA reads it in place (the calling operator synchronises before it
+                # returns, so the caller cannot modify it under the copy)
+                out = torch.empty(arr.size, dtype=F64, device=self.device)
+                out.copy_(torch.from_numpy(arr), non_blocking=True)
+                return out
             # host vectors go through a small ring of pinned staging buffers: one CPU memcpy, then an asynchronous DMA
             # on the current stream (a pageable cudaMemcpy would block and stage through the driver's own buffer).
             # Every public operator call ends with a synchronising read, so a ring of 8 cannot be overrun.
@@ -153,5 +161,14 @@ def is_host(a):
 
 
 def like_input(t, host):
-    """Return a device result in the form the caller used: NumPy for NumPy inputs, the tensor otherwise."""
-    return t.cpu().numpy() if host else t
+    """Return a device result in the form the caller used: NumPy for NumPy inputs, the tensor otherwise.
+    Host results are fresh arrays in page-locked memory (torch's caching host allocator owns the block and takes it back
+    when the array is dropped): the download is one DMA with no pageable staging copy."""
+    if not host:
+        return t
+    if t.dim() == 1 and 0 < t.numel() <= (1 << 24) and t.dtype == F64:
+        out = torch.empty(t.numel(), dtype=F64, pin_memory=True)
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return out.numpy()
+    return t.cpu().numpy()

@@ -422,3 +422,28 @@ def test_vertex_gram_matches_the_syrk_of_the_vertex(acc):
         ref = (f.H * s) @ f.H.T
         assert np.max(np.abs(Mv - ref)) <= 1e-12 * np.max(np.abs(ref))
         assert np.max(np.abs(Ms - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def test_host_results_are_fresh_arrays_and_can_be_passed_back(acc):
+    """Ownership rule of the reference protocol: operators return fresh, writable arrays and never mutate
+    their inputs.  Host results live in page-locked memory and are uploaded in place when passed back; the values must
+    equal those obtained from an ordinary copy of the same vector."""
+    fo, ho, Lo, x0 = orc.D_opt_design(60, 3000, randseed=4)
+    f = acc.DOptimalObj(fo.H)
+    h = acc.BurgEntropySimplex()
+    g1 = f.gradient(x0)
+    g2 = f.gradient(x0)
+    assert isinstance(g1, np.ndarray) and g1.flags.writeable and g1.dtype == np.float64
+    assert not np.shares_memory(g1, g2) and np.array_equal(g1, g2)
+    keep = g1.copy()
+    z_direct = h.div_prox_map(x0, g1, 0.9)                 # g1: page-locked result passed back
+    z_copy = h.div_prox_map(x0, np.array(keep), 0.9)       # ordinary pageable copy
+    assert np.array_equal(z_direct, z_copy) and np.array_equal(g1, keep)
+    z_view = h.div_prox_map(x0[5:], g1[5:], 0.9)           # a view into a page-locked result
+    assert np.array_equal(z_view, h.div_prox_map(x0[5:].copy(), keep[5:].copy(), 0.9))
+    g1 *= 2.0                                              # the caller owns the result
+    assert np.array_equal(f.gradient(x0), g2)
+    for _ in range(20):                                    # the host allocator recycles blocks of dropped results only
+        a = f.gradient(x0)
+        b = h.div_prox_map(x0, a, 0.9)
+        assert np.array_equal(a, g2) and np.array_equal(b, z_copy)
