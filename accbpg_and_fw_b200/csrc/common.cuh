@@ -153,6 +153,26 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, bool* s
 }
 
 __device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
+
+// ---- flag words in NVLink peer memory (symmetric buffers mapped into every rank) ----
+// A sender stores its payload into the receiver's buffer, fences at system scope and releases a monotonically increasing
+// epoch into its flag word on the receiver; the receiver acquires the word before touching the payload.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// bounded: a peer that never arrives (protocol error, dead rank) traps this kernel after about a minute instead of hanging
+__device__ __forceinline__ void peer_flag_wait(const unsigned long long* f, unsigned long long epoch) {
+    int spin = 0;
+    while (ld_acquire_sys(f) < epoch) {
+        if (++spin > (1 << 26)) __trap();
+        __nanosleep(20);
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace accbpg

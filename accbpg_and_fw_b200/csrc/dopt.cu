@@ -427,14 +427,6 @@ struct PeerGram {
     int64_t total;                              // m*m
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // Split reduction of the SYRK partials with the result pushed over NVLink: every thread sums the partial tiles of one
 // lower-triangle element and stores it into slot `rank` of EVERY rank's receive buffer (posted remote stores, 256-byte
@@ -474,12 +466,7 @@ __global__ void __launch_bounds__(256) syrk_reduce_push_kernel(const double* P, 
 // triangles in rank order (all ranks form bit-identical sums) and writes M with its mirror.
 __global__ void __launch_bounds__(256) gram_sum_received_kernel(PeerGram g, int m, double* M) {
     if (threadIdx.x < g.world) {
-        const unsigned long long* f = g.flags[g.rank] + threadIdx.x;
-        int spin = 0;
-        while (ld_acquire_sys(f) < g.epoch) {
-            if (++spin > (1 << 26)) __trap();
-            __nanosleep(20);
-        }
+        peer_flag_wait(g.flags[g.rank] + threadIdx.x, g.epoch);
     }
     __syncthreads();
     const int j = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -1252,7 +1239,10 @@ static int dopt_factor_grad(Ctx* c, cudaStream_t s, const double* H, int m, int6
     const int64_t npanels = (n + BN - 1) / BN;
     const int64_t ntiles = (int64_t)pl.nib * npanels;
     const bool al = aligned16(H) && (ldh % 2 == 0) && (n % 2 == 0);
-    const int n_early = pl.nib / 2 < 4 ? pl.nib / 2 : 4;      // row blocks 0 .. n_early-1 start under the chain
+    static int early_env = -2;
+    if (early_env == -2) { const char* e = getenv("ACCBPG_EARLY_BLOCKS"); early_env = e ? atoi(e) : -1; }
+    int n_early = pl.nib / 2 < 4 ? pl.nib / 2 : 4;            // row blocks 0 .. n_early-1 start under the chain
+    if (early_env >= 0) n_early = early_env < pl.nib - 1 ? early_env : pl.nib - 1;
     if (!overlap_enabled() || !al || !syrk_tma_enabled() || !encode_tiled_fn() || n_early < 1 || ntiles >= (1LL << 30)) {
         int rc = accbpg_dopt_factor(c, s, m, M, nullptr, 1, ws, d_f_out);
         if (rc) return rc;

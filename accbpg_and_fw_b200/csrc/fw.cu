@@ -119,7 +119,17 @@ __device__ __forceinline__ void fw_cand_block(FwCand& c, FwCand* sh /* >= 32 */)
     }
 }
 
+// Column-sharded loop over NVLink peer memory (accbpg_fw_run_peer): every rank's receive buffers, mapped everywhere.
+constexpr int FW_MAX_PEERS = 16;
+struct FwPeer {
+    FwCand* rec[FW_MAX_PEERS];                 // [2 (epoch parity)][world (sender)] selection records
+    double* col[FW_MAX_PEERS];                 // [2 (epoch parity)][m] the chosen column, written by its owner
+    unsigned long long* flags[FW_MAX_PEERS];   // [world] last record epoch per sender, [world] = last column epoch
+    int rank, world;                           // world == 0: not in use
+};
+
 struct FwParams {
+    FwPeer peer;
     const double* V; int m; int64_t n, ldv;
     double* x; double* w; double* Hinv; double* u; double* v;
     double* ctrl;
@@ -210,6 +220,23 @@ __device__ __forceinline__ void fw_decide(const FwParams& p, const FwCand& cd, i
     if (*sh_go) {
         const long long col = *sh_idx - p.col_offset;
         const bool mine = (col >= 0 && col < p.n);
+        if (p.peer.world > 0) {
+            // peer memory: the owner stores the column into every rank's receive slot of this epoch's parity and
+            // releases the column flag; nobody else writes
+            if (mine) {
+                const unsigned long long epoch = (unsigned long long)p.k + 1ULL;
+                const size_t slot = (size_t)(epoch & 1ULL) * p.m;
+                for (int r = threadIdx.x; r < p.m; r += blockDim.x) {
+                    const double val = p.V[(int64_t)r * p.ldv + col];
+                    for (int q = 0; q < p.peer.world; ++q) p.peer.col[q][slot + r] = val;
+                }
+                __threadfence_system();
+                __syncthreads();
+                if ((int)threadIdx.x < p.peer.world)
+                    st_release_sys(p.peer.flags[threadIdx.x] + p.peer.world, epoch);
+            }
+            return;
+        }
         // column-sharded: ranks that do not own the column contribute zeros; the caller sums v over the ranks
         for (int r = threadIdx.x; r < p.m; r += blockDim.x) p.v[r] = mine ? p.V[(int64_t)r * p.ldv + col] : 0.0;
     }
@@ -244,7 +271,17 @@ __device__ __forceinline__ void fw_select_tail(const FwParams& p, FwCand& cd, in
     __syncthreads();
     cd = sh_c[0];
     if (p.decide == 2) {
-        if (threadIdx.x == 0) *p.cand_out = cd;
+        if (p.peer.world > 0) {
+            // record of iteration p.k -> slot `rank` of every rank's receive buffer, then this rank's flag word there
+            if ((int)threadIdx.x < p.peer.world) {
+                const unsigned long long epoch = (unsigned long long)p.k + 1ULL;
+                p.peer.rec[threadIdx.x][(size_t)(epoch & 1ULL) * p.peer.world + p.peer.rank] = cd;
+                __threadfence_system();
+                st_release_sys(p.peer.flags[threadIdx.x] + p.peer.rank, epoch);
+            }
+        } else if (threadIdx.x == 0) {
+            *p.cand_out = cd;
+        }
         return;
     }
     fw_decide(p, cd, sh_go, sh_idx);
@@ -258,6 +295,29 @@ __global__ void __launch_bounds__(FW_THREADS) fw_decide_kernel(FwParams p, const
     FwCand cd;
     fw_cand_init(cd);
     for (int r = 0; r < world; ++r) {
+        FwCand q;
+        q.amax = ld_cg(&recs[r].amax); q.imax = __ldcg(&recs[r].imax);
+        q.smin = ld_cg(&recs[r].smin); q.imin = __ldcg(&recs[r].imin); q.xmin = ld_cg(&recs[r].xmin);
+        q.fmask = __ldcg(&recs[r].fmask); q.wmask = ld_cg(&recs[r].wmask); q.xmask = ld_cg(&recs[r].xmask);
+        fw_cand_merge(cd, q);
+    }
+    fw_decide(p, cd, &sh_go, &sh_idx);
+}
+
+// the same over peer memory: wait for every rank's record of iteration p.k in the local receive buffer
+__global__ void __launch_bounds__(FW_THREADS) fw_decide_peer_kernel(FwParams p) {
+    __shared__ int sh_go;
+    __shared__ long long sh_idx;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (ld_cg(&p.ctrl[C_STOP]) != 0.0) return;
+    const unsigned long long epoch = (unsigned long long)p.k + 1ULL;
+    if ((int)threadIdx.x < p.peer.world) peer_flag_wait(p.peer.flags[p.peer.rank] + threadIdx.x, epoch);
+    __syncthreads();
+    const FwCand* recs = p.peer.rec[p.peer.rank] + (size_t)(epoch & 1ULL) * p.peer.world;
+    FwCand cd;
+    fw_cand_init(cd);
+    for (int r = 0; r < p.peer.world; ++r) {
         FwCand q;
         q.amax = ld_cg(&recs[r].amax); q.imax = __ldcg(&recs[r].imax);
         q.smin = ld_cg(&recs[r].smin); q.imin = __ldcg(&recs[r].imin); q.xmin = ld_cg(&recs[r].xmin);
@@ -286,10 +346,15 @@ __global__ void __launch_bounds__(FW_THREADS) fw_select_kernel(FwParams p) {
 
 // u = Hinv v (warp per row)            D_opt_alg.py:78 / :165 / :174
 __global__ void __launch_bounds__(256) fw_hv_kernel(const double* __restrict__ Hinv, int m, const double* __restrict__ v,
-                                                    double* __restrict__ u, const double* ctrl) {
+                                                    double* __restrict__ u, const double* ctrl,
+                                                    const unsigned long long* col_flag, unsigned long long epoch) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (ld_cg(&ctrl[C_STOP]) != 0.0) return;
+    if (col_flag) {                          // peer memory: v arrives from the rank that owns the chosen column
+        if (threadIdx.x == 0) peer_flag_wait(col_flag, epoch);
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= m) return;
@@ -525,6 +590,7 @@ static int fw_prepare(Ctx* c, const double* V, int m, int64_t n, int64_t ldv, in
     p.hist_F = hist_F; p.hist_SP = hist_SP; p.hist_SN = hist_SN; p.hist_T = hist_T;
     p.parts = parts; p.counter = c->d_counter; p.away = away; p.eps = eps; p.nblk = L->nblk; p.nr1 = L->r1_ctas;
     p.k = 0; p.decide = 0; p.reverse = 0; p.cand_out = nullptr; p.col_offset = 0; p.sharded = 0;
+    p.peer.world = 0; p.peer.rank = 0;
     return ACCBPG_OK;
 }
 
@@ -568,7 +634,8 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
     for (int k = k_start; k < k_start + k_count; ++k) {
         ProfScope ps_iter(P_FW_ITER, s);
         cfg.gridDim = dim3(L.hv_grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.numAttrs = 1;
-        ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, fw_hv_kernel, (const double*)Hinv, m, (const double*)p.v, p.u, (const double*)ctrl));
+        ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, fw_hv_kernel, (const double*)Hinv, m, (const double*)p.v, p.u, (const double*)ctrl,
+                                       (const unsigned long long*)nullptr, 0ULL));
         ACCBPG_LAUNCHED("fw_hv_kernel");
         p.k = k + 1;                                        // the tail decides the next iteration ...
         p.decide = (k + 1 < k_start + k_count) ? 1 : 0;     // ... except after the last pass of the batch
@@ -631,7 +698,7 @@ int accbpg_fw_step(void* ctx, void* stream, const double* V, int m, int64_t n_lo
     int rc = fw_prepare(c, V, m, n_local, ldv, away, 0.0, ws, Hinv, x, w, ctrl, nullptr, nullptr, nullptr, nullptr, &L);
     if (rc) return rc;
     FwParams& p = L.p;
-    fw_hv_kernel<<<L.hv_grid, 256, 0, s>>>(Hinv, m, d_vcol, p.u, ctrl);
+    fw_hv_kernel<<<L.hv_grid, 256, 0, s>>>(Hinv, m, d_vcol, p.u, ctrl, nullptr, 0ULL);
     ACCBPG_LAUNCHED("fw_hv_kernel");
     p.k = k + 1; p.decide = 2; p.reverse = k & 1; p.cand_out = (FwCand*)d_record_out; p.col_offset = col_offset;
     auto pass_fn = L.pass_vec ? fw_pass_kernel<true> : fw_pass_kernel<false>;
@@ -640,6 +707,77 @@ int accbpg_fw_step(void* ctx, void* stream, const double* V, int m, int64_t n_lo
         pass_fn<<<L.nblk + L.r1_ctas, FWP_THREADS, L.pass_smem, s>>>(p);
     }
     ACCBPG_LAUNCHED("fw_pass_kernel");
+    return ACCBPG_OK;
+}
+
+// The column-sharded loop with both exchanges over NVLink peer memory instead of NCCL: iterations k_start ..
+// k_start+k_count-1 in one call, three launches each (programmatic dependent launch):
+//   decide(k): wait for the `world` records of iteration k, merge in rank order, decide; the owner of the chosen column
+//              stores it into every rank's column slot and releases the column flag
+//   u = Hinv v: waits for the column flag
+//   pass(k):   local pass + rank-one update; its tail stores this rank's record of iteration k+1 into every rank's
+//              record slots and releases this rank's flag word there
+// Records and columns are double-buffered on the iteration's parity; a rank can be one iteration ahead of a peer, never two.
+int accbpg_fw_run_peer(void* ctx, void* stream, const double* V, int m, int64_t n_local, int64_t ldv, int64_t col_offset,
+                       int away, double eps, int k_start, int k_count, int rank, int world, void* const* peer_rec,
+                       void* const* peer_col, void* const* peer_flags, void* ws, double* Hinv, double* x, double* w,
+                       double* ctrl, double* hist_F, double* hist_SP, double* hist_SN, double* hist_T) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !V || !ws || !Hinv || !x || !w || !ctrl || !hist_F || !hist_SP || !hist_SN || !hist_T || !peer_rec ||
+        !peer_col || !peer_flags)
+        return arg_err("fw_run_peer: NULL pointer");
+    if (world < 1 || world > FW_MAX_PEERS || rank < 0 || rank >= world || k_count < 0 || k_start < 0)
+        return arg_err("fw_run_peer: rank / world / range");
+    if (k_count == 0) return ACCBPG_OK;
+    FwLaunch L;
+    int rc = fw_prepare(c, V, m, n_local, ldv, away, eps, ws, Hinv, x, w, ctrl, hist_F, hist_SP, hist_SN, hist_T, &L);
+    if (rc) return rc;
+    FwParams& p = L.p;
+    for (int r = 0; r < world; ++r) {
+        p.peer.rec[r] = (FwCand*)peer_rec[r]; p.peer.col[r] = (double*)peer_col[r];
+        p.peer.flags[r] = (unsigned long long*)peer_flags[r];
+        if (!p.peer.rec[r] || !p.peer.col[r] || !p.peer.flags[r]) return arg_err("fw_run_peer: NULL peer pointer");
+    }
+    p.peer.rank = rank; p.peer.world = world;
+    p.col_offset = col_offset; p.sharded = 1;
+    auto pass_fn = L.pass_vec ? fw_pass_kernel<true> : fw_pass_kernel<false>;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = s;
+    cfg.attrs = attr;
+    if (away && k_start > 0) {           // re-anchor log det on the actual (replicated) Hinv, as accbpg_fw_run does
+        rc = accbpg_dopt_factor(ctx, stream, m, Hinv, nullptr, 0, ws, ctrl + C_LOGDET_HI);
+        if (rc) return rc;
+        fw_zero_lo_kernel<<<1, 1, 0, s>>>(ctrl);
+        ACCBPG_LAUNCHED("fw_zero_lo_kernel");
+    }
+    if (k_start == 0) {                  // the record of iteration 0; later ones come from the tail of the previous pass
+        p.k = 0; p.decide = 2; p.reverse = 0;
+        fw_select_kernel<<<L.sel_grid, FW_THREADS, 0, s>>>(p);
+        ACCBPG_LAUNCHED("fw_select_kernel");
+    }
+    const unsigned long long* col_flag = p.peer.flags[rank] + world;
+    for (int k = k_start; k < k_start + k_count; ++k) {
+        const unsigned long long epoch = (unsigned long long)k + 1ULL;
+        p.k = k; p.decide = 1;
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(FW_THREADS); cfg.dynamicSmemBytes = 0; cfg.numAttrs = 1;
+        ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, fw_decide_peer_kernel, p));
+        ACCBPG_LAUNCHED("fw_decide_peer_kernel");
+        const double* vcol = p.peer.col[rank] + (size_t)(epoch & 1ULL) * m;
+        cfg.gridDim = dim3(L.hv_grid); cfg.blockDim = dim3(256);
+        ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, fw_hv_kernel, (const double*)Hinv, m, vcol, p.u, (const double*)ctrl, col_flag, epoch));
+        ACCBPG_LAUNCHED("fw_hv_kernel");
+        p.k = k + 1; p.decide = 2; p.reverse = k & 1;
+        cfg.gridDim = dim3(L.nblk + L.r1_ctas); cfg.blockDim = dim3(FWP_THREADS); cfg.dynamicSmemBytes = L.pass_smem;
+        {
+            ProfScope ps(P_FW_PASS, s);
+            ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, pass_fn, p));
+        }
+        ACCBPG_LAUNCHED("fw_pass_kernel");
+    }
     return ACCBPG_OK;
 }
 

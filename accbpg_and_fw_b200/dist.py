@@ -109,3 +109,33 @@ class ColumnShard:
             if self.offsets[r] <= col < self.offsets[r + 1]:
                 return r
         raise IndexError(col)
+
+
+def peer_buffers(shard, device, specs):
+    """Symmetric (NVLink peer-mapped) buffers for the kernels that exchange data without NCCL.  specs: list of
+    (numel, dtype).  Returns (tensors, pointer arrays) - pointer array i holds every rank's address of buffer i, as a
+    ctypes array of `world` void pointers - or None when symmetric memory is not available (not NCCL, one rank, switched
+    off by config.peer_allreduce, or torch cannot map the buffers).  Collective: every rank of the group must call it.
+    The buffers come back zero-filled and a barrier has passed, so flag words are zero on every rank."""
+    import ctypes
+    import warnings
+    import torch.distributed as dist
+    from . import config
+    if shard is None or shard.world < 2 or shard.world > 16 or not config.peer_allreduce or not dist.is_initialized():
+        return None
+    if dist.get_backend(shard.group) != "nccl":
+        return None
+    try:
+        import torch.distributed._symmetric_memory as symm
+        grp = shard.group if shard.group is not None else dist.group.WORLD
+        bufs = [symm.empty(int(numel), dtype=dtype, device=device) for numel, dtype in specs]
+        for b in bufs:
+            b.zero_()
+        hdls = [symm.rendezvous(b, grp) for b in bufs]
+        arrs = [(ctypes.c_void_p * shard.world)(*[int(p) for p in hd.buffer_ptrs]) for hd in hdls]
+        torch.cuda.synchronize()
+        dist.barrier(grp)
+        return bufs, arrs, hdls
+    except Exception as exc:                              # no symmetric memory on this system: the callers use NCCL
+        warnings.warn(f"peer-memory buffers unavailable ({exc!r}); using NCCL")
+        return None

@@ -109,9 +109,14 @@ def _run_sharded(V, x0, eps, maxitrs, away, verbose, verbskip, batch, device, in
     nat.check(lib.accbpg_fw_setup_from_gram(rt.ctx, rt.stream, Vd.data_ptr(), m, n, st, M.data_ptr(), ws.data_ptr(),
                                             Hinv.data_ptr(), w.data_ptr(), ctrl.data_ptr()))
     rt.read(0, 0)
-    nat.check(lib.accbpg_fw_select_local(rt.ctx, rt.stream, n, shard.lo, int(away), x.data_ptr(), w.data_ptr(),
-                                         ws.data_ptr(), m, rec.data_ptr()))
-    shard.all_gather_equal(recs, rec)
+    # both per-iteration exchanges over NVLink peer memory (accbpg_fw_run_peer) when symmetric buffers can be mapped
+    from .dist import peer_buffers
+    peer = peer_buffers(shard, dev, [(2 * shard.world * rec_doubles, torch.float64), (2 * m, torch.float64),
+                                     (shard.world + 1, torch.int64)])
+    if peer is None:
+        nat.check(lib.accbpg_fw_select_local(rt.ctx, rt.stream, n, shard.lo, int(away), x.data_ptr(), w.data_ptr(),
+                                             ws.data_ptr(), m, rec.data_ptr()))
+        shard.all_gather_equal(recs, rec)
     if verbose and shard.rank == 0:
         print("\nSolving D-opt design problem using Frank-Wolfe method" + (" with away steps" if away else ""))
         print("     k      F(x)     pos_slack   neg_slack    time")
@@ -120,7 +125,13 @@ def _run_sharded(V, x0, eps, maxitrs, away, verbose, verbskip, batch, device, in
     done = 0
     while k < maxitrs:
         cnt = 1 if index_log is not None else min(batch, maxitrs - k)
-        for kk in range(k, k + cnt):
+        if peer is not None:
+            nat.check(lib.accbpg_fw_run_peer(rt.ctx, rt.stream, Vd.data_ptr(), m, n, st, shard.lo, int(away), float(eps),
+                                             k, cnt, shard.rank, shard.world, peer[1][0], peer[1][1], peer[1][2],
+                                             ws.data_ptr(), Hinv.data_ptr(), x.data_ptr(), w.data_ptr(), ctrl.data_ptr(),
+                                             hist[0].data_ptr(), hist[1].data_ptr(), hist[2].data_ptr(),
+                                             hist[3].data_ptr()))
+        for kk in range(k, k + cnt) if peer is None else ():
             nat.check(lib.accbpg_fw_decide(rt.ctx, rt.stream, Vd.data_ptr(), m, n, st, shard.lo, int(away), float(eps), kk,
                                            recs.data_ptr(), shard.world, ws.data_ptr(), ctrl.data_ptr(),
                                            hist[0].data_ptr(), hist[1].data_ptr(), hist[2].data_ptr(), hist[3].data_ptr(),
@@ -145,6 +156,10 @@ def _run_sharded(V, x0, eps, maxitrs, away, verbose, verbskip, batch, device, in
     hh = hist[:, :done].cpu().numpy()
     F, SP, SN = hh[0].copy(), hh[1].copy(), hh[2].copy()
     T = t_setup + (hh[3] - hh[3][0]) * 1e-9 if done > 0 else np.zeros(0)
+    if peer is not None:
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier(shard.group)        # nobody frees its receive buffers while a peer may still store into them
     return like_input(x, host), F, SP, SN, T
 
 

@@ -66,34 +66,11 @@ class DOptimalObj(RSmoothFunction):
     def _setup_peer_memory(self):
         """Symmetric buffers for accbpg_dopt_gram_allreduce: the receive slots for every rank's Gram matrix and the flag
         words, mapped into every peer (collective call: every rank constructs the objective)."""
-        from . import config
-        self._peer = None
-        sh = self.shard
-        if not config.peer_allreduce or sh.world > 16 or not torch.distributed.is_initialized():
-            return
-        if torch.distributed.get_backend(sh.group) != "nccl":
-            return
-        try:
-            import ctypes
-            import torch.distributed._symmetric_memory as symm
-            grp = sh.group if sh.group is not None else torch.distributed.group.WORLD
-            mm = self.m * self.m
-            dev = self.rt.device
-            bufs = [symm.empty(2 * sh.world * mm, dtype=torch.float64, device=dev),
-                    symm.empty(sh.world, dtype=torch.int64, device=dev)]
-            bufs[1].zero_()
-            hdls = [symm.rendezvous(b, grp) for b in bufs]
-            arrs = []
-            for hd in hdls:
-                arr = (ctypes.c_void_p * sh.world)(*[int(p) for p in hd.buffer_ptrs])
-                arrs.append(arr)
-            torch.cuda.synchronize()
-            torch.distributed.barrier(grp)              # flags are zero everywhere before the first call
-            self._peer = {"bufs": bufs, "hdls": hdls, "arrs": arrs, "epoch": 0}
-        except Exception as exc:                          # no symmetric memory on this system: NCCL all-reduce
-            import warnings
-            warnings.warn(f"peer-memory all-reduce unavailable ({exc!r}); using NCCL")
-            self._peer = None
+        from .dist import peer_buffers
+        mm = self.m * self.m
+        got = peer_buffers(self.shard, self.rt.device, [(2 * self.shard.world * mm, torch.float64),
+                                                        (self.shard.world, torch.int64)])
+        self._peer = None if got is None else {"bufs": got[0], "arrs": got[1], "hdls": got[2], "epoch": 0}
 
     def _gram_sharded(self, xd, M):
         """M <- sum over ranks of H_r diag(x_r) H_r^T."""

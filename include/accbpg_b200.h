@@ -282,6 +282,20 @@ int accbpg_fw_decide(void* ctx, void* stream, const double* d_V, int m, int64_t 
 int accbpg_fw_step(void* ctx, void* stream, const double* d_V, int m, int64_t n_local, int64_t ldv, int64_t col_offset,
                    int away, int k, void* d_ws, double* d_Hinv, const double* d_vcol, double* d_x, double* d_w,
                    double* d_ctrl, void* d_record_out);
+/* The column-sharded loop with both exchanges over NVLink peer memory instead of NCCL (D_opt_alg.py:52-82 / :136-179
+ * per iteration, as accbpg_fw_run): iterations k_start .. k_start+k_count-1 enqueued in one call, three launches each.
+ * The tail of every pass stores this rank's selection record into slot `rank` of EVERY rank's record buffer and releases
+ * a flag word there; the deciding kernel of the next iteration waits for the `world` flags, merges the records in rank
+ * order and decides (replicated); the rank that owns the chosen column stores it into every rank's column buffer and
+ * releases the column flag, on which u = Hinv v waits.  peer_rec / peer_col / peer_flags: host arrays of `world` device
+ * pointers to every rank's symmetric buffers - 2*world records, 2*m doubles, world+1 uint64 (zero-initialised once; one
+ * set of buffers per run, k_start = 0 first).  Records and columns are double-buffered on the iteration's parity.
+ * d_Hinv, d_ctrl and the histories are replicated; d_x, d_w are this rank's slices. */
+int accbpg_fw_run_peer(void* ctx, void* stream, const double* d_V, int m, int64_t n_local, int64_t ldv,
+                       int64_t col_offset, int away, double eps, int k_start, int k_count, int rank, int world,
+                       void* const* peer_rec, void* const* peer_col, void* const* peer_flags, void* d_ws,
+                       double* d_Hinv, double* d_x, double* d_w, double* d_ctrl, double* d_hist_F, double* d_hist_SP,
+                       double* d_hist_SN, double* d_hist_T);
 
 #ifdef __cplusplus
 }

@@ -175,6 +175,30 @@ def test_midsize_trajectory_vs_oracle(acc):
     assert ferr(a[1], b[1]) <= FTOL and np.array_equal(a[2], b[2])
 
 
+def test_c5_rows_reduced_columns_vs_oracle(acc):
+    """m = 2000 as in BASELINE configs[4] (32 block columns in the Cholesky chain, 16 row blocks in the triangular GEMM,
+    the overlap schedule of the large shape) with n cut to 6000 so the oracle finishes in seconds: operator values, then
+    ABPG_gain, BPG with line search and D_opt_FW_away trajectories."""
+    f, h, L, x0 = acc.D_opt_design(2000, 6000, randseed=5)
+    fo = orc.make_dopt(f.H)
+    ho = orc.make_burg("simplex")
+    fx, g = f.func_grad(x0)
+    fxo, go = fo.func_grad(x0)
+    assert abs(fx - fxo) <= 1e-10 * abs(fxo) and relerr(g, go) <= 1e-9
+    assert abs(float(np.dot(x0, g)) + 2000) <= 1e-9 * 2000
+    a = acc.ABPG_gain(f, h, L, x0, gamma=2, maxitrs=6, verbose=False)
+    b = orc.ABPG_gain(fo, ho, L, x0, gamma=2, maxitrs=6)
+    assert ferr(a[1], b[1]) <= FTOL and np.array_equal(a[2], b[2])
+    a = acc.BPG(f, h, L, x0, maxitrs=6, verbose=False)
+    b = orc.BPG(fo, ho, L, x0, maxitrs=6)
+    assert ferr(a[1], b[1]) <= FTOL and np.array_equal(a[2], b[2])
+    ga, gb = [], []
+    a = acc.D_opt_FW_away(f.H, x0, 1e-8, 150, verbose=False, index_log=ga)
+    b = orc.D_opt_FW_away(fo.H, x0, 1e-8, 150, index_log=gb)
+    assert ferr(a[1], b[1]) <= FTOL
+    assert [(i, j) for i, j, *_ in ga[:len(gb) - 1]] == [(i, j) for i, j, *_ in gb[:len(gb) - 1]]
+
+
 def test_direct_evaluation_mode_matches_too(acc, dopt, golden_traj):
     """config.linear_images = False: every f / grad f is evaluated from scratch (no carried Gram matrix / A x)."""
     from accbpg_and_fw_b200 import config

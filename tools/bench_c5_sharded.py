@@ -20,7 +20,9 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 import accbpg_and_fw_b200 as acc      # noqa: E402
 
-m, n = 2000, 1000000
+m = int(sys.argv[1]) if len(sys.argv) > 1 else 2000          # optional: rows, total columns, FW iterations
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 1000000
+fw_iters = int(sys.argv[3]) if len(sys.argv) > 3 else 200
 SLABS = 8                               # the instance is defined as 8 slabs of 125000 columns, whatever the rank count
 dev = torch.device("cuda", local)
 sh = acc.ColumnShard(n) if world > 1 else None
@@ -64,11 +66,14 @@ iters = 8
 res, ms = timed(lambda: acc.ABPG_gain(f, h, 1.0, x0, gamma=2, maxitrs=iters, verbose=False))
 F = res[1]
 acc.D_opt_FW_away(H, x0, 1e-12, 20, verbose=False, shard=sh)
-resf, msf = timed(lambda: acc.D_opt_FW_away(H, x0, 1e-12, 200, verbose=False, shard=sh))
+resf, msf = timed(lambda: acc.D_opt_FW_away(H, x0, 1e-12, fw_iters, verbose=False, shard=sh))
+Tf = resf[4]
 if rank == 0:
-    print(json.dumps({"config": "D-opt 2000x1000000, H column-sharded", "n_gpus": world,
+    print(json.dumps({"config": f"D-opt {m}x{n}, H column-sharded", "n_gpus": world,
                       "abpg_gain_ms_per_iteration": ms / len(F), "abpg_gain_it_per_s": len(F) / (ms * 1e-3),
                       "F": [float(v) for v in F],
-                      "fw_away_it_per_s": len(resf[1]) / (msf * 1e-3), "fw_away_F_last": float(resf[1][-1])}), flush=True)
+                      "fw_away_it_per_s": len(resf[1]) / (msf * 1e-3),        # whole call, setup included
+                      "fw_away_it_per_s_from_T": (len(Tf) - 1) / (Tf[-1] - Tf[0]),  # the reference's convention
+                      "peer_memory": bool(__import__("accbpg_and_fw_b200.config", fromlist=["x"]).peer_allreduce), "fw_away_F_last": float(resf[1][-1])}), flush=True)
 if world > 1:
     dist.destroy_process_group()
