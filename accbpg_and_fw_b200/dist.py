@@ -111,12 +111,17 @@ class ColumnShard:
         raise IndexError(col)
 
 
-def peer_buffers(shard, device, specs):
+_peer_cache = {}
+
+
+def peer_buffers(shard, device, specs, cache_key=None):
     """Symmetric (NVLink peer-mapped) buffers for the kernels that exchange data without NCCL.  specs: list of
     (numel, dtype).  Returns (tensors, pointer arrays) - pointer array i holds every rank's address of buffer i, as a
     ctypes array of `world` void pointers - or None when symmetric memory is not available (not NCCL, one rank, switched
     off by config.peer_allreduce, or torch cannot map the buffers).  Collective: every rank of the group must call it.
-    The buffers come back zero-filled and a barrier has passed, so flag words are zero on every rank."""
+    The buffers come back zero-filled and a barrier has passed, so flag words are zero on every rank.
+    cache_key: reuse the buffers of an earlier call with the same key (mapping symmetric memory costs ~0.1 s); the caller
+    guarantees that no peer still stores into them (a barrier after its last kernel)."""
     import ctypes
     import warnings
     import torch.distributed as dist
@@ -125,6 +130,16 @@ def peer_buffers(shard, device, specs):
         return None
     if dist.get_backend(shard.group) != "nccl":
         return None
+    key = None
+    if cache_key is not None:
+        key = (cache_key, id(shard.group), shard.world, str(device), tuple((int(a), str(b)) for a, b in specs))
+        hit = _peer_cache.get(key)
+        if hit is not None:
+            for b in hit[0]:
+                b.zero_()
+            torch.cuda.synchronize()
+            dist.barrier(shard.group)
+            return hit
     try:
         import torch.distributed._symmetric_memory as symm
         grp = shard.group if shard.group is not None else dist.group.WORLD
@@ -135,6 +150,8 @@ def peer_buffers(shard, device, specs):
         arrs = [(ctypes.c_void_p * shard.world)(*[int(p) for p in hd.buffer_ptrs]) for hd in hdls]
         torch.cuda.synchronize()
         dist.barrier(grp)
+        if key is not None:
+            _peer_cache[key] = (bufs, arrs, hdls)
         return bufs, arrs, hdls
     except Exception as exc:                              # no symmetric memory on this system: the callers use NCCL
         warnings.warn(f"peer-memory buffers unavailable ({exc!r}); using NCCL")

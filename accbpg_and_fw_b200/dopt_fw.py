@@ -112,7 +112,7 @@ def _run_sharded(V, x0, eps, maxitrs, away, verbose, verbskip, batch, device, in
     # both per-iteration exchanges over NVLink peer memory (accbpg_fw_run_peer) when symmetric buffers can be mapped
     from .dist import peer_buffers
     peer = peer_buffers(shard, dev, [(2 * shard.world * rec_doubles, torch.float64), (2 * m, torch.float64),
-                                     (shard.world + 1, torch.int64)])
+                                     (shard.world + 1, torch.int64)], cache_key="dopt_fw")
     if peer is None:
         nat.check(lib.accbpg_fw_select_local(rt.ctx, rt.stream, n, shard.lo, int(away), x.data_ptr(), w.data_ptr(),
                                              ws.data_ptr(), m, rec.data_ptr()))
