@@ -17,9 +17,10 @@ pipeline
     Switched off automatically with verbose=True or restart=True.
 
 peer_allreduce
-    Column-sharded D-optimal objective: sum the ranks' Gram matrices through NVLink peer memory in kernels of this
-    library (accbpg_dopt_gram_allreduce, buffers from torch.distributed._symmetric_memory) instead of an NCCL all-reduce
-    after the SYRK.  Falls back to NCCL when symmetric memory cannot be set up.
+    Column-sharded runs exchange through NVLink peer memory inside this library's kernels instead of NCCL calls between
+    them (buffers from torch.distributed._symmetric_memory): the ranks' Gram matrices are summed behind the SYRK
+    (accbpg_dopt_gram_allreduce), and D_opt_FW(_away) exchanges its selection records and the chosen column
+    (accbpg_fw_run_peer).  Falls back to NCCL when symmetric memory cannot be set up.
 """
 linear_images = True
 reanchor_every = 64

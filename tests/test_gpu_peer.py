@@ -1,0 +1,132 @@
+"""GPU (one device): the NVLink peer-memory exchanges of the column-sharded path, driven through the C ABI with TWO
+ranks emulated on one GPU - each "rank" has its own context, stream, workspace and receive buffers; the pointer tables
+a real run fills from symmetric memory simply point at both sets.  Small m keeps the waiting kernels to a few CTAs so the
+other rank's kernels always find room (on separate GPUs there is no such constraint).  The multi-process version of the
+same checks is tests/multigpu_check.py (needs >= 2 GPUs)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+F64 = torch.float64
+
+
+@pytest.fixture(scope="module")
+def acc():
+    import accbpg_and_fw_b200 as a
+    return a
+
+
+class _Rank:
+    def __init__(self, nat):
+        self.nat = nat
+        h = ctypes.c_void_p()
+        nat.check(nat.lib.accbpg_ctx_create(ctypes.byref(h)))
+        self.ctx = h
+        self.stream = torch.cuda.Stream()
+
+    def close(self):
+        self.nat.check(self.nat.lib.accbpg_ctx_destroy(self.ctx))
+
+
+def _table(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+@pytest.mark.parametrize("m,widths", [(96, (700, 500)), (33, (64, 130)), (128, (1024, 1024))])
+def test_gram_allreduce_over_peer_buffers_two_emulated_ranks(acc, m, widths):
+    from accbpg_and_fw_b200 import _native as nat
+    lib = nat.lib
+    dev = torch.device("cuda")
+    world = 2
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7 + m)
+    H = [torch.randn(m, w, dtype=F64, device=dev, generator=gen) for w in widths]
+    ranks = [_Rank(nat) for _ in range(world)]
+    try:
+        recv = [torch.zeros(2 * world * m * m, dtype=F64, device=dev) for _ in range(world)]
+        flags = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+        ws = [torch.empty(lib.accbpg_dopt_workspace_bytes(m, w), dtype=torch.uint8, device=dev) for w in widths]
+        M = [torch.empty(m, m, dtype=F64, device=dev) for _ in range(world)]
+        t_recv, t_flags = _table(recv), _table(flags)
+        torch.cuda.synchronize()
+        for epoch in range(1, 6):                           # several calls: flag epochs and the parity double buffer
+            x = [torch.rand(w, dtype=F64, device=dev, generator=gen) + 0.01 * epoch for w in widths]
+            torch.cuda.synchronize()
+            for r in range(world):
+                nat.check(lib.accbpg_dopt_gram_allreduce(
+                    ranks[r].ctx, ranks[r].stream.cuda_stream, H[r].data_ptr(), m, widths[r], H[r].stride(0),
+                    x[r].data_ptr(), ws[r].data_ptr(), r, world, t_recv, t_flags, epoch, M[r].data_ptr()))
+            torch.cuda.synchronize()
+            assert torch.equal(M[0], M[1])                  # every rank sums the same numbers in the same order
+            ref = sum((H[r] * x[r]) @ H[r].T for r in range(world))
+            err = float(((M[0] - ref).abs().max() / ref.abs().max()).item())
+            assert err <= 1e-13, (epoch, err)
+            assert torch.equal(M[0], M[0].T)
+        assert [int(v) for v in flags[0].tolist()] == [5, 5] and [int(v) for v in flags[1].tolist()] == [5, 5]
+    finally:
+        torch.cuda.synchronize()
+        for rk in ranks:
+            rk.close()
+
+
+@pytest.mark.parametrize("away", [1, 0])
+def test_fw_loop_over_peer_buffers_two_emulated_ranks(acc, away):
+    """accbpg_fw_run_peer on two emulated ranks against the single-device loop on the same instance: identical decisions
+    (history entries equal on both ranks), F / slacks equal to rounding, the gathered iterate equal."""
+    from accbpg_and_fw_b200 import _native as nat
+    lib = nat.lib
+    dev = torch.device("cuda")
+    m, n, its, world = 40, 3000, 150, 2
+    np.random.seed(5)
+    V = np.random.randn(m, n)
+    x0 = np.ones(n) / n
+    fn = acc.D_opt_FW_away if away else acc.D_opt_FW
+    xs, Fs, SPs, SNs, Ts = fn(V, x0, 1e-9, its, verbose=False, batch=50)
+    bounds = [0, 1300, n]
+    rec_d = lib.accbpg_fw_record_bytes() // 8
+    ranks = [_Rank(nat) for _ in range(world)]
+    try:
+        Vd = [torch.tensor(np.ascontiguousarray(V[:, bounds[r]:bounds[r + 1]]), device=dev) for r in range(world)]
+        xd = [torch.tensor(x0[bounds[r]:bounds[r + 1]], device=dev) for r in range(world)]
+        Mtot = torch.tensor((V * x0) @ V.T, device=dev)
+        rec = [torch.zeros(2 * world * rec_d, dtype=F64, device=dev) for _ in range(world)]
+        col = [torch.zeros(2 * m, dtype=F64, device=dev) for _ in range(world)]
+        flags = [torch.zeros(world + 1, dtype=torch.int64, device=dev) for _ in range(world)]
+        t_rec, t_col, t_flags = _table(rec), _table(col), _table(flags)
+        st = []
+        for r in range(world):
+            nl = bounds[r + 1] - bounds[r]
+            d = {"ws": torch.empty(lib.accbpg_fw_workspace_bytes(m, nl), dtype=torch.uint8, device=dev),
+                 "Hinv": torch.empty(m, m, dtype=F64, device=dev), "w": torch.empty(nl, dtype=F64, device=dev),
+                 "ctrl": torch.zeros(nat.MACROS["ACCBPG_FW_CTRL_DOUBLES"], dtype=F64, device=dev), "hist": torch.zeros(4, its, dtype=F64, device=dev)}
+            nat.check(lib.accbpg_fw_setup_from_gram(ranks[r].ctx, ranks[r].stream.cuda_stream, Vd[r].data_ptr(), m, nl,
+                                                    Vd[r].stride(0), Mtot.data_ptr(), d["ws"].data_ptr(),
+                                                    d["Hinv"].data_ptr(), d["w"].data_ptr(), d["ctrl"].data_ptr()))
+            st.append(d)
+        torch.cuda.synchronize()
+        for k0 in range(0, its, 50):                        # three batches: the records carry over between calls
+            for r in range(world):
+                nl = bounds[r + 1] - bounds[r]
+                d = st[r]
+                nat.check(lib.accbpg_fw_run_peer(
+                    ranks[r].ctx, ranks[r].stream.cuda_stream, Vd[r].data_ptr(), m, nl, Vd[r].stride(0), bounds[r], away,
+                    1e-9, k0, 50, r, world, t_rec, t_col, t_flags, d["ws"].data_ptr(), d["Hinv"].data_ptr(),
+                    xd[r].data_ptr(), d["w"].data_ptr(), d["ctrl"].data_ptr(), d["hist"][0].data_ptr(),
+                    d["hist"][1].data_ptr(), d["hist"][2].data_ptr(), d["hist"][3].data_ptr()))
+            torch.cuda.synchronize()
+        h0, h1 = st[0]["hist"].cpu().numpy(), st[1]["hist"].cpu().numpy()
+        assert np.array_equal(h0[:3], h1[:3])               # replicated decisions: bit-identical histories
+        assert torch.equal(st[0]["Hinv"], st[1]["Hinv"])
+        nF = len(Fs)
+        assert nF == its
+        assert float(np.max(np.abs(h0[0, :nF] - Fs) / np.maximum(np.abs(Fs), 1e-3))) <= 1e-10
+        assert float(np.max(np.abs(h0[1, :nF] - SPs))) <= 1e-9 and float(np.max(np.abs(h0[2, :nF] - SNs))) <= 1e-9
+        xg = np.concatenate([t.cpu().numpy() for t in xd])
+        assert float(np.max(np.abs(xg - xs))) <= 1e-12
+    finally:
+        torch.cuda.synchronize()
+        for rk in ranks:
+            rk.close()
