@@ -202,10 +202,26 @@ class BurgEntropySimplex(BurgEntropy):
         sh = self.shard
         key = (n, sh.width, sh.world)
         if getattr(self, "_gg_key", None) != key:
+            from .dist import peer_buffers
             self._gg_key = key
             self._gg_loc = torch.full((sh.width,), float("inf"), dtype=torch.float64, device=rt.device)
             self._gg_all = torch.empty(sh.width * sh.world, dtype=torch.float64, device=rt.device)
+            # gathered vector in NVLink peer memory (double-buffered) + one flag word per rank; None -> NCCL all-gather
+            self._gg_peer = peer_buffers(sh, rt.device, [(2 * sh.world * sh.width, torch.float64),
+                                                         (sh.world, torch.int64)],
+                                         cache_key=("burg_gg", sh.width), reset=False)
         gg = self._gg_loc
+        if self._gg_peer is not None:
+            pb = self._gg_peer
+            info = rt.slot(rt.S_AUX1)
+            ep = pb.next_epoch()
+            nat.check(lib.accbpg_burg_simplex_push_peer(rt.ctx, rt.stream, n, sh.width, yp, gd.data_ptr(), L, sh.rank,
+                                                        sh.world, pb.tables[0], pb.tables[1], ep, gg.data_ptr()))
+            nat.check(lib.accbpg_burg_simplex_root_peer(rt.ctx, rt.stream, sh.width, float(self.eps), sh.rank, sh.world,
+                                                        pb.tables[0], pb.tables[1], ep, info))
+            nat.check(lib.accbpg_burg_simplex_finish_dev(rt.ctx, rt.stream, n, gg.data_ptr(), info + 16,
+                                                         out.data_ptr()))
+            return
         s0 = rt.S_TMP + 8
         nat.check(lib.accbpg_burg_simplex_prepare(rt.ctx, rt.stream, n, yp, gd.data_ptr(), L, gg.data_ptr(),
                                                   rt.slot(s0)))

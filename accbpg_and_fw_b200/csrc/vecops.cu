@@ -466,6 +466,67 @@ __global__ void __launch_bounds__(kThreads) burg_prepare_kernel(int64_t n, const
     }
 }
 
+// ---- exchanges over NVLink peer memory (column-sharded runs; buffers mapped into every rank) ----
+constexpr int kMaxPeerRanks = 16;
+constexpr int kPeerScalars = 16;
+struct PeerVec {
+    double* buf[kMaxPeerRanks];                    // every rank's receive buffer, double-buffered on the epoch's parity
+    unsigned long long* flags[kMaxPeerRanks];      // every rank's flag words, one per sender
+    int rank, world;
+    unsigned long long epoch;
+};
+
+// gg = (g [+ L/y]) / L for this rank's slice, padded with +inf up to `width`, stored locally (for the finishing map) and
+// into segment `rank` of every rank's gathered vector; the last CTA releases this rank's flag word on every rank
+__global__ void __launch_bounds__(kThreads) burg_prepare_push_kernel(int64_t n, int64_t width, const double* y,
+                                                                     const double* g, double L, double* gg, PeerVec pv,
+                                                                     unsigned int* counter, uint32_t* status) {
+    __shared__ bool is_last;
+    uint32_t st = 0;
+    const size_t seg = ((size_t)(pv.epoch & 1ULL) * pv.world + pv.rank) * (size_t)width;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < width; i += stride) {
+        double v = kInf;
+        if (i < n) { v = burg_shift(y, g, L, i, st) / L; gg[i] = v; }
+        for (int r = 0; r < pv.world; ++r) {
+            int q = pv.rank + r;
+            if (q >= pv.world) q -= pv.world;
+            pv.buf[q][seg + i] = v;
+        }
+    }
+    if (st) atomicOr(status, st);
+    __threadfence_system();
+    if (last_block_ticket(counter, &is_last)) {
+        __threadfence_system();
+        if ((int)threadIdx.x < pv.world) st_release_sys(pv.flags[threadIdx.x] + pv.rank, pv.epoch);
+    }
+}
+
+// stream-ordered wait: returns once every one of the `count` flag words has reached `epoch`
+__global__ void peer_wait_kernel(const unsigned long long* flags, int count, unsigned long long epoch) {
+    if ((int)threadIdx.x < count) peer_flag_wait(flags + threadIdx.x, epoch);
+}
+
+__global__ void __launch_bounds__(64) peer_sum_scalars_kernel(double* vals, int count, PeerVec pv) {
+    const int t = threadIdx.x;
+    const size_t row = (size_t)(pv.epoch & 1ULL) * pv.world;
+    if (t < pv.world) {
+        double* dst = pv.buf[t] + (row + pv.rank) * kPeerScalars;
+        for (int k = 0; k < count; ++k) dst[k] = vals[k];
+        __threadfence_system();
+        st_release_sys(pv.flags[t] + pv.rank, pv.epoch);
+    }
+    __syncthreads();
+    if (t < pv.world) peer_flag_wait(pv.flags[pv.rank] + t, pv.epoch);
+    __syncthreads();
+    if (t < count) {
+        const double* tab = pv.buf[pv.rank] + row * kPeerScalars;
+        double s = 0.0;
+        for (int r = 0; r < pv.world; ++r) s += __ldcg(tab + (size_t)r * kPeerScalars + t);
+        vals[t] = s;
+    }
+}
+
 }  // namespace accbpg
 
 using namespace accbpg;
@@ -702,6 +763,89 @@ int accbpg_burg_simplex_root(void* ctx, void* stream, int64_t n, const double* g
     ProfScope ps(P_BURG_SIMPLEX, s);
     ACCBPG_CUDA(cudaLaunchCooperativeKernel((void*)burg_simplex_kernel, dim3(grid), dim3(kBurgThreads), args, 0, s));
     ACCBPG_LAUNCHED("burg_simplex_root");
+    return ACCBPG_OK;
+}
+
+// Column-sharded prox over NVLink peer memory, in two calls.  push: the prepare kernel stores this rank's (padded) slice
+// of gg straight into every rank's gathered vector and releases a flag word there.  root: a one-warp kernel waits for
+// the `world` flags (so the cooperative root-find never spins on a peer while it holds the whole GPU), then the
+// root-find runs on the gathered vector.
+static int peer_vec_fill(PeerVec& pv, int rank, int world, void* const* bufs, void* const* flags, uint64_t epoch,
+                         const char* what) {
+    if (!bufs || !flags) return arg_err(what);
+    if (world < 1 || world > kMaxPeerRanks || rank < 0 || rank >= world || epoch < 1) return arg_err(what);
+    for (int r = 0; r < world; ++r) {
+        pv.buf[r] = (double*)bufs[r]; pv.flags[r] = (unsigned long long*)flags[r];
+        if (!pv.buf[r] || !pv.flags[r]) return arg_err(what);
+    }
+    pv.rank = rank; pv.world = world; pv.epoch = epoch;
+    return ACCBPG_OK;
+}
+int accbpg_burg_simplex_push_peer(void* ctx, void* stream, int64_t n_local, int64_t width, const double* y,
+                                  const double* g, double L, int rank, int world, void* const* peer_gg,
+                                  void* const* peer_flags, uint64_t epoch, double* d_gg_local) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c) return arg_err("ctx is NULL");
+    if (!g || !d_gg_local) return arg_err("burg_simplex_push_peer: NULL pointer");
+    if (!(L > 0.0)) return arg_err("L must be positive");
+    if (n_local < 0 || width < n_local || width < 1) return arg_err("burg_simplex_push_peer: width");
+    PeerVec pv;
+    int rc = peer_vec_fill(pv, rank, world, peer_gg, peer_flags, epoch, "burg_simplex_push_peer: peer tables / rank / epoch");
+    if (rc) return rc;
+    int pgrid = grid_for(c, width, kThreads, 4, 4);
+    burg_prepare_push_kernel<<<pgrid, kThreads, 0, s>>>(n_local, width, y, g, L, d_gg_local, pv, c->d_counter + 18,
+                                                        c->d_status);
+    ACCBPG_LAUNCHED("burg_prepare_push_kernel");
+    return ACCBPG_OK;
+}
+int accbpg_burg_simplex_root_peer(void* ctx, void* stream, int64_t width, double eps, int rank, int world,
+                                  void* const* peer_gg, void* const* peer_flags, uint64_t epoch, double* d_info) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c) return arg_err("ctx is NULL");
+    if (!d_info || width < 1) return arg_err("burg_simplex_root_peer: NULL pointer / width");
+    PeerVec pv;
+    int rc = peer_vec_fill(pv, rank, world, peer_gg, peer_flags, epoch, "burg_simplex_root_peer: peer tables / rank / epoch");
+    if (rc) return rc;
+    peer_wait_kernel<<<1, 32, 0, s>>>(pv.flags[rank], world, epoch);
+    ACCBPG_LAUNCHED("peer_wait_kernel");
+    int64_t n = width * world;
+    int64_t want = (n + kBurgThreads - 1) / kBurgThreads;
+    int grid = (int)(want < c->coop_blocks_burg ? want : c->coop_blocks_burg);
+    double* partials = c->d_partials;
+    uint32_t* status = c->d_status;
+    const double* yy = nullptr;
+    const double* gg0 = nullptr;
+    double* out = nullptr;
+    double one = 1.0;
+    const double* gg = pv.buf[rank] + (size_t)(epoch & 1ULL) * (size_t)n;
+    void* args[] = {&n, &yy, &gg0, &one, &eps, &out, &d_info, &partials, &status, &gg};
+    ProfScope ps(P_BURG_SIMPLEX, s);
+    ACCBPG_CUDA(cudaLaunchCooperativeKernel((void*)burg_simplex_kernel, dim3(grid), dim3(kBurgThreads), args, 0, s));
+    ACCBPG_LAUNCHED("burg_simplex_root");
+    return ACCBPG_OK;
+}
+
+// Sum `count` (<= 16) per-rank partial scalars over the ranks through peer memory, in rank order, in place: one CTA
+// stores its values into slot `rank` of every rank's table, releases its flag word there, waits for the `world` flags
+// of its own table and adds the rows up (every rank forms the same sums).
+int accbpg_peer_sum_scalars(void* ctx, void* stream, double* d_vals, int count, int rank, int world,
+                            void* const* peer_tab, void* const* peer_flags, uint64_t epoch) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c) return arg_err("ctx is NULL");
+    if (!d_vals || !peer_tab || !peer_flags) return arg_err("peer_sum_scalars: NULL pointer");
+    if (count < 1 || count > kPeerScalars || world < 1 || world > kMaxPeerRanks || rank < 0 || rank >= world || epoch < 1)
+        return arg_err("peer_sum_scalars: count / rank / world / epoch");
+    PeerVec pv;
+    for (int r = 0; r < world; ++r) {
+        pv.buf[r] = (double*)peer_tab[r]; pv.flags[r] = (unsigned long long*)peer_flags[r];
+        if (!pv.buf[r] || !pv.flags[r]) return arg_err("peer_sum_scalars: NULL peer pointer");
+    }
+    pv.rank = rank; pv.world = world; pv.epoch = epoch;
+    peer_sum_scalars_kernel<<<1, 64, 0, s>>>(d_vals, count, pv);
+    ACCBPG_LAUNCHED("peer_sum_scalars_kernel");
     return ACCBPG_OK;
 }
 int accbpg_burg_simplex_finish_dev(void* ctx, void* stream, int64_t n, const double* gg, const double* d_c, double* out) {

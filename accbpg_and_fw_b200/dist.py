@@ -114,17 +114,30 @@ class ColumnShard:
 _peer_cache = {}
 
 
-def peer_buffers(shard, device, specs, cache_key=None):
+class PeerBuffers:
+    """Symmetric buffers of one exchange: `tensors` (this rank's), `tables` (per buffer, a ctypes array with every
+    rank's device address of it) and a call counter for the kernels' flag epochs."""
+
+    def __init__(self, tensors, tables, handles):
+        self.tensors, self.tables, self.handles = tensors, tables, handles
+        self.epoch = 0
+
+    def next_epoch(self):
+        self.epoch += 1
+        return self.epoch
+
+
+def peer_buffers(shard, device, specs, cache_key=None, reset=True):
     """Symmetric (NVLink peer-mapped) buffers for the kernels that exchange data without NCCL.  specs: list of
-    (numel, dtype).  Returns (tensors, pointer arrays) - pointer array i holds every rank's address of buffer i, as a
-    ctypes array of `world` void pointers - or None when symmetric memory is not available (not NCCL, one rank, switched
+    (numel, dtype).  Returns a PeerBuffers, or None when symmetric memory is not available (not NCCL, one rank, switched
     off by config.peer_allreduce, or torch cannot map the buffers).  Collective: every rank of the group must call it.
-    The buffers come back zero-filled and a barrier has passed, so flag words are zero on every rank.
-    cache_key: reuse the buffers of an earlier call with the same key (mapping symmetric memory costs ~0.1 s); the caller
-    guarantees that no peer still stores into them (a barrier after its last kernel)."""
+    New buffers come back zero-filled and a barrier has passed, so flag words are zero on every rank.
+    cache_key: reuse the buffers of an earlier call with the same key (mapping symmetric memory costs ~0.1 s).  With
+    reset=True a reused set is zeroed again behind a barrier and its epoch restarts (the caller guarantees that no peer
+    still stores into it: a barrier after its last kernel); with reset=False it is handed back as it is and the epochs
+    simply continue (exchanges whose every store is awaited by the receiving kernel of the same call)."""
     import ctypes
     import warnings
-    import torch.distributed as dist
     from . import config
     if shard is None or shard.world < 2 or shard.world > 16 or not config.peer_allreduce or not dist.is_initialized():
         return None
@@ -135,10 +148,12 @@ def peer_buffers(shard, device, specs, cache_key=None):
         key = (cache_key, id(shard.group), shard.world, str(device), tuple((int(a), str(b)) for a, b in specs))
         hit = _peer_cache.get(key)
         if hit is not None:
-            for b in hit[0]:
-                b.zero_()
-            torch.cuda.synchronize()
-            dist.barrier(shard.group)
+            if reset:
+                for b in hit.tensors:
+                    b.zero_()
+                hit.epoch = 0
+                torch.cuda.synchronize()
+                dist.barrier(shard.group)
             return hit
     try:
         import torch.distributed._symmetric_memory as symm
@@ -150,9 +165,10 @@ def peer_buffers(shard, device, specs, cache_key=None):
         arrs = [(ctypes.c_void_p * shard.world)(*[int(p) for p in hd.buffer_ptrs]) for hd in hdls]
         torch.cuda.synchronize()
         dist.barrier(grp)
+        pb = PeerBuffers(bufs, arrs, hdls)
         if key is not None:
-            _peer_cache[key] = (bufs, arrs, hdls)
-        return bufs, arrs, hdls
+            _peer_cache[key] = pb
+        return pb
     except Exception as exc:                              # no symmetric memory on this system: the callers use NCCL
         warnings.warn(f"peer-memory buffers unavailable ({exc!r}); using NCCL")
         return None

@@ -127,7 +127,7 @@ def _run_sharded(V, x0, eps, maxitrs, away, verbose, verbskip, batch, device, in
         cnt = 1 if index_log is not None else min(batch, maxitrs - k)
         if peer is not None:
             nat.check(lib.accbpg_fw_run_peer(rt.ctx, rt.stream, Vd.data_ptr(), m, n, st, shard.lo, int(away), float(eps),
-                                             k, cnt, shard.rank, shard.world, peer[1][0], peer[1][1], peer[1][2],
+                                             k, cnt, shard.rank, shard.world, peer.tables[0], peer.tables[1], peer.tables[2],
                                              ws.data_ptr(), Hinv.data_ptr(), x.data_ptr(), w.data_ptr(), ctrl.data_ptr(),
                                              hist[0].data_ptr(), hist[1].data_ptr(), hist[2].data_ptr(),
                                              hist[3].data_ptr()))

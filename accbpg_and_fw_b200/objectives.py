@@ -68,9 +68,8 @@ class DOptimalObj(RSmoothFunction):
         words, mapped into every peer (collective call: every rank constructs the objective)."""
         from .dist import peer_buffers
         mm = self.m * self.m
-        got = peer_buffers(self.shard, self.rt.device, [(2 * self.shard.world * mm, torch.float64),
-                                                        (self.shard.world, torch.int64)])
-        self._peer = None if got is None else {"bufs": got[0], "arrs": got[1], "hdls": got[2], "epoch": 0}
+        self._peer = peer_buffers(self.shard, self.rt.device, [(2 * self.shard.world * mm, torch.float64),
+                                                               (self.shard.world, torch.int64)])
 
     def _gram_sharded(self, xd, M):
         """M <- sum over ranks of H_r diag(x_r) H_r^T."""
@@ -78,10 +77,9 @@ class DOptimalObj(RSmoothFunction):
         H = self._Hd
         if self._peer is not None:
             pr = self._peer
-            pr["epoch"] += 1
             nat.check(lib.accbpg_dopt_gram_allreduce(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
                                                      xd.data_ptr(), self._ws.data_ptr(), self.shard.rank, self.shard.world,
-                                                     pr["arrs"][0], pr["arrs"][1], pr["epoch"], M.data_ptr()))
+                                                     pr.tables[0], pr.tables[1], pr.next_epoch(), M.data_ptr()))
             return
         nat.check(lib.accbpg_dopt_gram(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0),
                                        xd.data_ptr(), self._ws.data_ptr(), M.data_ptr()))

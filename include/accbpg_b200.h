@@ -142,6 +142,24 @@ int accbpg_burg_simplex_finish(void* ctx, void* stream, int64_t n, const double*
 int accbpg_burg_simplex_root(void* ctx, void* stream, int64_t n, const double* d_gg, double eps, double* d_info);
 int accbpg_burg_simplex_finish_dev(void* ctx, void* stream, int64_t n, const double* d_gg, const double* d_c,
                                    double* d_out_vec);
+/* The column-sharded prox with the gather over NVLink peer memory instead of an NCCL all-gather, in two calls.
+ * push: the preparing kernel stores this rank's slice of gg = (g [+ L/y]) / L (d_y may be NULL), padded with +inf up to
+ * `width`, into segment `rank` of EVERY rank's gathered vector (and into d_gg_local for
+ * accbpg_burg_simplex_finish_dev) and releases a flag word on every rank.  root: a one-warp kernel waits for the
+ * `world` flags, then the recurrence of functions.py:341-356 runs on the gathered world*width vector exactly as in
+ * accbpg_burg_simplex_root (d_info likewise).  peer_gg / peer_flags: host arrays of `world` device pointers to every
+ * rank's symmetric buffers (2*world*width doubles, double-buffered on the epoch's parity; world uint64, zeroed once);
+ * epoch 1, 2, 3, ... per push/root pair on these buffers, the same on every rank. */
+int accbpg_burg_simplex_push_peer(void* ctx, void* stream, int64_t n_local, int64_t width, const double* d_y,
+                                  const double* d_g, double L, int rank, int world, void* const* peer_gg,
+                                  void* const* peer_flags, uint64_t epoch, double* d_gg_local);
+int accbpg_burg_simplex_root_peer(void* ctx, void* stream, int64_t width, double eps, int rank, int world,
+                                  void* const* peer_gg, void* const* peer_flags, uint64_t epoch, double* d_info);
+/* Sum `count` (<= 16) per-rank partial scalars at d_vals over the ranks through peer memory, in rank order, in place
+ * (the batched divergence / dot-product partials of a driver iteration, algorithms.py:53,153-154,...): one small kernel
+ * instead of an NCCL all-reduce.  peer_tab: every rank's 2*world*16 doubles; peer_flags: world uint64, zeroed once. */
+int accbpg_peer_sum_scalars(void* ctx, void* stream, double* d_vals, int count, int rank, int world,
+                            void* const* peer_tab, void* const* peer_flags, uint64_t epoch);
 
 /* ---- Shannon entropy kernels  h(x) = sum x log x   (accbpg/functions.py:398-490) */
 int accbpg_shannon_value(void* ctx, void* stream, int64_t n, const double* d_x, double delta, double* d_out);   /* :405-408 */

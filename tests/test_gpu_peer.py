@@ -130,3 +130,91 @@ def test_fw_loop_over_peer_buffers_two_emulated_ranks(acc, away):
         torch.cuda.synchronize()
         for rk in ranks:
             rk.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_scalar_sums_over_peer_buffers_emulated_ranks(acc, world):
+    from accbpg_and_fw_b200 import _native as nat
+    lib = nat.lib
+    dev = torch.device("cuda")
+    count = 4
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11)
+    ranks = [_Rank(nat) for _ in range(world)]
+    try:
+        tab = [torch.zeros(2 * world * 16, dtype=F64, device=dev) for _ in range(world)]
+        flags = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+        t_tab, t_flags = _table(tab), _table(flags)
+        for epoch in range(1, 8):
+            parts = [torch.randn(count, dtype=F64, device=dev, generator=gen) * 10.0 ** (r % 3) for r in range(world)]
+            vals = [p.clone() for p in parts]
+            torch.cuda.synchronize()
+            for r in range(world):
+                nat.check(lib.accbpg_peer_sum_scalars(ranks[r].ctx, ranks[r].stream.cuda_stream, vals[r].data_ptr(), count,
+                                                      r, world, t_tab, t_flags, epoch))
+            torch.cuda.synchronize()
+            ref = np.zeros(count)
+            for r in range(world):                           # rank order, as the kernel adds them
+                ref = ref + parts[r].cpu().numpy()
+            for r in range(world):
+                assert np.array_equal(vals[r].cpu().numpy(), ref), (epoch, r)
+    finally:
+        torch.cuda.synchronize()
+        for rk in ranks:
+            rk.close()
+
+
+@pytest.mark.parametrize("world,n", [(2, 1000), (3, 1499), (8, 4001)])
+def test_burg_simplex_prox_gather_over_peer_buffers_emulated_ranks(acc, world, n):
+    """prepare + push, root-find on the gathered vector, finishing map: the multiplier is bit-identical on every rank
+    and the assembled prox equals the oracle's BurgEntropySimplex.div_prox_map on the whole vector."""
+    from accbpg_and_fw_b200 import _native as nat
+    from oracle import accbpg_oracle as orc
+    lib = nat.lib
+    dev = torch.device("cuda")
+    rng = np.random.RandomState(3 + world)
+    sh = acc.ColumnShard(n, rank=0, world=world)
+    width, off = sh.width, sh.offsets
+    ho = orc.make_burg("simplex")
+    ranks = [_Rank(nat) for _ in range(world)]
+    try:
+        ggbuf = [torch.zeros(2 * world * width, dtype=F64, device=dev) for _ in range(world)]
+        flags = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+        t_gg, t_flags = _table(ggbuf), _table(flags)
+        for epoch in range(1, 5):
+            y = rng.rand(n) + 0.05
+            y /= y.sum()
+            g = rng.randn(n)
+            L = 0.5 + epoch
+            yd = [torch.tensor(y[off[r]:off[r + 1]], device=dev) for r in range(world)]
+            gd = [torch.tensor(g[off[r]:off[r + 1]], device=dev) for r in range(world)]
+            loc = [torch.full((width,), float("inf"), dtype=F64, device=dev) for _ in range(world)]
+            info = [torch.zeros(8, dtype=F64, device=dev) for _ in range(world)]
+            out = [torch.empty(off[r + 1] - off[r], dtype=F64, device=dev) for r in range(world)]
+            torch.cuda.synchronize()
+            # all pushes first: cooperative launches of different streams are serialised against each other on ONE
+            # device, so a root-find queued behind a waiting kernel would hold back the other "ranks"' pushes here
+            # (on separate GPUs the two calls simply follow each other)
+            for r in range(world):
+                nl = off[r + 1] - off[r]
+                nat.check(lib.accbpg_burg_simplex_push_peer(ranks[r].ctx, ranks[r].stream.cuda_stream, nl, width,
+                                                            yd[r].data_ptr(), gd[r].data_ptr(), L, r, world, t_gg,
+                                                            t_flags, epoch, loc[r].data_ptr()))
+            for r in range(world):
+                nl = off[r + 1] - off[r]
+                st = ranks[r].stream.cuda_stream
+                nat.check(lib.accbpg_burg_simplex_root_peer(ranks[r].ctx, st, width, 1e-8, r, world, t_gg, t_flags, epoch,
+                                                            info[r].data_ptr()))
+                nat.check(lib.accbpg_burg_simplex_finish_dev(ranks[r].ctx, st, nl, loc[r].data_ptr(),
+                                                             info[r].data_ptr() + 16, out[r].data_ptr()))
+            torch.cuda.synchronize()
+            cs = [float(i[2].item()) for i in info]
+            assert len(set(cs)) == 1, cs
+            x = np.concatenate([o.cpu().numpy() for o in out])
+            xo = ho.div_prox_map(y, g, L)
+            assert float(np.max(np.abs(x - xo) / np.abs(xo))) <= 1e-10
+            assert abs(x.sum() - 1.0) <= 2e-8
+    finally:
+        torch.cuda.synchronize()
+        for rk in ranks:
+            rk.close()
