@@ -165,12 +165,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// bounded: a peer that never arrives (protocol error, dead rank) traps this kernel after about a minute instead of hanging
+// bounded by wall time: a peer that has not arrived after two minutes (protocol error, dead rank) traps this kernel
+// instead of hanging the GPU; ordinary host-side skew between ranks (seconds) is waited out
 __device__ __forceinline__ void peer_flag_wait(const unsigned long long* f, unsigned long long epoch) {
-    int spin = 0;
+    unsigned long long t0 = 0;
+    unsigned int spin = 0;
     while (ld_acquire_sys(f) < epoch) {
-        if (++spin > (1 << 26)) __trap();
-        __nanosleep(20);
+        __nanosleep(40);
+        if ((++spin & 0xffffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 120000000000ULL) __trap();
+        }
     }
 }
 #endif  // __CUDACC__

@@ -206,7 +206,7 @@ int accbpg_dopt_gram(void* ctx, void* stream, const double* d_H, int m, int64_t 
  * M.  peer_recv / peer_flags: host arrays of `world` device pointers to every rank's symmetric buffers
  * (2*world*m*m doubles - double-buffered on epoch parity - and `world` uint64 flag words, zero-initialised once; e.g.
  * torch.distributed._symmetric_memory buffer_ptrs); epoch: 1, 2, 3, ..., one per call on these buffers, the same on
- * every rank.  world <= 16.  A rank that waits longer than ~1 min for a peer traps. */
+ * every rank.  world <= 16.  A rank that waits longer than two minutes for a peer traps. */
 int accbpg_dopt_gram_allreduce(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
                                const double* d_x, void* d_ws, int rank, int world, void* const* peer_recv,
                                void* const* peer_flags, uint64_t epoch, double* d_M);
