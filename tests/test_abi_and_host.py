@@ -128,6 +128,11 @@ pad = torch.full((sh.width,), float("inf"), dtype=torch.float64); pad[: loc.nume
 allv = torch.empty(sh.width * world, dtype=torch.float64); sh.all_gather_equal(allv, pad)
 got = torch.cat([allv[r * sh.width: r * sh.width + (sh.offsets[r + 1] - sh.offsets[r])] for r in range(world)])
 assert torch.equal(got, full) and torch.isinf(allv).sum().item() == sh.width * world - 11
+# the NVLink peer-memory exchanges need NCCL: on any other backend the buffer factory declines and callers use the
+# collectives above
+from accbpg_and_fw_b200.dist import peer_buffers
+assert peer_buffers(sh, torch.device("cpu"), [(16, torch.float64), (2, torch.int64)]) is None
+assert peer_buffers(None, torch.device("cpu"), [(16, torch.float64)]) is None
 dist.destroy_process_group()
 print("ok", rank)
 '''
