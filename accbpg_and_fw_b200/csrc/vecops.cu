@@ -527,6 +527,64 @@ __global__ void __launch_bounds__(64) peer_sum_scalars_kernel(double* vals, int 
     }
 }
 
+// lowest (value, global index) pair over the ranks: the same single-CTA exchange with a different combine.  Ties in the
+// value go to the lowest index, so the selected vertex does not depend on the number of ranks (functions_lmo.py:153-158).
+__global__ void __launch_bounds__(64) peer_argmin_pair_kernel(double* pair, PeerVec pv) {
+    const int t = threadIdx.x;
+    const size_t row = (size_t)(pv.epoch & 1ULL) * pv.world;
+    if (t < pv.world) {
+        double* dst = pv.buf[t] + (row + pv.rank) * kPeerScalars;
+        dst[0] = pair[0]; dst[1] = pair[1];
+        __threadfence_system();
+        st_release_sys(pv.flags[t] + pv.rank, pv.epoch);
+    }
+    __syncthreads();
+    if (t < pv.world) peer_flag_wait(pv.flags[pv.rank] + t, pv.epoch);
+    __syncthreads();
+    if (t == 0) {
+        const double* tab = pv.buf[pv.rank] + row * kPeerScalars;
+        double bv = __ldcg(tab), bi = __ldcg(tab + 1);
+        for (int r = 1; r < pv.world; ++r) {
+            const double v = __ldcg(tab + (size_t)r * kPeerScalars), i = __ldcg(tab + (size_t)r * kPeerScalars + 1);
+            if (v < bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+        pair[0] = bv; pair[1] = bi;
+    }
+}
+
+// all-reduce(sum) of an n-vector over peer memory: push this rank's vector into slot `rank` of every rank's buffer ...
+__global__ void __launch_bounds__(kThreads) peer_vec_push_kernel(const double* x, int64_t n, int64_t cap, PeerVec pv,
+                                                                 unsigned int* counter) {
+    __shared__ bool is_last;
+    const size_t seg = ((size_t)(pv.epoch & 1ULL) * pv.world + pv.rank) * (size_t)cap;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = x[i];
+        for (int r = 0; r < pv.world; ++r) {
+            int q = pv.rank + r;
+            if (q >= pv.world) q -= pv.world;
+            pv.buf[q][seg + i] = v;
+        }
+    }
+    __threadfence_system();
+    if (last_block_ticket(counter, &is_last)) {
+        __threadfence_system();
+        if ((int)threadIdx.x < pv.world) st_release_sys(pv.flags[threadIdx.x] + pv.rank, pv.epoch);
+    }
+}
+// ... and, once all `world` vectors have arrived, add them up in rank order (every rank forms the same sums)
+__global__ void __launch_bounds__(kThreads) peer_vec_sum_kernel(double* x, int64_t n, int64_t cap, PeerVec pv) {
+    if ((int)threadIdx.x < pv.world) peer_flag_wait(pv.flags[pv.rank] + threadIdx.x, pv.epoch);
+    __syncthreads();
+    const double* src = pv.buf[pv.rank] + (size_t)(pv.epoch & 1ULL) * pv.world * (size_t)cap;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double s = 0.0;
+        for (int r = 0; r < pv.world; ++r) s += __ldcg(src + (size_t)r * cap + i);
+        x[i] = s;
+    }
+}
+
 }  // namespace accbpg
 
 using namespace accbpg;
@@ -846,6 +904,40 @@ int accbpg_peer_sum_scalars(void* ctx, void* stream, double* d_vals, int count, 
     pv.rank = rank; pv.world = world; pv.epoch = epoch;
     peer_sum_scalars_kernel<<<1, 64, 0, s>>>(d_vals, count, pv);
     ACCBPG_LAUNCHED("peer_sum_scalars_kernel");
+    return ACCBPG_OK;
+}
+
+// lowest (value, global index) over the ranks, in place on the two doubles at d_pair (tables as accbpg_peer_sum_scalars)
+int accbpg_peer_argmin_pair(void* ctx, void* stream, double* d_pair, int rank, int world, void* const* peer_tab,
+                            void* const* peer_flags, uint64_t epoch) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c) return arg_err("ctx is NULL");
+    if (!d_pair) return arg_err("peer_argmin_pair: NULL pointer");
+    PeerVec pv;
+    int rc = peer_vec_fill(pv, rank, world, peer_tab, peer_flags, epoch, "peer_argmin_pair: peer tables / rank / epoch");
+    if (rc) return rc;
+    peer_argmin_pair_kernel<<<1, 64, 0, s>>>(d_pair, pv);
+    ACCBPG_LAUNCHED("peer_argmin_pair_kernel");
+    return ACCBPG_OK;
+}
+
+// all-reduce(sum), in place, of the n doubles at d_x over peer memory; every rank's buffer holds 2*world slots of `cap`
+// doubles (cap >= n)
+int accbpg_peer_sum_vector(void* ctx, void* stream, double* d_x, int64_t n, int64_t cap, int rank, int world,
+                           void* const* peer_buf, void* const* peer_flags, uint64_t epoch) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c) return arg_err("ctx is NULL");
+    if (!d_x || n < 1 || cap < n) return arg_err("peer_sum_vector: NULL pointer / n / cap");
+    PeerVec pv;
+    int rc = peer_vec_fill(pv, rank, world, peer_buf, peer_flags, epoch, "peer_sum_vector: peer tables / rank / epoch");
+    if (rc) return rc;
+    int grid = grid_for(c, n, kThreads, 4, 4);
+    peer_vec_push_kernel<<<grid, kThreads, 0, s>>>(d_x, n, cap, pv, c->d_counter + 19);
+    ACCBPG_LAUNCHED("peer_vec_push_kernel");
+    peer_vec_sum_kernel<<<grid, kThreads, 0, s>>>(d_x, n, cap, pv);
+    ACCBPG_LAUNCHED("peer_vec_sum_kernel");
     return ACCBPG_OK;
 }
 int accbpg_burg_simplex_finish_dev(void* ctx, void* stream, int64_t n, const double* gg, const double* d_c, double* out) {

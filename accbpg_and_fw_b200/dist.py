@@ -75,9 +75,36 @@ class ColumnShard:
 
     # ---- collectives ----------------------------------------------------------------------
     def sum_(self, t):
-        if self.world > 1:
+        """In-place sum over the ranks.  float64 CUDA tensors up to 2**21 elements go through NVLink peer memory
+        (accbpg_peer_sum_scalars / accbpg_peer_sum_vector: rank-ordered sums, identical bits on every rank); anything
+        else, and every case where symmetric memory is unavailable, is an NCCL / gloo all-reduce."""
+        if self.world > 1 and not self._peer_sum(t):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
+
+    def _peer_sum(self, t):
+        n = t.numel()
+        if not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous() or n == 0 or n > (1 << 21):
+            return False
+        from . import _native as nat
+        from .runtime import Runtime
+        rt = Runtime.get(t.device)
+        if n <= 16:
+            pb = peer_buffers(self, t.device, [(2 * self.world * 16, torch.float64), (self.world, torch.int64)],
+                              cache_key="sum16", reset=False)
+            if pb is None:
+                return False
+            nat.check(nat.lib.accbpg_peer_sum_scalars(rt.ctx, rt.stream, t.data_ptr(), n, self.rank, self.world,
+                                                      pb.tables[0], pb.tables[1], pb.next_epoch()))
+            return True
+        cap = 1 << (n - 1).bit_length()
+        pb = peer_buffers(self, t.device, [(2 * self.world * cap, torch.float64), (self.world, torch.int64)],
+                          cache_key=("sumvec", cap), reset=False)
+        if pb is None:
+            return False
+        nat.check(nat.lib.accbpg_peer_sum_vector(rt.ctx, rt.stream, t.data_ptr(), n, cap, self.rank, self.world,
+                                                 pb.tables[0], pb.tables[1], pb.next_epoch()))
+        return True
 
     def min_(self, t):
         if self.world > 1:
@@ -94,6 +121,16 @@ class ColumnShard:
         among ranks attaining it, the lowest global index -- independent of the GPU count."""
         if self.world == 1:
             return pair
+        if pair.is_cuda and pair.dtype == torch.float64 and pair.is_contiguous() and pair.numel() == 2:
+            pb = peer_buffers(self, pair.device, [(2 * self.world * 16, torch.float64), (self.world, torch.int64)],
+                              cache_key="argmin", reset=False)
+            if pb is not None:
+                from . import _native as nat
+                from .runtime import Runtime
+                rt = Runtime.get(pair.device)
+                nat.check(nat.lib.accbpg_peer_argmin_pair(rt.ctx, rt.stream, pair.data_ptr(), self.rank, self.world,
+                                                          pb.tables[0], pb.tables[1], pb.next_epoch()))
+                return pair
         bufs = [torch.empty_like(pair) for _ in range(self.world)]
         dist.all_gather(bufs, pair, group=self.group)
         allp = torch.stack(bufs)                          # [world, 2]
@@ -147,6 +184,8 @@ def peer_buffers(shard, device, specs, cache_key=None, reset=True):
     if cache_key is not None:
         key = (cache_key, id(shard.group), shard.world, str(device), tuple((int(a), str(b)) for a, b in specs))
         hit = _peer_cache.get(key)
+        if hit is False:                                  # mapping failed before: do not try (and warn) on every call
+            return None
         if hit is not None:
             if reset:
                 for b in hit.tensors:
@@ -171,4 +210,6 @@ def peer_buffers(shard, device, specs, cache_key=None, reset=True):
         return pb
     except Exception as exc:                              # no symmetric memory on this system: the callers use NCCL
         warnings.warn(f"peer-memory buffers unavailable ({exc!r}); using NCCL")
+        if key is not None:
+            _peer_cache[key] = False
         return None

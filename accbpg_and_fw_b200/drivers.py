@@ -50,7 +50,6 @@ class _Loop:
         # ranks by ONE all-reduce at fetch time instead of one per scalar
         self.sharded = self.shard is not None and self.shard.world > 1
         h._defer_reduce = self.sharded
-        self._peer_scal = None
 
     # ---- linear images (all no-ops returning None when the switch is off) -----------------------------------
     def img(self, x):
@@ -142,18 +141,6 @@ class _Loop:
         if self.sharded:
             rt = self.rt
             # S_DXY, S_DZZ, S_DOT, S_PSI are per-rank partials: one small kernel over NVLink peer memory, else NCCL
-            if self._peer_scal is None:
-                from .dist import peer_buffers
-                got = peer_buffers(self.shard, rt.device, [(2 * self.shard.world * 16, torch.float64),
-                                                           (self.shard.world, torch.int64)],
-                                   cache_key="driver_scalars", reset=False)
-                self._peer_scal = got if got is not None else False
-            pb = self._peer_scal
-            if pb:
-                nat.check(lib.accbpg_peer_sum_scalars(rt.ctx, rt.stream, rt.slot(rt.S_DXY), rt.S_PSI + 1 - rt.S_DXY,
-                                                      self.shard.rank, self.shard.world, pb.tables[0], pb.tables[1],
-                                                      pb.next_epoch()))
-                return
             self.shard.sum_(rt.scal[rt.S_DXY:rt.S_PSI + 1])
 
     def fetch(self):

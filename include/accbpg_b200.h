@@ -160,6 +160,17 @@ int accbpg_burg_simplex_root_peer(void* ctx, void* stream, int64_t width, double
  * instead of an NCCL all-reduce.  peer_tab: every rank's 2*world*16 doubles; peer_flags: world uint64, zeroed once. */
 int accbpg_peer_sum_scalars(void* ctx, void* stream, double* d_vals, int count, int rank, int world,
                             void* const* peer_tab, void* const* peer_flags, uint64_t epoch);
+/* The column-sharded LMO's reduction (functions_lmo.py:153-158 with the columns split over ranks): the lowest
+ * (value, global index) pair over the ranks, ties to the lowest index, in place on the two doubles at d_pair.  Tables
+ * as accbpg_peer_sum_scalars. */
+int accbpg_peer_argmin_pair(void* ctx, void* stream, double* d_pair, int rank, int world, void* const* peer_tab,
+                            void* const* peer_flags, uint64_t epoch);
+/* In-place all-reduce(sum) of n doubles over peer memory (the m-vector A x of PoissonRegression / KLdivRegression,
+ * functions.py:102-158, and other replicated sums): every rank stores its vector into slot `rank` of every rank's
+ * buffer, releases a flag word there, waits for the `world` flags and adds the slots in rank order.  peer_buf: every
+ * rank's 2*world*cap doubles (cap >= n); peer_flags: world uint64, zeroed once. */
+int accbpg_peer_sum_vector(void* ctx, void* stream, double* d_x, int64_t n, int64_t cap, int rank, int world,
+                           void* const* peer_buf, void* const* peer_flags, uint64_t epoch);
 
 /* ---- Shannon entropy kernels  h(x) = sum x log x   (accbpg/functions.py:398-490) */
 int accbpg_shannon_value(void* ctx, void* stream, int64_t n, const double* d_x, double delta, double* d_out);   /* :405-408 */

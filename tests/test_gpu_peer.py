@@ -218,3 +218,63 @@ def test_burg_simplex_prox_gather_over_peer_buffers_emulated_ranks(acc, world, n
         torch.cuda.synchronize()
         for rk in ranks:
             rk.close()
+
+
+@pytest.mark.parametrize("world,n", [(2, 17), (4, 1000), (8, 100000)])
+def test_vector_sum_over_peer_buffers_emulated_ranks(acc, world, n):
+    from accbpg_and_fw_b200 import _native as nat
+    lib = nat.lib
+    dev = torch.device("cuda")
+    cap = 1 << (n - 1).bit_length()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(13)
+    ranks = [_Rank(nat) for _ in range(world)]
+    try:
+        buf = [torch.zeros(2 * world * cap, dtype=F64, device=dev) for _ in range(world)]
+        flags = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+        t_buf, t_flags = _table(buf), _table(flags)
+        for epoch in range(1, 5):
+            parts = [torch.randn(n, dtype=F64, device=dev, generator=gen) for _ in range(world)]
+            vals = [p.clone() for p in parts]
+            torch.cuda.synchronize()
+            for r in range(world):
+                nat.check(lib.accbpg_peer_sum_vector(ranks[r].ctx, ranks[r].stream.cuda_stream, vals[r].data_ptr(), n, cap,
+                                                     r, world, t_buf, t_flags, epoch))
+            torch.cuda.synchronize()
+            ref = torch.zeros(n, dtype=F64, device=dev)
+            for r in range(world):                           # rank order, as the kernel adds them
+                ref = ref + parts[r]
+            for r in range(world):
+                assert torch.equal(vals[r], ref), (epoch, r)
+    finally:
+        torch.cuda.synchronize()
+        for rk in ranks:
+            rk.close()
+
+
+def test_argmin_pair_over_peer_buffers_lowest_index_wins(acc):
+    from accbpg_and_fw_b200 import _native as nat
+    lib = nat.lib
+    dev = torch.device("cuda")
+    world = 4
+    ranks = [_Rank(nat) for _ in range(world)]
+    try:
+        tab = [torch.zeros(2 * world * 16, dtype=F64, device=dev) for _ in range(world)]
+        flags = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+        t_tab, t_flags = _table(tab), _table(flags)
+        cases = [([(0.5, 3.0), (0.25, 40.0), (0.25, 17.0), (0.9, 2.0)], (0.25, 17.0)),      # tie in the value
+                 ([(-1.0, 9.0), (2.0, 1.0), (3.0, 0.0), (-1.0, 8.0)], (-1.0, 8.0)),
+                 ([(7.0, 5.0), (7.0, 6.0), (7.0, 4.0), (7.0, 11.0)], (7.0, 4.0))]
+        for epoch, (pairs, want) in enumerate(cases, start=1):
+            vals = [torch.tensor(p, dtype=F64, device=dev) for p in pairs]
+            torch.cuda.synchronize()
+            for r in range(world):
+                nat.check(lib.accbpg_peer_argmin_pair(ranks[r].ctx, ranks[r].stream.cuda_stream, vals[r].data_ptr(), r,
+                                                      world, t_tab, t_flags, epoch))
+            torch.cuda.synchronize()
+            for r in range(world):
+                assert tuple(vals[r].tolist()) == want, (epoch, r, vals[r].tolist())
+    finally:
+        torch.cuda.synchronize()
+        for rk in ranks:
+            rk.close()
