@@ -6,7 +6,10 @@ m-sized objects (M, L, Ax, b) and all scalars are replicated.  The only exchange
   * all-reduce(sum) of the m x m Gram matrix (D-opt) or of the m-vector Ax (Poisson / KL),
   * all-reduce of a handful of scalars per driver step (divergences, dot products, Newton sums),
   * (value, index) extremum with lowest-index tie-break for the simplex LMO.
-torch.distributed carries them (NCCL over NVLink on GPUs, gloo in the CPU tests).
+On GPUs under NCCL these exchanges run over NVLink peer memory inside this library's own kernels (payload stores into
+every rank's symmetric receive buffer + a released flag word; peer_buffers below hands out the buffers and
+config.peer_allreduce switches the scheme off); torch.distributed collectives are the fallback and carry everything
+else (gloo in the CPU tests).
 """
 import torch
 import torch.distributed as dist
