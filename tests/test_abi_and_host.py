@@ -43,6 +43,36 @@ def test_library_is_sm100a_with_dmma():
     assert tma.count("DMMA.8x8x4") >= 64 and "UTMALDG" in tma and "SYNCS" in tma
 
 
+def test_peer_memory_kernels_use_system_scope_release_acquire():
+    """The NVLink peer-memory exchanges rest on: payload stores, a system-scope fence, a release store of the flag word;
+    an acquire load of the flag (which also drops stale L1 lines) before the payload is read.  Check that this is what
+    was compiled: MEMBAR.*.SYS + STG.*.STRONG.SYS on the sending side, LDG.*.STRONG.SYS + CCTL.IVALL on the waiting side."""
+    from accbpg_and_fw_b200 import _native as nat
+    sass = subprocess.run(["cuobjdump", "-sass", nat.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = {}
+    cur = None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            funcs[cur] = []
+        elif cur is not None:
+            funcs[cur].append(line)
+
+    def body(substr):
+        hits = [k for k in funcs if substr in k]
+        assert hits, substr
+        return "\n".join(funcs[hits[0]])
+
+    for sender in ("syrk_reduce_push_kernel", "burg_prepare_push_kernel", "peer_vec_push_kernel",
+                   "peer_sum_scalars_kernel", "peer_argmin_pair_kernel", "fw_pass_kernel", "fw_decide_peer_kernel"):
+        b = body(sender)
+        assert re.search(r"MEMBAR\.\w+\.SYS", b) and re.search(r"STG\.E\.64\.STRONG\.SYS", b), sender
+    for waiter in ("gram_sum_received_kernel", "peer_wait_kernel", "peer_vec_sum_kernel", "peer_sum_scalars_kernel",
+                   "peer_argmin_pair_kernel", "fw_decide_peer_kernel", "fw_hv_kernel"):
+        b = body(waiter)
+        assert re.search(r"LDG\.E\.64\.STRONG\.SYS", b) and "CCTL.IVALL" in b and "NANOSLEEP" in b, waiter
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
