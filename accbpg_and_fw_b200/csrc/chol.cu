@@ -529,12 +529,14 @@ __global__ void __launch_bounds__(256, 1) chol_inv_step_kernel(CholStep p) {
 #ifdef CHOL_TRACE
 long long* g_chol_trace = nullptr;
 #endif
-static bool g_chol_attr = false;
+static bool g_chol_attr[kMaxDevices] = {};        // the attribute is per device
 static int ensure_attrs() {
-    if (g_chol_attr) return ACCBPG_OK;
+    int dev = 0;
+    ACCBPG_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < kMaxDevices && g_chol_attr[dev]) return ACCBPG_OK;
     ACCBPG_CUDA(cudaFuncSetAttribute(chol_inv_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(chol_inv_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM));
-    g_chol_attr = true;
+    if (dev >= 0 && dev < kMaxDevices) g_chol_attr[dev] = true;
     return ACCBPG_OK;
 }
 

@@ -63,9 +63,21 @@ inline int arg_err(const char* what) {
         if (e__ != cudaSuccess) return accbpg::set_err(name, e__); \
     } while (0)
 
+// Every entry point runs on the device its context was created on, whatever device is current in the calling thread
+// (the previous one is restored on return): `device=` of the Python operators works without torch.cuda.set_device.
+struct DeviceGuard {
+    int prev_; bool switched_;
+    explicit DeviceGuard(int dev) : prev_(-1), switched_(false) {
+        if (cudaGetDevice(&prev_) == cudaSuccess && prev_ != dev) switched_ = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (switched_) cudaSetDevice(prev_); }
+};
+#define ACCBPG_ON_DEVICE(c) accbpg::DeviceGuard dev_guard__((c)->device)
+constexpr int kMaxDevices = 64;      // per-device once-flags (function attributes are per device)
+
 // optional cudaEvent bracketing of selected launches (prof.cu); a no-op unless accbpg_prof_enable(1)
 enum ProfId { P_SYRK = 0, P_SYRK_REDUCE, P_CHOL, P_TRINV, P_TRMM, P_GRAD_FIN, P_BURG_SIMPLEX, P_MATVEC, P_RMATVEC,
-              P_FW_PASS, P_FW_ITER, P_COUNT };
+              P_FW_PASS, P_FW_ITER, P_GRAM_PUSH, P_GRAM_SUM, P_GG_PUSH, P_GG_WAIT, P_SCAL_SUM, P_COUNT };
 struct ProfScope {
     ProfScope(int id, cudaStream_t s);
     ~ProfScope();

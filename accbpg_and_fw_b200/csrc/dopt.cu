@@ -971,9 +971,11 @@ static int device_sm_count() {
     return sms;
 }
 
-static bool g_attr_done = false;
+static bool g_attr_done[kMaxDevices] = {};       // the attribute is per device
 static int ensure_smem_attrs() {
-    if (g_attr_done) return ACCBPG_OK;
+    int dev = 0;
+    ACCBPG_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < kMaxDevices && g_attr_done[dev]) return ACCBPG_OK;
     ACCBPG_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMAJOR_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMAJOR_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
@@ -981,7 +983,7 @@ static int ensure_smem_attrs() {
     ACCBPG_CUDA(cudaFuncSetAttribute(trmm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRP_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(trmm_colnorm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
     ACCBPG_CUDA(cudaFuncSetAttribute(trmm_colnorm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
-    g_attr_done = true;
+    if (dev >= 0 && dev < kMaxDevices) g_attr_done[dev] = true;
     return ACCBPG_OK;
 }
 
@@ -1092,6 +1094,7 @@ int accbpg_dopt_gram(void* ctx, void* stream, const double* H, int m, int64_t n,
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !H || !x || !ws || !M) return arg_err("dopt_gram: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     int rc = syrk_partials(c, s, H, m, n, ldh, x, ws);
     if (rc) return rc;
     DoptPlan pl = make_plan(m, n, c->sm_count);
@@ -1111,6 +1114,7 @@ int accbpg_dopt_gram_allreduce(void* ctx, void* stream, const double* H, int m, 
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !H || !x || !ws || !M || !peer_recv || !peer_flags) return arg_err("dopt_gram_allreduce: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return arg_err("dopt_gram_allreduce: rank / world");
     if (m < 1 || n < 1 || ldh < n || epoch < 1) return arg_err("dopt_gram_allreduce: shape / epoch");
     PeerGram g;
@@ -1128,9 +1132,12 @@ int accbpg_dopt_gram_allreduce(void* ctx, void* stream, const double* H, int m, 
     const double* P = (const double*)((char*)ws + pl.off_P);
     dim3 rg((m + 31) / 32, (m + 7) / 8);
     {
-        ProfScope ps(P_SYRK_REDUCE, s);
+        ProfScope ps(P_GRAM_PUSH, s);
         syrk_reduce_push_kernel<<<rg, 256, 0, s>>>(P, pl.s_off, pl.s_diag, m, pl.mp, g, c->d_counter + 16);
         ACCBPG_LAUNCHED("syrk_reduce_push_kernel");
+    }
+    {
+        ProfScope ps(P_GRAM_SUM, s);          // includes the wait for the slowest rank's push
         gram_sum_received_kernel<<<rg, 256, 0, s>>>(g, m, M);
         ACCBPG_LAUNCHED("gram_sum_received_kernel");
     }
@@ -1142,6 +1149,7 @@ int accbpg_dopt_vertex_gram(void* ctx, void* stream, const double* H, int m, int
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !H || !G || !d_idx || !out) return arg_err("dopt_vertex_gram: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (m < 1 || n < 1 || ldh < n) return arg_err("dopt_vertex_gram: shape");
     int grid = grid_for(c, (int64_t)m * m, 256, 2, 8);
     vertex_gram_kernel<<<grid, 256, 0, s>>>(H, m, n, ldh, G, fill, d_idx, col_offset, radius, out);
@@ -1154,6 +1162,7 @@ int accbpg_dopt_factor(void* ctx, void* stream, int m, const double* M, double* 
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !M || !ws || !d_out) return arg_err("dopt_factor: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (m < 1) return arg_err("dopt_factor: m");
     if (M == L) return arg_err("dopt_factor: in-place factorisation is not supported");
     // the factor scratch lives in the m-only head of the workspace (independent of n_local)
@@ -1168,6 +1177,7 @@ int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n,
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !H || !ws || !g) return arg_err("dopt_grad: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (m < 1 || n < 1 || ldh < n) return arg_err("dopt_grad: shape");
     int rc = ensure_smem_attrs();
     if (rc) return rc;
@@ -1311,6 +1321,7 @@ int accbpg_dopt_func_grad(void* ctx, void* stream, const double* H, int m, int64
                           int flag, void* ws, double* d_f_out, double* g) {
     Ctx* c = (Ctx*)ctx;
     if (!c || !ws) return arg_err("dopt_func_grad: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (flag < 0 || flag > 2) return arg_err("dopt_func_grad: flag");
     if (flag >= 1 && !g) return arg_err("dopt_func_grad: gradient buffer is NULL");
     DoptPlan pl = make_plan(m, n, c->sm_count);
@@ -1329,6 +1340,7 @@ int accbpg_dopt_pair(void* ctx, void* stream, const double* H, int m, int64_t n,
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !ws || !xf || !yg || !d_fx_out) return arg_err("dopt_pair: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (flag_y < 1 || flag_y > 2 || !g) return arg_err("dopt_pair: flag_y must be 1 or 2 with a gradient buffer");
     DoptPlan pl = make_plan(m, n, c->sm_count);
     double* M1 = (double*)((char*)ws + pl.off_M);
@@ -1357,6 +1369,7 @@ int accbpg_dopt_pair_from_gram(void* ctx, void* stream, const double* H, int m, 
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !ws || !My) return arg_err("dopt_pair_from_gram: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (flag_y < 0 || flag_y > 2 || (flag_y >= 1 && !g)) return arg_err("dopt_pair_from_gram: flag_y / gradient buffer");
     if (Mx && !d_fx_out) return arg_err("dopt_pair_from_gram: d_fx_out is NULL");
     DoptPlan pl = make_plan(m, n, c->sm_count);

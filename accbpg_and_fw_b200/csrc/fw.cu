@@ -530,6 +530,7 @@ int accbpg_fw_setup(void* ctx, void* stream, const double* V, int m, int64_t n, 
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !V || !x0 || !ws || !Hinv || !w || !ctrl) return arg_err("fw_setup: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     double* slot = c->d_slots + 247;
     // func_grad(flag=2): slot <- -log det M, w <- gradient = -(v_j^T Hinv v_j); Linv stays in the workspace
     int rc = accbpg_dopt_func_grad(ctx, stream, V, m, n, ldv, x0, 2, ws, slot, w);
@@ -650,6 +651,7 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !V || !ws || !Hinv || !x || !w || !ctrl || !hist_F || !hist_SP || !hist_SN || !hist_T)
         return arg_err("fw_run: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (k_count < 0) return arg_err("fw_run: shape");
     if (k_count == 0) return ACCBPG_OK;
     FwLaunch L;
@@ -710,6 +712,7 @@ int accbpg_fw_select_local(void* ctx, void* stream, int64_t n_local, int64_t col
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !x || !w || !ws || !d_record_out) return arg_err("fw_select_local: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     FwLaunch L;
     int rc = fw_prepare(c, x /* any aligned pointer: V is not read */, m, n_local, n_local, away, 0.0, ws, nullptr,
                         (double*)x, (double*)w, nullptr, nullptr, nullptr, nullptr, nullptr, &L);
@@ -727,6 +730,7 @@ int accbpg_fw_decide(void* ctx, void* stream, const double* V, int m, int64_t n_
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !V || !d_records || !ws || !ctrl || !hist_F || !hist_SP || !hist_SN || !hist_T || !d_vcol)
         return arg_err("fw_decide: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (world < 1) return arg_err("fw_decide: world");
     FwLaunch L;
     int rc = fw_prepare(c, V, m, n_local, ldv, away, eps, ws, nullptr, nullptr, nullptr, ctrl, hist_F, hist_SP, hist_SN,
@@ -744,6 +748,7 @@ int accbpg_fw_step(void* ctx, void* stream, const double* V, int m, int64_t n_lo
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !V || !ws || !Hinv || !d_vcol || !x || !w || !ctrl || !d_record_out) return arg_err("fw_step: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     FwLaunch L;
     int rc = fw_prepare(c, V, m, n_local, ldv, away, 0.0, ws, Hinv, x, w, ctrl, nullptr, nullptr, nullptr, nullptr, &L);
     if (rc) return rc;
@@ -777,6 +782,7 @@ int accbpg_fw_run_peer(void* ctx, void* stream, const double* V, int m, int64_t 
     if (!c || !V || !ws || !Hinv || !x || !w || !ctrl || !hist_F || !hist_SP || !hist_SN || !hist_T || !peer_rec ||
         !peer_col || !peer_flags)
         return arg_err("fw_run_peer: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (world < 1 || world > FW_MAX_PEERS || rank < 0 || rank >= world || k_count < 0 || k_start < 0)
         return arg_err("fw_run_peer: rank / world / range");
     if (k_count == 0) return ACCBPG_OK;
@@ -838,6 +844,7 @@ int accbpg_fw_setup_from_gram(void* ctx, void* stream, const double* V, int m, i
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !V || !M || !ws || !Hinv || !w || !ctrl) return arg_err("fw_setup_from_gram: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     double* slot = c->d_slots + 247;
     int rc = accbpg_dopt_factor(ctx, stream, m, M, nullptr, 1, ws, slot);
     if (rc) return rc;

@@ -242,6 +242,7 @@ int accbpg_linreg_matvec(void* ctx, void* stream, const double* A, int64_t m, in
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !A || !x || !Ax) return arg_err("linreg_matvec: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (m < 1 || n < 1 || lda < n) return arg_err("linreg_matvec: shape");
     LinregPlan pl = linreg_plan(m, n, c->sm_count);
     if (pl.nseg > 1 && !ws) return arg_err("linreg_matvec: workspace required when n_local > 65536");
@@ -269,6 +270,7 @@ int accbpg_linreg_value_resid(void* ctx, void* stream, int kind, int64_t m, cons
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !Ax || !b) return arg_err("linreg_value_resid: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (kind != ACCBPG_LINREG_POISSON && kind != ACCBPG_LINREG_KL) return arg_err("linreg kind");
     if (m < 1) return arg_err("linreg_value_resid: m");
     int g = grid_for(c, m, 256, 4, 4);
@@ -282,6 +284,7 @@ int accbpg_linreg_rmatvec(void* ctx, void* stream, const double* A, int64_t m, i
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !A || !r || !ws || !g) return arg_err("linreg_rmatvec: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (m < 1 || n < 1 || lda < n) return arg_err("linreg_rmatvec: shape");
     LinregPlan pl = linreg_plan(m, n, c->sm_count);
     double* partial = (double*)((char*)ws + pl.off_rmv);

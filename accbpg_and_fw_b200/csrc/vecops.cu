@@ -507,24 +507,39 @@ __global__ void peer_wait_kernel(const unsigned long long* flags, int count, uns
     if ((int)threadIdx.x < count) peer_flag_wait(flags + threadIdx.x, epoch);
 }
 
-__global__ void __launch_bounds__(64) peer_sum_scalars_kernel(double* vals, int count, PeerVec pv) {
+// The last slot of a table row carries the sender's status word: every rank ORs all of them into its own, so a
+// precondition violated on one rank's slice raises the same exception on every rank at the same fetch.
+__global__ void __launch_bounds__(64) peer_sum_scalars_kernel(const double* in, double* out, int count, PeerVec pv,
+                                                              uint32_t* status) {
     const int t = threadIdx.x;
     const size_t row = (size_t)(pv.epoch & 1ULL) * pv.world;
     if (t < pv.world) {
         double* dst = pv.buf[t] + (row + pv.rank) * kPeerScalars;
-        for (int k = 0; k < count; ++k) dst[k] = vals[k];
+        for (int k = 0; k < count; ++k) dst[k] = in[k];
+        dst[kPeerScalars - 1] = (double)__ldcg(status);
         __threadfence_system();
         st_release_sys(pv.flags[t] + pv.rank, pv.epoch);
     }
     __syncthreads();
     if (t < pv.world) peer_flag_wait(pv.flags[pv.rank] + t, pv.epoch);
     __syncthreads();
+    const double* tab = pv.buf[pv.rank] + row * kPeerScalars;
     if (t < count) {
-        const double* tab = pv.buf[pv.rank] + row * kPeerScalars;
         double s = 0.0;
         for (int r = 0; r < pv.world; ++r) s += __ldcg(tab + (size_t)r * kPeerScalars + t);
-        vals[t] = s;
+        out[t] = s;
+    } else if (t == kPeerScalars - 1) {
+        uint32_t all = 0;
+        for (int r = 0; r < pv.world; ++r) all |= (uint32_t)__ldcg(tab + (size_t)r * kPeerScalars + kPeerScalars - 1);
+        if (all) atomicOr(status, all);
     }
+}
+
+// status word <-> a float64 slot (the NCCL / gloo fallback of the same exchange carries it through an all-reduce(max))
+__global__ void status_export_kernel(const uint32_t* status, double* slot) { slot[0] = (double)__ldcg(status); }
+__global__ void status_import_kernel(uint32_t* status, const double* slot) {
+    const uint32_t v = (uint32_t)__ldcg(slot);
+    if (v) atomicOr(status, v);
 }
 
 // lowest (value, global index) pair over the ranks: the same single-CTA exchange with a different combine.  Ties in the
@@ -634,6 +649,7 @@ int accbpg_ctx_create(void** out) {
 int accbpg_ctx_destroy(void* ctx) {
     Ctx* c = (Ctx*)ctx;
     if (!c) return ACCBPG_OK;
+    ACCBPG_ON_DEVICE(c);
     cudaFree(c->d_slots); cudaFree(c->d_status); cudaFree(c->d_partials);
     cudaFree(c->d_ipartials); cudaFree(c->d_counter);
     cudaFreeHost(c->h_slots); cudaFreeHost(c->h_status);
@@ -651,6 +667,7 @@ int accbpg_ctx_read(void* ctx, void* stream, const double* d_src, int count, dou
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c) return arg_err("ctx is NULL");
+    ACCBPG_ON_DEVICE(c);
     if (count < 0 || count > kSlots) return arg_err("ctx_read: count must be in [0, 256]");
     if (count > 0 && (!d_src || !h_out)) return arg_err("ctx_read: NULL pointer");
     if (count > 0)
@@ -667,6 +684,7 @@ int accbpg_ctx_read_async(void* ctx, void* stream, const double* d_src, int coun
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !ticket) return arg_err("ctx_read_async: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (count < 0 || count > kSlots) return arg_err("ctx_read_async: count must be in [0, 256]");
     if (count > 0 && !d_src) return arg_err("ctx_read_async: NULL pointer");
     const int t = c->ring_next;
@@ -682,6 +700,7 @@ int accbpg_ctx_read_async(void* ctx, void* stream, const double* d_src, int coun
 int accbpg_ctx_read_wait(void* ctx, int ticket, int count, double* h_out, uint32_t* h_status) {
     Ctx* c = (Ctx*)ctx;
     if (!c) return arg_err("ctx is NULL");
+    ACCBPG_ON_DEVICE(c);
     if (ticket < 0 || ticket >= kReadRing) return arg_err("ctx_read_wait: bad ticket");
     if (count < 0 || count > kSlots || (count > 0 && !h_out)) return arg_err("ctx_read_wait: count / NULL pointer");
     ACCBPG_CUDA(cudaEventSynchronize(c->ring_ev[ticket]));
@@ -695,6 +714,7 @@ int accbpg_ctx_read_wait(void* ctx, int ticket, int count, double* h_out, uint32
     Ctx* c = (Ctx*)ctx;                  \
     cudaStream_t s = (cudaStream_t)stream; \
     if (!c) return arg_err("ctx is NULL"); \
+    ACCBPG_ON_DEVICE(c);                 \
     if (n < 0) return arg_err("n < 0");
 
 int accbpg_vec_axpby(void* ctx, void* stream, int64_t n, double a, const double* x, double b, const double* y,
@@ -736,6 +756,7 @@ int accbpg_mat_outer(void* ctx, void* stream, int64_t p, const double* u, int64_
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !u || !v || !out) return arg_err("mat_outer: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
     if (p < 1 || q < 1) return arg_err("mat_outer: shape");
     int grid = grid_for(c, p * q, 256, 2, 8);
     outer_kernel<<<grid, 256, 0, s>>>(u, p, v, q, out);
@@ -845,6 +866,7 @@ int accbpg_burg_simplex_push_peer(void* ctx, void* stream, int64_t n_local, int6
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c) return arg_err("ctx is NULL");
+    ACCBPG_ON_DEVICE(c);
     if (!g || !d_gg_local) return arg_err("burg_simplex_push_peer: NULL pointer");
     if (!(L > 0.0)) return arg_err("L must be positive");
     if (n_local < 0 || width < n_local || width < 1) return arg_err("burg_simplex_push_peer: width");
@@ -852,6 +874,7 @@ int accbpg_burg_simplex_push_peer(void* ctx, void* stream, int64_t n_local, int6
     int rc = peer_vec_fill(pv, rank, world, peer_gg, peer_flags, epoch, "burg_simplex_push_peer: peer tables / rank / epoch");
     if (rc) return rc;
     int pgrid = grid_for(c, width, kThreads, 4, 4);
+    ProfScope ps(P_GG_PUSH, s);
     burg_prepare_push_kernel<<<pgrid, kThreads, 0, s>>>(n_local, width, y, g, L, d_gg_local, pv, c->d_counter + 18,
                                                         c->d_status);
     ACCBPG_LAUNCHED("burg_prepare_push_kernel");
@@ -862,12 +885,16 @@ int accbpg_burg_simplex_root_peer(void* ctx, void* stream, int64_t width, double
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c) return arg_err("ctx is NULL");
+    ACCBPG_ON_DEVICE(c);
     if (!d_info || width < 1) return arg_err("burg_simplex_root_peer: NULL pointer / width");
     PeerVec pv;
     int rc = peer_vec_fill(pv, rank, world, peer_gg, peer_flags, epoch, "burg_simplex_root_peer: peer tables / rank / epoch");
     if (rc) return rc;
-    peer_wait_kernel<<<1, 32, 0, s>>>(pv.flags[rank], world, epoch);
-    ACCBPG_LAUNCHED("peer_wait_kernel");
+    {
+        ProfScope psw(P_GG_WAIT, s);
+        peer_wait_kernel<<<1, 32, 0, s>>>(pv.flags[rank], world, epoch);
+        ACCBPG_LAUNCHED("peer_wait_kernel");
+    }
     int64_t n = width * world;
     int64_t want = (n + kBurgThreads - 1) / kBurgThreads;
     int grid = (int)(want < c->coop_blocks_burg ? want : c->coop_blocks_burg);
@@ -885,16 +912,17 @@ int accbpg_burg_simplex_root_peer(void* ctx, void* stream, int64_t width, double
     return ACCBPG_OK;
 }
 
-// Sum `count` (<= 16) per-rank partial scalars over the ranks through peer memory, in rank order, in place: one CTA
-// stores its values into slot `rank` of every rank's table, releases its flag word there, waits for the `world` flags
-// of its own table and adds the rows up (every rank forms the same sums).
-int accbpg_peer_sum_scalars(void* ctx, void* stream, double* d_vals, int count, int rank, int world,
+// Sum `count` (<= 15) per-rank partial scalars over the ranks through peer memory, in rank order: one CTA stores its
+// values (and its status word) into slot `rank` of every rank's table, releases its flag word there, waits for the
+// `world` flags of its own table and adds the rows up (every rank forms the same sums).  d_out may equal d_in.
+int accbpg_peer_sum_scalars(void* ctx, void* stream, const double* d_in, double* d_out, int count, int rank, int world,
                             void* const* peer_tab, void* const* peer_flags, uint64_t epoch) {
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c) return arg_err("ctx is NULL");
-    if (!d_vals || !peer_tab || !peer_flags) return arg_err("peer_sum_scalars: NULL pointer");
-    if (count < 1 || count > kPeerScalars || world < 1 || world > kMaxPeerRanks || rank < 0 || rank >= world || epoch < 1)
+    ACCBPG_ON_DEVICE(c);
+    if (!d_in || !d_out || !peer_tab || !peer_flags) return arg_err("peer_sum_scalars: NULL pointer");
+    if (count < 1 || count > kPeerScalars - 1 || world < 1 || world > kMaxPeerRanks || rank < 0 || rank >= world || epoch < 1)
         return arg_err("peer_sum_scalars: count / rank / world / epoch");
     PeerVec pv;
     for (int r = 0; r < world; ++r) {
@@ -902,8 +930,28 @@ int accbpg_peer_sum_scalars(void* ctx, void* stream, double* d_vals, int count, 
         if (!pv.buf[r] || !pv.flags[r]) return arg_err("peer_sum_scalars: NULL peer pointer");
     }
     pv.rank = rank; pv.world = world; pv.epoch = epoch;
-    peer_sum_scalars_kernel<<<1, 64, 0, s>>>(d_vals, count, pv);
+    ProfScope ps(P_SCAL_SUM, s);
+    peer_sum_scalars_kernel<<<1, 64, 0, s>>>(d_in, d_out, count, pv, c->d_status);
     ACCBPG_LAUNCHED("peer_sum_scalars_kernel");
+    return ACCBPG_OK;
+}
+
+int accbpg_ctx_status_export(void* ctx, void* stream, double* d_slot) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !d_slot) return arg_err("ctx_status_export: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
+    status_export_kernel<<<1, 1, 0, s>>>(c->d_status, d_slot);
+    ACCBPG_LAUNCHED("status_export_kernel");
+    return ACCBPG_OK;
+}
+int accbpg_ctx_status_import(void* ctx, void* stream, const double* d_slot) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !d_slot) return arg_err("ctx_status_import: NULL pointer");
+    ACCBPG_ON_DEVICE(c);
+    status_import_kernel<<<1, 1, 0, s>>>(c->d_status, d_slot);
+    ACCBPG_LAUNCHED("status_import_kernel");
     return ACCBPG_OK;
 }
 
@@ -913,6 +961,7 @@ int accbpg_peer_argmin_pair(void* ctx, void* stream, double* d_pair, int rank, i
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c) return arg_err("ctx is NULL");
+    ACCBPG_ON_DEVICE(c);
     if (!d_pair) return arg_err("peer_argmin_pair: NULL pointer");
     PeerVec pv;
     int rc = peer_vec_fill(pv, rank, world, peer_tab, peer_flags, epoch, "peer_argmin_pair: peer tables / rank / epoch");
@@ -929,6 +978,7 @@ int accbpg_peer_sum_vector(void* ctx, void* stream, double* d_x, int64_t n, int6
     Ctx* c = (Ctx*)ctx;
     cudaStream_t s = (cudaStream_t)stream;
     if (!c) return arg_err("ctx is NULL");
+    ACCBPG_ON_DEVICE(c);
     if (!d_x || n < 1 || cap < n) return arg_err("peer_sum_vector: NULL pointer / n / cap");
     PeerVec pv;
     int rc = peer_vec_fill(pv, rank, world, peer_buf, peer_flags, epoch, "peer_sum_vector: peer tables / rank / epoch");

@@ -92,14 +92,8 @@ class ColumnShard:
         from . import _native as nat
         from .runtime import Runtime
         rt = Runtime.get(t.device)
-        if n <= 16:
-            pb = peer_buffers(self, t.device, [(2 * self.world * 16, torch.float64), (self.world, torch.int64)],
-                              cache_key="sum16", reset=False)
-            if pb is None:
-                return False
-            nat.check(nat.lib.accbpg_peer_sum_scalars(rt.ctx, rt.stream, t.data_ptr(), n, self.rank, self.world,
-                                                      pb.tables[0], pb.tables[1], pb.next_epoch()))
-            return True
+        if n <= 15:
+            return self.sum_scalars_into(t, t)
         cap = 1 << (n - 1).bit_length()
         pb = peer_buffers(self, t.device, [(2 * self.world * cap, torch.float64), (self.world, torch.int64)],
                           cache_key=("sumvec", cap), reset=False)
@@ -107,6 +101,24 @@ class ColumnShard:
             return False
         nat.check(nat.lib.accbpg_peer_sum_vector(rt.ctx, rt.stream, t.data_ptr(), n, cap, self.rank, self.world,
                                                  pb.tables[0], pb.tables[1], pb.next_epoch()))
+        return True
+
+    def sum_scalars_into(self, src, dst):
+        """dst <- sum over the ranks of src (<= 15 float64 CUDA scalars; dst may be src) through peer memory, with every
+        rank's device status word OR-ed into every other rank's (an assertion that fails on one rank's slice is then
+        raised by all ranks at the same read instead of leaving the others waiting in the next exchange).  Returns False
+        when peer memory is unavailable: the caller falls back to collectives."""
+        if self.world < 2 or not src.is_cuda:
+            return False
+        from . import _native as nat
+        from .runtime import Runtime
+        pb = peer_buffers(self, src.device, [(2 * self.world * 16, torch.float64), (self.world, torch.int64)],
+                          cache_key="sum16", reset=False)
+        if pb is None:
+            return False
+        rt = Runtime.get(src.device)
+        nat.check(nat.lib.accbpg_peer_sum_scalars(rt.ctx, rt.stream, src.data_ptr(), dst.data_ptr(), src.numel(),
+                                                  self.rank, self.world, pb.tables[0], pb.tables[1], pb.next_epoch()))
         return True
 
     def min_(self, t):
@@ -197,6 +209,7 @@ def peer_buffers(shard, device, specs, cache_key=None, reset=True):
                 torch.cuda.synchronize()
                 dist.barrier(shard.group)
             return hit
+    pb, err = None, None
     try:
         import torch.distributed._symmetric_memory as symm
         grp = shard.group if shard.group is not None else dist.group.WORLD
@@ -206,13 +219,18 @@ def peer_buffers(shard, device, specs, cache_key=None, reset=True):
         hdls = [symm.rendezvous(b, grp) for b in bufs]
         arrs = [(ctypes.c_void_p * shard.world)(*[int(p) for p in hd.buffer_ptrs]) for hd in hdls]
         torch.cuda.synchronize()
-        dist.barrier(grp)
         pb = PeerBuffers(bufs, arrs, hdls)
-        if key is not None:
-            _peer_cache[key] = pb
-        return pb
     except Exception as exc:                              # no symmetric memory on this system: the callers use NCCL
-        warnings.warn(f"peer-memory buffers unavailable ({exc!r}); using NCCL")
+        err = exc
+    # the ranks must take the same path: one that could not map its buffers sends everybody to the collectives
+    ok = torch.tensor([1 if pb is not None else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=shard.group)
+    if int(ok.item()) == 0:
+        warnings.warn(f"peer-memory buffers unavailable on some rank ({err!r}); using NCCL")
         if key is not None:
             _peer_cache[key] = False
         return None
+    dist.barrier(shard.group)
+    if key is not None:
+        _peer_cache[key] = pb
+    return pb

@@ -32,7 +32,8 @@ def _run(V, x0, eps, maxitrs, away, verbose, verbskip, batch, device, index_log)
     x = rt.to_device(x0).clone()
     assert x.numel() == n, "x0.size not equal to the number of columns of V"
     dev = rt.device
-    ws = rt.workspace(("fw", m, n), lib.accbpg_fw_workspace_bytes(m, n))
+    with rt.on_device():
+        ws = rt.workspace(("fw", m, n), lib.accbpg_fw_workspace_bytes(m, n))
     Hinv = torch.empty(m, m, dtype=torch.float64, device=dev)
     w = torch.empty(n, dtype=torch.float64, device=dev)
     ctrl = torch.zeros(NCTRL, dtype=torch.float64, device=dev)
@@ -93,7 +94,8 @@ def _run_sharded(V, x0, eps, maxitrs, away, verbose, verbskip, batch, device, in
     x = rt.to_device(x0).clone()
     assert x.numel() == n, "x0 must be this rank's slice (ColumnShard.part)"
     dev = rt.device
-    ws = rt.workspace(("fw", m, n), lib.accbpg_fw_workspace_bytes(m, n))
+    with rt.on_device():
+        ws = rt.workspace(("fw", m, n), lib.accbpg_fw_workspace_bytes(m, n))
     Hinv = torch.empty(m, m, dtype=torch.float64, device=dev)
     M = torch.empty(m, m, dtype=torch.float64, device=dev)
     w = torch.empty(n, dtype=torch.float64, device=dev)

@@ -138,22 +138,43 @@ class _Loop:
         self.h._enq_divergence(x, y, slot)
 
     def _sum_partials(self):
-        if self.sharded:
-            rt = self.rt
-            # S_DXY, S_DZZ, S_DOT, S_PSI are per-rank partials: one small kernel over NVLink peer memory, else NCCL
-            self.shard.sum_(rt.scal[rt.S_DXY:rt.S_PSI + 1])
+        """Column-sharded runs: S_DXY, S_DZZ, S_DOT, S_PSI hold per-rank partials.  Their sums over the ranks go to the
+        separate slots S_SUM.. (so a second fetch without new partials cannot add them up twice), and the same exchange
+        makes the device status word the union over the ranks: one small kernel over NVLink peer memory, else collectives."""
+        rt = self.rt
+        src = rt.scal[rt.S_DXY:rt.S_PSI + 1]
+        dst = rt.scal[rt.S_SUM:rt.S_SUM + 4]
+        if self.shard.sum_scalars_into(src, dst):
+            return
+        dst.copy_(src)
+        self.shard.sum_(dst)
+        st = rt.scal[rt.S_SUM + 4:rt.S_SUM + 5]
+        nat.check(lib.accbpg_ctx_status_export(rt.ctx, rt.stream, st.data_ptr()))
+        self.shard.max_(st)
+        nat.check(lib.accbpg_ctx_status_import(rt.ctx, rt.stream, st.data_ptr()))
+
+    def _merge(self, vals):
+        rt = self.rt
+        vals[rt.S_DXY:rt.S_PSI + 1] = vals[rt.S_SUM:rt.S_SUM + 4]
+        return vals
 
     def fetch(self):
+        if not self.sharded:
+            return self.rt.read(0, 7)      # S_F .. S_PSI and S_AUX0 in one pinned read
         self._sum_partials()
-        return self.rt.read(0, 7)          # S_F .. S_PSI and S_AUX0 in one pinned read
+        return self._merge(self.rt.read(0, self.rt.S_SUM + 4))
 
     def fetch_async(self):
         """Deferred fetch: the copy is enqueued now, `fetch_wait(ticket)` collects it later."""
+        if not self.sharded:
+            return self.rt.read_async(0, 7)
         self._sum_partials()
-        return self.rt.read_async(0, 7)
+        return self.rt.read_async(0, self.rt.S_SUM + 4)
 
     def fetch_wait(self, ticket):
-        return self.rt.read_wait(ticket, 7)
+        if not self.sharded:
+            return self.rt.read_wait(ticket, 7)
+        return self._merge(self.rt.read_wait(ticket, self.rt.S_SUM + 4))
 
     def pipeline_depth(self, verbose, restart=False):
         """How many iterations may be enqueued beyond the one whose scalars the host has seen (config.pipeline)."""
@@ -403,7 +424,10 @@ def ABPG_expo(f, h, L, x0, gamma0, maxitrs, epsilon=1e-14, delta=0.2,
             else:
                 again = False
         fx_known = None if checkdiv else vals[rt.S_F]       # f at the accepted x: next iteration's F[k+1]
-        Ix = lp.img_refresh(k, x, Ix)
+        Ix_new = lp.img_refresh(k, x, Ix)
+        if Ix_new is not Ix:
+            fx_known = None                                 # re-anchored: F[k+1] is evaluated from the fresh image
+        Ix = Ix_new
         G[k] = Gdr
         Gamma[k] = gamma
         if verbose and k % verbskip == 0:
@@ -492,7 +516,10 @@ def ABPG_gain(f, h, L, x0, gamma, maxitrs, epsilon=1e-14, G0=1,
             if again:
                 G = G * ls_inc
         fx_known = None if checkdiv else vals[rt.S_F]       # f at the accepted x: next iteration's F[k+1]
-        Ix = lp.img_refresh(k, x, Ix)
+        Ix_new = lp.img_refresh(k, x, Ix)
+        if Ix_new is not Ix:
+            fx_known = None                                 # re-anchored: F[k+1] is evaluated from the fresh image
+        Ix = Ix_new
         Gain[k] = G
         Gdiv[k] = Gdr       # stale (or unbound on the very first trip) after the break above, as in the reference
         sumlogG += np.log(G)

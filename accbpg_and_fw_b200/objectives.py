@@ -55,8 +55,9 @@ class DOptimalObj(RSmoothFunction):
         self.m, self.n_local = int(self._Hd.shape[0]), int(self._Hd.shape[1])
         self.n = shard.n if shard is not None else self.n_local
         assert self.m < self.n, "DOptimalObj: need m < n"
-        self._ws = self.rt.workspace(("dopt", self.m, self.n_local),
-                                     lib.accbpg_dopt_workspace_bytes(self.m, self.n_local))
+        with self.rt.on_device():                      # the plan depends on the device's SM count
+            self._ws = self.rt.workspace(("dopt", self.m, self.n_local),
+                                         lib.accbpg_dopt_workspace_bytes(self.m, self.n_local))
         self._peer = None
         if shard is not None and shard.world > 1:
             self._M = torch.empty(self.m, self.m, dtype=torch.float64, device=self.rt.device)
@@ -177,8 +178,9 @@ class _LinearInverse(RSmoothFunction):
         self._bd = self.rt.to_device(b)
         self.m, self.n_local = int(self._Ad.shape[0]), int(self._Ad.shape[1])
         self.n = shard.n if shard is not None else self.n_local
-        self._ws = self.rt.workspace(("linreg", self.m, self.n_local),
-                                     lib.accbpg_linreg_workspace_bytes(self.m, self.n_local))
+        with self.rt.on_device():
+            self._ws = self.rt.workspace(("linreg", self.m, self.n_local),
+                                         lib.accbpg_linreg_workspace_bytes(self.m, self.n_local))
         self._Ax = self.rt.empty(self.m)
         self._r = self.rt.empty(self.m)
 

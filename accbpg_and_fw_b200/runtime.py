@@ -32,6 +32,7 @@ class Runtime:
 
     # slot map (indices into self.scal) used by the drivers so one read fetches a whole line-search trip
     S_F, S_F2, S_DXY, S_DZZ, S_DOT, S_PSI, S_AUX0, S_AUX1, S_AUX2, S_AUX3 = range(10)
+    S_SUM = 16          # S_SUM .. S_SUM+3: sums over the ranks of S_DXY .. S_PSI (column-sharded runs); +4: status
     S_TMP = 32          # scratch for the synchronous operator methods
     N_SLOTS = 64
 
@@ -65,6 +66,10 @@ class Runtime:
         self._ws = {}
         self.dist = None            # set by dist.ColumnShard when the problem is column-sharded
         self._pin = {}              # numel -> (ring of pinned staging buffers, next index) for host-vector uploads
+
+    def on_device(self):
+        """Context manager that makes this runtime's device current (for the few calls that take no context)."""
+        return torch.cuda.device(self.index)
 
     # ---- streams / pointers ------------------------------------------------------------
     @property

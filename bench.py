@@ -4,22 +4,31 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): D-optimal design, H = randn(500, 50000) per GPU
+Headline workload (BASELINE.json configs[1]): D-optimal design, H = randn(500, 50000) per GPU
 (D_opt_design(500, 50000, randseed=1) at N=1), solved by ABPG with gamma=2.  One *step* is one ABPG outer
-iteration: f(x) [SYRK + Cholesky], grad f(y) [SYRK + Cholesky + L^-1 + triangular GEMM with column-norm
-epilogue], the Burg-simplex Bregman step, two axpby and two Burg divergences.  N > 1 is weak scaling:
-every rank owns a 500 x 50000 column slab of a 500 x (50000 N) design, the Gram matrix is all-reduced.
+iteration: f(x) [Cholesky of the carried Gram matrix], grad f(y) [Cholesky + L^-1 + triangular GEMM with column-norm
+epilogue], the Burg-simplex Bregman step [+ SYRK of the new prox point], two axpby and two Burg divergences.
+N > 1 is weak scaling: every rank owns a 500 x 50000 column slab of a 500 x (50000 N) design, the Gram matrix is
+summed over the ranks.  It is the one configuration whose CPU arm runs at full size.
 
 Printed JSON (one line, rank 0):
-  value     ABPG iterations/s with H and the iterates resident in HBM (x N slabs under weak scaling)
+  value     ABPG iterations/s with H and the iterates resident in HBM (x N slabs under weak scaling); the timed region
+            repeats the K-step solve `reps` times so that it is long enough for the in-line clock sampler to see load
   e2e       the same iteration driven through the public operator protocol with HOST vectors
             (NumPy in / NumPy out on every call, H resident in the operator as in the reference)
   roofline  the dominant kernel (FP64 DMMA SYRK) against the FP64 GEMM rate measured in this run
-  cpu_baseline  the NumPy oracle port of the reference on this box's host cores (bounded sample)
-`--impl reference` times only that CPU path, on the same metric and config.
+  cpu_baseline  the reference (oracle/_ref, the unmodified accbpg package; else the NumPy oracle port) on this box's cores
+  extra     the other BASELINE.json configurations, device-generated: c1 (80x200 BPG-LS), c2 (ABPG_gain, FW-away on the
+            headline instance), c5 (2000 x 10^6 ABPG_gain: the north_star target; strong-scaled over the ranks when
+            N > 1, with the one-GPU run of the same instance timed by rank 0 in the same process), c3 (KL 20000x200000),
+            c4_slab (Poisson 100000x125000 = the per-GPU slab of the 8-GPU shape); at N > 1 also the sharded-vs-single
+            parity of the headline trajectory and of the FW-away vertex sequence, and a per-exchange breakdown.
+`--impl reference` times only the CPU path, on the same metric and config.
 """
 import argparse
+import ctypes
 import json
+import math
 import os
 import subprocess
 import sys
@@ -34,6 +43,16 @@ sys.path.insert(0, ROOT)
 M_ROWS = 500
 N_PER_GPU = 50000
 GAMMA = 2
+C5_M, C5_N, C5_SLABS = 2000, 1000000, 8
+
+
+def workload_text(world):
+    """config.workload: identical in both arms."""
+    return (f"D-opt {M_ROWS}x{N_PER_GPU * world} (H=randn, seed 1+rank per {M_ROWS}x{N_PER_GPU} slab), ABPG gamma=2, "
+            f"x0=1/n, L=1, BurgEntropySimplex")
+
+
+UNIT = "it/s (x N slabs of 500x50000 under weak scaling)"
 
 
 def make_slab(rank, n_local):
@@ -43,51 +62,62 @@ def make_slab(rank, n_local):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference (test infrastructure; only ever the thing *compared against*)
+# CPU arm: the reference itself (oracle/_ref) or the oracle port; only ever the thing *compared against*
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_threads():
+def set_cpu_threads():
+    """All host cores for BLAS, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1).  Returns the count."""
+    want = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        from threadpoolctl import threadpool_limits, threadpool_info
+        threadpool_limits(limits=want)
+        got = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        return got
     except Exception:
-        return os.cpu_count() or 1
+        return 1
 
 
-def run_cpu_abpg(H, iters):
-    """ABPG(gamma=2) of the oracle on H; returns seconds per iteration measured from its own T array."""
-    from oracle import accbpg_oracle as orc
-    f = orc.make_dopt(H)
-    h = orc.make_burg("simplex")
+def cpu_abpg(H, iters):
+    """ABPG(gamma=2) on H by the reference package when oracle/_ref holds it, else by the oracle port.
+    Returns (seconds per iteration from the driver's own T array, F, kind)."""
     n = H.shape[1]
     x0 = (1.0 / n) * np.ones(n)
-    t0 = time.time()
-    x, F, G, T = orc.ABPG(f, h, 1.0, x0, gamma=GAMMA, maxitrs=iters + 1, theta_eq=False)
-    wall = time.time() - t0
-    per_it = (T[-1] - T[0]) / (len(T) - 1) if len(T) > 1 else wall
-    return per_it, F
+    try:
+        from oracle import ref_loader
+        ref = ref_loader.import_reference()
+        f, h = ref.DOptimalObj(H), ref.BurgEntropySimplex()
+        x, F, G, T = ref.ABPG(f, h, 1.0, x0, gamma=GAMMA, maxitrs=iters + 1, theta_eq=False, verbose=False)
+        kind = "reference"
+    except ImportError:
+        from oracle import accbpg_oracle as orc
+        f, h = orc.make_dopt(H), orc.make_burg("simplex")
+        x, F, G, T = orc.ABPG(f, h, 1.0, x0, gamma=GAMMA, maxitrs=iters + 1, theta_eq=False)
+        kind = "port"
+    per_it = (T[-1] - T[0]) / (len(T) - 1)
+    return per_it, np.asarray(F), kind
 
 
 def reference_arm(args, world):
+    cores = set_cpu_threads()
     n = N_PER_GPU * world
     H = np.concatenate([make_slab(r, N_PER_GPU) for r in range(world)], axis=1) if world > 1 else make_slab(0, n)
     if args.warmup > 0:
-        run_cpu_abpg(H, 1)
+        cpu_abpg(H, 1)
     # bounded sample: about 0.6 s per iteration and slab on 16 cores; keep the whole arm under ~2 minutes
     iters = max(3, min(args.steps, int(100.0 / (0.6 * world))))
-    per_it, F = run_cpu_abpg(H, iters)
-    cores = cpu_threads()
+    per_it, F, kind = cpu_abpg(H, iters)
     value = world / per_it
+    what = ("the unmodified reference package (oracle/_ref/accbpg, copied by oracle/build_ref.py)" if kind == "reference"
+            else "the NumPy oracle port (oracle/accbpg_oracle.py)")
     line = {
-        "impl": "reference", "metric": "abpg_gamma2_iterations_per_sec", "value": value,
-        "unit": "it/s (x N slabs of 500x50000 under weak scaling)", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_it * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"D-opt {M_ROWS}x{n} (H=randn, seed 1+rank per slab), ABPG gamma=2, x0=1/n, L=1",
-                   "timing": "reference's own T array (time.time() at the top of each iteration)"},
-        "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": "port",
-                         "sample": f"{iters} ABPG iterations of the NumPy oracle port (oracle/accbpg_oracle.py) "
-                                   f"on the full {M_ROWS}x{n} instance (of the {args.steps} steps asked for: the arm is "
-                                   f"bounded to about two minutes), os.cpu_count()={os.cpu_count()}"},
+        "impl": "reference", "metric": "abpg_gamma2_iterations_per_sec", "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_it * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_text(world),
+                   "timing": "the driver's own T array (time.time() at the top of each iteration)"},
+        "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": kind,
+                         "sample": f"{iters} ABPG iterations of {what} on the full {M_ROWS}x{n} instance (of the "
+                                   f"{args.steps} steps asked for: the arm is bounded to about two minutes); "
+                                   f"{cores} BLAS threads set explicitly, os.cpu_count()={os.cpu_count()}"},
         "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -98,20 +128,57 @@ def reference_arm(args, world):
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: NVML polled every ~2 ms from a thread (nvidia-smi's
+    100 ms loop cannot see a region of tens of milliseconds); nvidia-smi is the fallback when NVML cannot be loaded."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, torch_index):
+        self.rows, self.proc, self.thread, self.stop = [], None, None, False
+        self.handle, self.nv, self.max_mhz, self.source = None, None, None, None
+        self.index = torch_index
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[torch_index]) if vis and vis.split(",")[torch_index].isdigit() else torch_index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml, 2 ms poll"
+        except Exception:
+            self.handle = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                bits = int(reasons_fn(self.handle))
+                self.rows.append((mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
+        if self.handle is not None:
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            self.source = "nvidia-smi -lms 20"
         except Exception:
             self.proc = None
         return self
@@ -121,8 +188,11 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
-        if self.proc is not None:
-            time.sleep(0.15)
+        self.stop = True
+        if self.handle is not None:
+            self.thread.join(timeout=1)
+        elif self.proc is not None:
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -130,19 +200,33 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
+        sm, mx, reasons = [], [], set()
+        if self.handle is not None:
+            nv = self.nv
+            masks = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            for mhz, bits in self.rows:
+                sm.append(mhz)
+                for nm, mk in masks.items():
+                    if bits & mk:
                         reasons.add(nm)
-            except Exception:
-                pass
+            mx = [self.max_mhz]
+        else:
+            for r in self.rows:
+                try:
+                    sm.append(float(r[0])); mx.append(float(r[1]))
+                    for nm, v in zip(names, r[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+                except Exception:
+                    pass
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "source": self.source}
 
 
 def measure_fp64_peak(torch):
@@ -182,45 +266,43 @@ def host_vector_abpg(f, h, L, x0, gamma, iters):
     return F, up, down
 
 
-def native_arm(args, rank, local_rank, world):
-    import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    import accbpg_and_fw_b200 as acc
-    from accbpg_and_fw_b200 import _native as nat
-    lib = nat.lib
-    import ctypes
+class Bench:
+    """State shared by the legs of the GPU arm."""
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def __init__(self, args, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        import accbpg_and_fw_b200 as acc
+        from accbpg_and_fw_b200 import _native as nat
+        self.args, self.rank, self.local, self.world = args, rank, local_rank, world
+        self.torch, self.dist, self.acc, self.nat, self.lib = torch, dist, acc, nat, nat.lib
+        self.dev = torch.device("cuda", local_rank)
+        self.peaks = {}
+        try:
+            self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.hbm = float(self.peaks.get("hbm_gbs", 6551.0))
+        self.hbm_source = ("MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in self.peaks
+                           else "fallback 6551 GB/s (B200_PROFILING.md measured copy figure; MEASURED_PEAKS.json absent)")
+        self.fp64_peak = float("nan")
 
-    def max_over_ranks(v):
-        if world == 1:
+    # ---- helpers ------------------------------------------------------------------------------------------------
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
             return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    fp64_peak = measure_fp64_peak(torch) if not args.lean else float("nan")
-
-    n_total = N_PER_GPU * world
-    shard = acc.ColumnShard(n_total) if world > 1 else None
-    Hh = make_slab(rank, N_PER_GPU)
-    f = acc.DOptimalObj(Hh, shard=shard)
-    h = acc.BurgEntropySimplex(shard=shard)
-    L = 1.0
-    x0_host = (1.0 / n_total) * np.ones(N_PER_GPU)
-    x0 = torch.tensor(x0_host, device="cuda")
-    m, n = M_ROWS, N_PER_GPU
-
-    def prof_read():
+    def prof_read(self):
+        lib, nat = self.lib, self.nat
         out = {}
         tot, cnt = ctypes.c_double(0), ctypes.c_int64(0)
         for i in range(lib.accbpg_prof_count()):
@@ -230,149 +312,440 @@ def native_arm(args, rank, local_rank, world):
                                                          "ms_avg": tot.value / cnt.value}
         return out
 
-    # ---- device-resident arm: W warm-up iterations, then exactly K timed iterations -----------------------
-    acc.ABPG(f, h, L, x0, gamma=GAMMA, maxitrs=max(args.warmup, 1), verbose=False)
-    lib.accbpg_prof_enable(1)
-    prof_read()
-    barrier()
-    launches0 = nat.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        e0.record()
-        x, F, G, T = acc.ABPG(f, h, L, x0, gamma=GAMMA, maxitrs=args.steps, verbose=False)
-        e1.record()
-        barrier()
-    launches = nat.launch_count() - launches0
-    kern = prof_read()
-    lib.accbpg_prof_enable(0)
-    assert len(F) == args.steps, "ABPG stopped early: the timed region must contain exactly K iterations"
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = ms_total / args.steps
-    value = world * args.steps / (ms_total * 1e-3)
+    def timed(self, fn, collective=True):
+        """CUDA events on the launch stream around fn(); max over ranks when the call is collective."""
+        torch = self.torch
+        if collective:
+            self.barrier()
+        else:
+            torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        return r, (self.max_over_ranks(ms) if collective else ms)
 
-    # ---- e2e arm: host vectors through the public operator protocol ------------------------------------------
-    if args.lean:
-        if rank == 0:
-            print(json.dumps({"lean": True, "ms_per_step": ms_per_step, "value": value, "gpu_launches": launches,
-                              "kernel_ms_per_step": {k: v["ms_total"] / args.steps for k, v in kern.items()}}))
-        return
-    host_vector_abpg(f, h, L, x0_host, GAMMA, max(1, min(args.warmup, 3)))
-    barrier()
+    def free(self):
+        import gc
+        gc.collect()
+        self.torch.cuda.empty_cache()
+
+
+def run_headline(B):
+    """Device-resident arm: W warm-up iterations, then `reps` x K timed iterations."""
+    args, acc, torch, lib = B.args, B.acc, B.torch, B.lib
+    world, rank = B.world, B.rank
+    n_total = N_PER_GPU * world
+    shard = acc.ColumnShard(n_total) if world > 1 else None
+    Hh = make_slab(rank, N_PER_GPU)
+    f = acc.DOptimalObj(Hh, shard=shard)
+    h = acc.BurgEntropySimplex(shard=shard)
+    x0_host = (1.0 / n_total) * np.ones(N_PER_GPU)
+    x0 = torch.tensor(x0_host, device="cuda")
+    B.f, B.h, B.x0, B.x0_host, B.Hh, B.shard = f, h, x0, x0_host, Hh, shard
+
+    acc.ABPG(f, h, 1.0, x0, gamma=GAMMA, maxitrs=max(args.warmup, 1), verbose=False)
+    (_, ms_probe) = B.timed(lambda: acc.ABPG(f, h, 1.0, x0, gamma=GAMMA, maxitrs=args.steps, verbose=False))
+    reps = max(1, min(50, int(math.ceil(args.min_timed_ms / max(ms_probe, 1e-3)))))
+    if world > 1:                                  # every rank must run the same number of solves
+        t = torch.tensor([reps], dtype=torch.int64, device="cuda")
+        B.dist.broadcast(t, 0)
+        reps = int(t.item())
+    lib.accbpg_prof_enable(1)
+    B.prof_read()
+    B.barrier()
+    launches0 = B.nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(B.local) as clk:
+        e0.record()
+        for _ in range(reps):
+            x, F, G, T = acc.ABPG(f, h, 1.0, x0, gamma=GAMMA, maxitrs=args.steps, verbose=False)
+        e1.record()
+        B.barrier()
+    launches = B.nat.launch_count() - launches0
+    kern = B.prof_read()
+    lib.accbpg_prof_enable(0)
+    assert len(F) == args.steps, "ABPG stopped early: the timed region must contain exactly K iterations per solve"
+    ms_total = B.max_over_ranks(e0.elapsed_time(e1))
+    timed_steps = reps * args.steps
+    return {"F": F, "T": T, "ms_total": ms_total, "ms_per_step": ms_total / timed_steps, "reps": reps,
+            "timed_steps": timed_steps, "value": world * timed_steps / (ms_total * 1e-3), "launches": launches,
+            "kern": kern, "clocks": clk.summary()}
+
+
+def run_e2e(B, head):
+    args, torch = B.args, B.torch
+    host_vector_abpg(B.f, B.h, 1.0, B.x0_host, GAMMA, max(1, min(args.warmup, 3)))
+    B.barrier()
     t0 = time.perf_counter()
-    Fh, up, down = host_vector_abpg(f, h, L, x0_host, GAMMA, args.steps)
+    Fh, up, down = host_vector_abpg(B.f, B.h, 1.0, B.x0_host, GAMMA, args.steps)
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s = B.max_over_ranks(time.perf_counter() - t0)
+    F = head["F"]
     devs = np.abs(Fh - F) / np.abs(F)
     # the two arms evaluate the same iteration in a different floating-point order (carried linear images vs direct
     # evaluation); ABPG amplifies such rounding differences exponentially with k (DESIGN.md section 5: the reference's
     # own +-1 ulp noise), so the agreement bar holds on the first 100 iterations and the rest is reported
     dev = float(np.max(devs[:100]))
     assert dev < 1e-9, f"host-vector and device-resident runs disagree: {dev:.3e}"
-    e2e = {"value": world * args.steps / e2e_s, "unit": "it/s", "h2d_bytes_per_step": up // args.steps,
-           "d2h_bytes_per_step": down // args.steps, "ms_per_step": e2e_s / args.steps * 1e3,
-           "max_rel_dF_vs_device_arm": float(np.max(devs)),
-           "how": "ABPG call sequence with NumPy vectors through f()/f.gradient()/h.div_prox_map()/h.divergence(); "
-                  "H stays bound to the operator (as f.H does in the reference)"}
+    return {"value": B.world * args.steps / e2e_s, "unit": "it/s", "h2d_bytes_per_step": up // args.steps,
+            "d2h_bytes_per_step": down // args.steps, "ms_per_step": e2e_s / args.steps * 1e3,
+            "max_rel_dF_vs_device_arm": float(np.max(devs)),
+            "how": "ABPG call sequence with NumPy vectors through f()/f.gradient()/h.div_prox_map()/h.divergence(); "
+                   "H stays bound to the operator (as f.H does in the reference)"}
 
-    # ---- second headline algorithm of this config: D_opt_FW_away (HBM-bound pass over V) --------------------
-    extra = {}
-    if world == 1:
-        # iterations/s without the per-kernel events (they sit between the launches and break their programmatic
-        # chaining), then a second run with them for the pass kernel's own duration
-        xa, Fa, SPa, SNa, Ta = acc.D_opt_FW_away(f._Hd, x0, 1e-12, 1500, verbose=False)
-        if len(Ta) > 1:
-            extra["fw_away_it_per_s"] = (len(Ta) - 1) / (Ta[-1] - Ta[0])
-        lib.accbpg_prof_enable(1)
-        prof_read()
-        acc.D_opt_FW_away(f._Hd, x0, 1e-12, 300, verbose=False)
-        kfw = prof_read()
-        lib.accbpg_prof_enable(0)
-        p = kfw.get("fw_pass_kernel")
-        if p:
-            gbs = 8.0 * m * n / (p["ms_avg"] * 1e-3) / 1e9
-            extra["fw_pass_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                                         "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                                         "ms_avg": p["ms_avg"], "bytes_per_launch": 8 * m * n,
-                                         "note": "V (200 MB) exceeds the 126 MB L2; launch, the u broadcast and the selection / "
-                                                 "decision tail are inside this duration (about 8 us of the 47)"}
-        it = kfw.get("fw_iteration(5 kernels)")
-        if it:
-            extra["fw_iteration_ms_avg"] = it["ms_avg"]
 
-    # ---- roofline of the dominant kernel ---------------------------------------------------------------------
-    syrk = kern.get("syrk_dmma_kernel")
-    roof = None
+def run_rooflines(B, head):
+    """roofline of the dominant kernel (SYRK) from the timed region; the triangular GEMM timed alone afterwards."""
+    lib, f, x0 = B.lib, B.f, B.x0
+    kern, m, n = head["kern"], M_ROWS, N_PER_GPU
     traffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")))
     except Exception:
         pass
+    roof = None
+    syrk = kern.get("syrk_tma_kernel")
     if syrk:
         flops = float(m) * m * n                     # algorithmic SYRK count of SURVEY 8(d): m^2 n per launch
         tf = flops / (syrk["ms_avg"] * 1e-3) / 1e12
-        tr = traffic.get("syrk_kernel", {})
+        tr = traffic.get("syrk_tma_kernel", {})
         roof = {"bound": "tensor", "kernel": "syrk_tma_kernel (FP64 DMMA.8x8x4 fed by a TMA + mbarrier pipeline)",
-                "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                "achieved": tf, "peak": B.fp64_peak, "unit": "TFLOP/s", "frac": tf / B.fp64_peak,
                 "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
                 "algorithmic_bytes_per_launch": 8 * m * n,
                 "flops_per_launch": flops, "ms_avg": syrk["ms_avg"], "launches": syrk["launches"],
                 "peak_source": "torch.matmul float64 8192^3 burst measured in this run "
                                "(MEASURED_PEAKS.json records no FP64 figure); the bare DMMA issue rate measured by "
                                "tools/pipe_probe.cu on this pool is 37.1 TFLOP/s"}
-    trmm = kern.get("trmm_colnorm_kernel")
-    if trmm is None and world == 1:
+    trmm_roof = None
+    if B.world == 1:
         # inside the timed iterations the triangular GEMM runs under the Cholesky chain and has no interval of its own
         # (factor_gradient_interval_ms covers both); time it alone over a few gradient evaluations with the overlap off
         # (ACCBPG_OVERLAP is read at every call), outside the timed region
+        trmm = None
         try:
             os.environ["ACCBPG_OVERLAP"] = "0"
             lib.accbpg_prof_enable(1)
-            prof_read()
+            B.prof_read()
             for _ in range(5):
                 f.gradient(x0)
-            trmm = prof_read().get("trmm_colnorm_kernel")
-        except Exception:
-            trmm = None
+            pr = B.prof_read()
+            trmm = pr.get("trmm_persistent_kernel")
+            chain = pr.get("chol_inv_step_kernel(all block columns)")
         finally:
             lib.accbpg_prof_enable(0)
             os.environ.pop("ACCBPG_OVERLAP", None)
-    if trmm:
-        flops = float(m) * m * n                     # triangular solve-as-GEMM: m^2 n per launch
-        tf = flops / (trmm["ms_avg"] * 1e-3) / 1e12
-        extra_roof = {"bound": "tensor", "kernel": "trmm_persistent_kernel (L^-1 H with fused column norms, TMA + mbarrier ring, dedicated producer warp)", "achieved": tf,
-                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
-                      "traffic": traffic.get("trmm_colnorm_kernel", {}).get("dram_bytes_per_launch"),
-                      "flops_per_launch": flops, "ms_avg": trmm["ms_avg"], "launches": trmm["launches"],
-                      "note": "timed alone (overlap with the Cholesky chain switched off) after the timed region"}
-    else:
-        extra_roof = None
-    step_ms = {k: v["ms_total"] / args.steps for k, v in kern.items()}
+        if trmm:
+            flops = float(m) * m * n                 # triangular solve-as-GEMM: m^2 n per launch (SURVEY 8d)
+            tf = flops / (trmm["ms_avg"] * 1e-3) / 1e12
+            trmm_roof = {"bound": "tensor", "kernel": "trmm_persistent_kernel (L^-1 H with fused column norms, TMA + mbarrier "
+                                                      "ring, dedicated producer warp)",
+                         "achieved": tf, "peak": B.fp64_peak, "unit": "TFLOP/s", "frac": tf / B.fp64_peak,
+                         "traffic": traffic.get("trmm_persistent_kernel", {}).get("dram_bytes_per_launch"),
+                         "flops_per_launch": flops, "ms_avg": trmm["ms_avg"], "launches": trmm["launches"],
+                         "chol_inv_chain_ms_alone": chain["ms_avg"] if chain else None,
+                         "note": "timed alone (overlap with the Cholesky chain switched off) after the timed region"}
+    return roof, trmm_roof
 
-    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -------------------------------
+
+# ---- extras: the other BASELINE.json configurations -----------------------------------------------------------------
+def extra_c2(B):
+    """Second headline algorithm of configs[1] (D_opt_FW_away: HBM-bound pass over V) and ABPG_gain on the same instance."""
+    acc, lib, f, x0 = B.acc, B.lib, B.f, B.x0
+    m, n = M_ROWS, N_PER_GPU
+    out = {}
+    # iterations/s without the per-kernel events (they sit between the launches and break their programmatic
+    # chaining), then a second run with them for the pass kernel's own duration
+    xa, Fa, SPa, SNa, Ta = acc.D_opt_FW_away(f._Hd, x0, 1e-12, 1500, verbose=False)
+    if len(Ta) > 1:
+        out["fw_away_it_per_s"] = (len(Ta) - 1) / (Ta[-1] - Ta[0])
+    lib.accbpg_prof_enable(1)
+    B.prof_read()
+    acc.D_opt_FW_away(f._Hd, x0, 1e-12, 300, verbose=False)
+    kfw = B.prof_read()
+    lib.accbpg_prof_enable(0)
+    p = kfw.get("fw_pass_kernel")
+    if p:
+        gbs = 8.0 * m * n / (p["ms_avg"] * 1e-3) / 1e9
+        out["fw_pass_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": B.hbm, "unit": "GB/s", "frac": gbs / B.hbm,
+                                   "ms_avg": p["ms_avg"], "bytes_per_launch": 8 * m * n, "peak_source": B.hbm_source}
+    it = kfw.get("fw_iteration")
+    if it:
+        out["fw_iteration_ms_avg"] = it["ms_avg"]
+    acc.ABPG_gain(f, B.h, 1.0, x0, gamma=GAMMA, maxitrs=5, verbose=False)
+    res, ms = B.timed(lambda: acc.ABPG_gain(f, B.h, 1.0, x0, gamma=GAMMA, maxitrs=60, verbose=False), collective=False)
+    out["abpg_gain"] = {"iterations": len(res[1]), "ms_per_iteration": ms / len(res[1]),
+                        "it_per_s": len(res[1]) / (ms * 1e-3)}
+    return out
+
+
+def extra_c1(B):
+    """configs[0]: D_opt_design(80, 200) solved by BPG with line search, 1000 iterations (latency bound)."""
+    acc = B.acc
+    f, h, L, x0 = acc.D_opt_design(80, 200, randseed=10)
+    acc.BPG(f, h, L, x0, maxitrs=50, verbose=False)
+    t0 = time.perf_counter()
+    x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=1000, verbose=False)
+    wall = time.perf_counter() - t0
+    return {"workload": "D_opt_design(80,200,randseed=10), BPG linesearch=True ls_ratio=1.2, maxitrs=1000, host x0",
+            "iterations": len(F), "it_per_s": (len(T) - 1) / (T[-1] - T[0]), "wall_s": wall, "F_last": float(F[-1]),
+            "L_last": float(Ls[-1])}
+
+
+def c5_slab(B, lo, hi):
+    """Columns [lo, hi) of the C5 instance: 8 slabs of 125000 columns, each from its own device generator, so the
+    instance does not depend on the number of ranks."""
+    torch = B.torch
+    per = C5_N // C5_SLABS
+    H = torch.empty(C5_M, hi - lo, dtype=torch.float64, device=B.dev)
+    for sl in range(C5_SLABS):
+        a, b = sl * per, (sl + 1) * per
+        if b <= lo or a >= hi:
+            continue
+        gen = torch.Generator(device=B.dev)
+        gen.manual_seed(100 + sl)
+        slab = torch.randn(C5_M, per, dtype=torch.float64, device=B.dev, generator=gen)
+        H[:, max(lo, a) - lo: min(hi, b) - lo] = slab[:, max(lo, a) - a: min(hi, b) - a]
+        del slab
+    return H
+
+
+def c5_run(B, shard, iters, kernel_times):
+    """ABPG_gain(gamma=2) on (this rank's slab of) the C5 instance.  Returns the result dict."""
+    acc, lib, torch = B.acc, B.lib, B.torch
+    m, n = C5_M, C5_N
+    lo, hi = (shard.lo, shard.hi) if shard is not None else (0, n)
+    H = c5_slab(B, lo, hi)
+    f = acc.DOptimalObj(H, shard=shard)
+    h = acc.BurgEntropySimplex(shard=shard)
+    x0 = torch.full((hi - lo,), 1.0 / n, dtype=torch.float64, device=B.dev)
+    coll = shard is not None
+    acc.ABPG_gain(f, h, 1.0, x0, gamma=GAMMA, maxitrs=2, verbose=False)
+    res, ms = B.timed(lambda: acc.ABPG_gain(f, h, 1.0, x0, gamma=GAMMA, maxitrs=iters, verbose=False), collective=coll)
+    x, F, Gain, Gdiv, Gavg, T = res
+    out = {"iterations": len(F), "ms_per_iteration": ms / len(F), "it_per_s": len(F) / (ms * 1e-3),
+           "columns_per_gpu": hi - lo, "F": [float(v) for v in F], "gain": [float(v) for v in Gain]}
+    if kernel_times:
+        # per-kernel durations with the triangular GEMM serialised behind the Cholesky chain (events between the launches)
+        k_it = iters
+        os.environ["ACCBPG_OVERLAP"] = "0"
+        try:
+            lib.accbpg_prof_enable(1)
+            B.prof_read()
+            acc.ABPG_gain(f, h, 1.0, x0, gamma=GAMMA, maxitrs=k_it, verbose=False)
+            kern = B.prof_read()
+        finally:
+            lib.accbpg_prof_enable(0)
+            os.environ.pop("ACCBPG_OVERLAP", None)
+        syrk, trmm = kern.get("syrk_tma_kernel"), kern.get("trmm_persistent_kernel")
+        chain = kern.get("chol_inv_step_kernel(all block columns)")
+        fl = float(m) * m * (hi - lo)
+        if syrk and trmm:
+            # executed oracle work per iteration of the timed run: the driver's call counts are the same in both runs
+            # (same instance, same decisions), so launches / k_it are per-iteration counts
+            per_it = (syrk["launches"] + trmm["launches"]) / k_it
+            chains_per_it = (chain["launches"] / k_it) if chain else 0.0
+            executed = per_it * fl + chains_per_it * (m ** 3 / 3.0)
+            tfs = executed / (out["ms_per_iteration"] * 1e-3) / 1e12
+            out.update({
+                "line_search_trips_per_iteration": trmm["launches"] / k_it,
+                "syrk_launches_per_iteration": syrk["launches"] / k_it,
+                "syrk_ms": syrk["ms_avg"], "syrk_tflops": fl / syrk["ms_avg"] / 1e9,
+                "syrk_frac": fl / syrk["ms_avg"] / 1e9 / B.fp64_peak,
+                "trmm_ms": trmm["ms_avg"], "trmm_tflops": fl / trmm["ms_avg"] / 1e9,
+                "trmm_frac": fl / trmm["ms_avg"] / 1e9 / B.fp64_peak,
+                "chol_inv_chain_ms": chain["ms_avg"] if chain else None,
+                "chol_inv_chains_per_iteration": chains_per_it,
+                "executed_tflops_whole_iteration": tfs,
+                "executed_frac_of_fp64_roof_whole_iteration": tfs / B.fp64_peak,
+                "exchange_ms": {k: v["ms_avg"] for k, v in kern.items()
+                                if k.startswith(("syrk_reduce_push", "gram_sum", "burg_prepare_push", "peer_wait", "peer_sum"))},
+            })
+    del f, h, H, x, res
+    B.free()
+    return out
+
+
+def extra_c5(B):
+    """configs[4] / north_star target: D-opt 2000 x 1 000 000, ABPG_gain gamma=2.  N = 1: the whole 16 GB instance on
+    one GPU.  N > 1: strong scaling, n/N columns per rank, and rank 0 alone also times the whole instance on its own
+    GPU in this process so the line carries the ratio of the two."""
+    acc, torch = B.acc, B.torch
+    iters = B.args.c5_iters
+    out = {"workload": f"D-opt {C5_M}x{C5_N} (8 device-generated slabs, seeds 100..107), ABPG_gain gamma=2, x0=1/n, L=1, "
+                       f"BurgEntropySimplex, {iters} iterations"}
+    if B.world == 1:
+        out.update(c5_run(B, None, iters, True))
+        out["n_gpus"] = 1
+        return out
+    shard = acc.ColumnShard(C5_N)
+    sh = c5_run(B, shard, iters, True)
+    out.update(sh)
+    out["n_gpus"] = B.world
+    out["scaling"] = "strong"
+    single = None
+    if B.rank == 0 and not B.args.no_c5_single:
+        single = c5_run(B, None, iters, False)
+    B.barrier()
+    if single is not None:
+        Fs, Fn = np.array(single["F"]), np.array(sh["F"])
+        k = min(len(Fs), len(Fn))
+        fork = next((i for i in range(k) if single["gain"][i] != sh["gain"][i]), k)
+        out["single_gpu_ms_per_iteration_same_run"] = single["ms_per_iteration"]
+        out["speedup_vs_single_gpu"] = single["ms_per_iteration"] / sh["ms_per_iteration"]
+        out["strong_scaling_efficiency"] = single["ms_per_iteration"] / sh["ms_per_iteration"] / B.world
+        out["sharded_vs_single_max_rel_dF"] = float(np.max(np.abs(Fs[:k] - Fn[:k]) / np.abs(Fs[:k])))
+        out["sharded_vs_single_first_gain_fork"] = fork
+    return out
+
+
+def linreg_extra(B, kind, m, n, seed, iters, label):
+    """C3 / C4-slab: device-generated instance (applications.py:116-132, :192-204 shapes), ABPG_gain, GEMV-pair rooflines."""
+    acc, lib, torch = B.acc, B.lib, B.torch
+    gen = torch.Generator(device=B.dev)
+    gen.manual_seed(seed)
+    A = torch.rand(m, n, dtype=torch.float64, device=B.dev, generator=gen)
+    A /= A.sum(dim=0, keepdim=True)                                   # columns sum to one (applications.py:194-196)
+    if kind == "kl":
+        xs = torch.rand(n, dtype=torch.float64, device=B.dev, generator=gen)
+        xs /= xs.sum()
+        b = (A @ xs) * (1 + 0.01 * (torch.rand(m, dtype=torch.float64, device=B.dev, generator=gen) - 0.5))
+        f, h, L = acc.KLdivRegression(A, b), acc.ShannonEntropySimplex(), 1.0
+        x0 = torch.full((n,), 1.0 / n, dtype=torch.float64, device=B.dev)
+    else:
+        xt = torch.clamp(torch.rand(n, dtype=torch.float64, device=B.dev, generator=gen) / n - 0.5 / n, min=0) * 10
+        b = A @ xt + 1e-6 * torch.rand(m, dtype=torch.float64, device=B.dev, generator=gen)
+        f, h, L = acc.PoissonRegression(A, b), acc.BurgEntropyL1(lamda=1e-3), float(b.sum())
+        x0 = torch.full((n,), 10.0 / n, dtype=torch.float64, device=B.dev)
+    acc.ABPG_gain(f, h, L, x0, gamma=2.0, maxitrs=2, verbose=False)
+    lib.accbpg_prof_enable(1)
+    B.prof_read()
+    res, ms = B.timed(lambda: acc.ABPG_gain(f, h, L, x0, gamma=2.0, maxitrs=iters, verbose=False), collective=False)
+    kern = B.prof_read()
+    lib.accbpg_prof_enable(0)
+    F = res[1]
+    mv, rmv = kern.get("matvec_kernel"), kern.get("rmatvec_kernel")
+    byt = 8.0 * m * n
+    out = {"workload": label, "iterations": len(F), "ms_per_iteration": ms / len(F), "it_per_s": len(F) / (ms * 1e-3),
+           "passes_over_A_per_iteration": ((mv["launches"] if mv else 0) + (rmv["launches"] if rmv else 0)) / len(F),
+           "F_first_last": [float(F[0]), float(F[-1])]}
+    for nm, k in (("matvec", mv), ("rmatvec", rmv)):
+        if k:
+            gbs = byt / (k["ms_avg"] * 1e-3) / 1e9
+            out[nm + "_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": B.hbm, "unit": "GB/s", "frac": gbs / B.hbm,
+                                     "ms_avg": k["ms_avg"], "launches": k["launches"], "bytes_per_launch": byt,
+                                     "peak_source": B.hbm_source}
+    del f, h, A, res
+    B.free()
+    return out
+
+
+def sharded_parity(B, head):
+    """N > 1: rank 0 runs the same 500 x (50000 N) instance unsharded on its own GPU for the K iterations of the timed
+    solve and compares trajectories; the same for the vertex sequence of the column-sharded D_opt_FW_away."""
+    acc, torch, args = B.acc, B.torch, B.args
+    world, rank = B.world, B.rank
+    n_total = N_PER_GPU * world
+    out = {}
+    fw_iters = 200
+    glog = []
+    xa, Fa, SPa, SNa, Ta = acc.D_opt_FW_away(B.f._Hd, B.x0, 1e-12, fw_iters, verbose=False, shard=B.shard, index_log=glog)
+    B.barrier()
+    if rank == 0:
+        H = np.concatenate([make_slab(r, N_PER_GPU) for r in range(world)], axis=1)
+        Hd = torch.tensor(H, device=B.dev)
+        del H
+        f1 = acc.DOptimalObj(Hd)
+        h1 = acc.BurgEntropySimplex()
+        x01 = torch.full((n_total,), 1.0 / n_total, dtype=torch.float64, device=B.dev)
+        x1, F1, G1, T1 = acc.ABPG(f1, h1, 1.0, x01, gamma=GAMMA, maxitrs=args.steps, verbose=False)
+        F = head["F"]
+        k = min(len(F), len(F1))
+        out["sharded_vs_single_max_rel_dF"] = float(np.max(np.abs(F[:k] - F1[:k]) / np.abs(F1[:k])))
+        out["sharded_vs_single_iterations"] = k
+        slog = []
+        xb, Fb, SPb, SNb, Tb = acc.D_opt_FW_away(Hd, x01, 1e-12, fw_iters, verbose=False, index_log=slog)
+        kk = min(len(glog), len(slog))
+        same = [(a[0], a[1], a[2]) for a in glog[:kk]] == [(a[0], a[1], a[2]) for a in slog[:kk]]
+        out["fw_away_vertex_sequence_identical"] = bool(same and len(glog) == len(slog))
+        out["fw_away_iterations_compared"] = kk
+        out["fw_away_max_rel_dF"] = float(np.max(np.abs(Fa[:kk] - Fb[:kk]) / np.abs(Fb[:kk])))
+        del f1, h1, Hd
+        B.free()
+    B.barrier()
+    if rank == 0:
+        assert out["sharded_vs_single_max_rel_dF"] <= 1e-11, out
+        assert out["fw_away_vertex_sequence_identical"], out
+    return out
+
+
+def native_arm(args, rank, local_rank, world):
+    B = Bench(args, rank, local_rank, world)
+    torch = B.torch
+    B.fp64_peak = measure_fp64_peak(torch) if not args.lean else float("nan")
+    head = run_headline(B)
+    if args.lean:
+        if rank == 0:
+            print(json.dumps({"lean": True, "ms_per_step": head["ms_per_step"], "value": head["value"],
+                              "gpu_launches": head["launches"], "reps": head["reps"],
+                              "kernel_ms_per_step": {k: v["ms_total"] / head["timed_steps"] for k, v in head["kern"].items()}}))
+        return
+    e2e = run_e2e(B, head)
+    roof, trmm_roof = run_rooflines(B, head)
+    extra = {}
+    if world > 1:
+        extra["parity"] = sharded_parity(B, head)
+        ex = {k: v["ms_total"] / head["timed_steps"] for k, v in head["kern"].items()
+              if k.startswith(("syrk_reduce_push", "gram_sum", "burg_prepare_push", "peer_wait", "peer_sum", "burg_simplex"))}
+        extra["exchange_ms_per_step"] = ex
+    else:
+        extra["c2"] = extra_c2(B)
+        extra["c1"] = extra_c1(B)
+    # CPU baseline (rank 0, N = 1 only): bounded sample of the same workload, before the big instances take the memory
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        per_it, Fc = run_cpu_abpg(Hh, args.cpu_iters)
+        cores = set_cpu_threads()
+        per_it, Fc, kind = cpu_abpg(B.Hh, args.cpu_iters)
+        F = head["F"]
         kk = min(len(Fc), len(F))
-        cpu = {"value": 1.0 / per_it, "unit": "it/s", "cores": cpu_threads(), "kind": "port",
-               "sample": f"{args.cpu_iters} ABPG iterations of the NumPy oracle port on the same {m}x{n} instance "
-                         f"(os.cpu_count()={os.cpu_count()}); F agrees with the GPU run to "
-                         f"{float(np.max(np.abs(Fc[:kk] - F[:kk]) / np.abs(Fc[:kk]))):.1e} over {kk} iterations"}
-
+        cpu = {"value": 1.0 / per_it, "unit": "it/s", "cores": cores, "kind": kind,
+               "sample": f"{args.cpu_iters} ABPG iterations of "
+                         f"{'the unmodified reference package (oracle/_ref)' if kind == 'reference' else 'the NumPy oracle port'} "
+                         f"on the same {M_ROWS}x{N_PER_GPU} instance (os.cpu_count()={os.cpu_count()}); F agrees with the "
+                         f"GPU run to {float(np.max(np.abs(Fc[:kk] - F[:kk]) / np.abs(Fc[:kk]))):.1e} over {kk} iterations"}
+    # release the headline instance before the large configurations
+    B.f = B.h = None
+    B.free()
+    if not args.no_extra:
+        extra["c5"] = extra_c5(B)
+        if world == 1:
+            extra["c3"] = linreg_extra(B, "kl", 20000, 200000, 3, 30,
+                                       "KL regression 20000x200000 (32 GB, device-generated, columns normalised, x* on the "
+                                       "simplex) + ShannonEntropySimplex, ABPG_gain gamma=2, 30 iterations")
+            extra["c4_slab"] = linreg_extra(B, "poisson", 100000, 125000, 4, 10,
+                                            "Poisson regression 100000x125000 (100 GB: the per-GPU column slab of the "
+                                            "8-GPU 100000x1000000 shape) + BurgEntropyL1(1e-3), ABPG_gain gamma=2, "
+                                            "10 iterations")
     if rank == 0:
+        kern, T = head["kern"], head["T"]
         line = {
-            "metric": "abpg_gamma2_iterations_per_sec", "value": value,
-            "unit": "it/s (x N slabs of 500x50000 under weak scaling)", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": "abpg_gamma2_iterations_per_sec", "value": head["value"], "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "reps": head["reps"], "timed_steps": head["timed_steps"],
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"D-opt {m}x{n * world} (H=randn, seed 1+rank per {m}x{n} slab), ABPG gamma=2, "
-                                   f"x0=1/n, L=1, BurgEntropySimplex",
+            "config": {"workload": workload_text(world),
                        "l2": "H slab is 200 MB per GPU (> 126 MB L2); no flush needed",
                        "calls_per_step": "1 f(x) + 1 grad f(y) + 1 div_prox_map + 2 axpby + 2 divergence "
                                          "(f(x_k), f(y_k) are evaluated from Gram matrices carried along the "
                                          "iterates, so one SYRK per iteration: accbpg_and_fw_b200/config.py)",
-                       "timing": "CUDA events on the launch stream around the K-iteration solve, max over ranks"},
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "kernel_ms_per_step": step_ms, "extra": extra, "roofline_trmm": extra_roof,
+                       "timing": "CUDA events on the launch stream around `reps` back-to-back K-iteration solves, max "
+                                 "over ranks; ms_per_step = total / (reps * K)"},
+            "clocks": head["clocks"], "e2e": e2e, "gpu_launches": head["launches"], "roofline": roof, "cpu_baseline": cpu,
+            "kernel_ms_per_step": {k: v["ms_total"] / head["timed_steps"] for k, v in kern.items()},
+            "extra": extra, "roofline_trmm": trmm_roof,
             "factor_gradient_interval_ms": (kern.get("factor+gradient interval (chain with overlapped triangular GEMM)")
                                             or {}).get("ms_avg"),
             "it_per_s_from_T": (len(T) - 1) / (T[-1] - T[0]) if len(T) > 1 else None,
@@ -388,6 +761,11 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-iters", type=int, default=20, help="iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the large configurations (c5, c3, c4_slab)")
+    ap.add_argument("--no-c5-single", action="store_true", help="N > 1: do not time the whole C5 instance on rank 0")
+    ap.add_argument("--c5-iters", type=int, default=20)
+    ap.add_argument("--min-timed-ms", type=float, default=300.0,
+                    help="the timed region repeats the K-step solve until it is at least this long")
     ap.add_argument("--lean", action="store_true",
                     help="device-resident arm only (no FP64 probe, e2e, FW or CPU legs): the command profiled under ncu")
     args = ap.parse_args()

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ACCBPG_ABI_VERSION 1
+#define ACCBPG_ABI_VERSION 2
 
 /* return codes */
 #define ACCBPG_OK      0
@@ -155,11 +155,17 @@ int accbpg_burg_simplex_push_peer(void* ctx, void* stream, int64_t n_local, int6
                                   void* const* peer_flags, uint64_t epoch, double* d_gg_local);
 int accbpg_burg_simplex_root_peer(void* ctx, void* stream, int64_t width, double eps, int rank, int world,
                                   void* const* peer_gg, void* const* peer_flags, uint64_t epoch, double* d_info);
-/* Sum `count` (<= 16) per-rank partial scalars at d_vals over the ranks through peer memory, in rank order, in place
- * (the batched divergence / dot-product partials of a driver iteration, algorithms.py:53,153-154,...): one small kernel
- * instead of an NCCL all-reduce.  peer_tab: every rank's 2*world*16 doubles; peer_flags: world uint64, zeroed once. */
-int accbpg_peer_sum_scalars(void* ctx, void* stream, double* d_vals, int count, int rank, int world,
+/* Sum `count` (<= 15) per-rank partial scalars at d_in over the ranks through peer memory, in rank order, into d_out
+ * (may equal d_in) (the batched divergence / dot-product partials of a driver iteration, algorithms.py:53,153-154,...):
+ * one small kernel instead of an NCCL all-reduce.  The exchange also carries every rank's status word and ORs them into
+ * the local one, so an assertion of the reference that fails on one rank's slice is raised on every rank at the same
+ * read.  peer_tab: every rank's 2*world*16 doubles; peer_flags: world uint64, zeroed once. */
+int accbpg_peer_sum_scalars(void* ctx, void* stream, const double* d_in, double* d_out, int count, int rank, int world,
                             void* const* peer_tab, void* const* peer_flags, uint64_t epoch);
+/* The same status exchange for the NCCL / gloo fallback: export writes the status word as a float64 into d_slot (which
+ * the caller all-reduces with max), import ORs the reduced value back into the local status word. */
+int accbpg_ctx_status_export(void* ctx, void* stream, double* d_slot);
+int accbpg_ctx_status_import(void* ctx, void* stream, const double* d_slot);
 /* The column-sharded LMO's reduction (functions_lmo.py:153-158 with the columns split over ranks): the lowest
  * (value, global index) pair over the ranks, ties to the lowest index, in place on the two doubles at d_pair.  Tables
  * as accbpg_peer_sum_scalars. */

@@ -23,38 +23,10 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "g
 
 
 def import_reference(ref_root=REF_ROOT):
-    """Import the reference package with stubbed optional dependencies."""
-    class _Anything:
-        def __init__(self, *a, **k):
-            pass
-
-        def __call__(self, *a, **k):
-            if len(a) == 1 and callable(a[0]) and not k:
-                return a[0]          # used as a decorator: hand the function back
-            return _Anything()
-
-        def __getattr__(self, name):
-            return _Anything()
-
-    def _stub(name, **attrs):
-        mod = types.ModuleType(name)
-        mod.__getattr__ = lambda attr: _Anything()
-        for key, val in attrs.items():
-            setattr(mod, key, val)
-        sys.modules.setdefault(name, mod)
-        return sys.modules[name]
-
-    _stub("cvxpy")
-    jax = _stub("jax")
-    jax.numpy = _stub("jax.numpy")
-    jax.scipy = _stub("jax.scipy")
-    jax.scipy.linalg = _stub("jax.scipy.linalg", cholesky=_Anything())
-    mpl = _stub("matplotlib")
-    mpl.pyplot = _stub("matplotlib.pyplot", __all__=[])
-    if ref_root not in sys.path:
-        sys.path.insert(0, ref_root)
-    import accbpg  # noqa
-    return accbpg
+    """Import the reference package with stubbed optional dependencies (oracle/ref_loader.py)."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ref_loader
+    return ref_loader.import_reference(ref_root)
 
 
 def quiet(fn, *a, **k):

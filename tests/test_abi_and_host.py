@@ -163,6 +163,8 @@ assert torch.equal(got, full) and torch.isinf(allv).sum().item() == sh.width * w
 from accbpg_and_fw_b200.dist import peer_buffers
 assert peer_buffers(sh, torch.device("cpu"), [(16, torch.float64), (2, torch.int64)]) is None
 assert peer_buffers(None, torch.device("cpu"), [(16, torch.float64)]) is None
+# ... and so does the scalar exchange that also carries the status words (drivers then use all-reduce sum + max)
+assert sh.sum_scalars_into(t, t) is False
 dist.destroy_process_group()
 print("ok", rank)
 '''
@@ -194,5 +196,7 @@ def test_bench_reference_arm_contract():
     for key in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
                 "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_loader
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_loader.locate() else "port")
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)      # set explicitly, whatever the launcher exported
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0

@@ -147,17 +147,30 @@ def test_scalar_sums_over_peer_buffers_emulated_ranks(acc, world):
         t_tab, t_flags = _table(tab), _table(flags)
         for epoch in range(1, 8):
             parts = [torch.randn(count, dtype=F64, device=dev, generator=gen) * 10.0 ** (r % 3) for r in range(world)]
-            vals = [p.clone() for p in parts]
+            vals = [torch.zeros(count, dtype=F64, device=dev) for _ in parts]
             torch.cuda.synchronize()
+            if epoch == 3:
+                # a precondition fails on the LAST rank's slice only (Burg divergence of a non-positive vector):
+                # the exchange must hand its status bit to every rank
+                bad = torch.tensor([-1.0, 1.0], dtype=F64, device=dev)
+                with torch.cuda.stream(ranks[-1].stream):
+                    nat.check(lib.accbpg_burg_divergence(ranks[-1].ctx, ranks[-1].stream.cuda_stream, 2, bad.data_ptr(),
+                                                         bad.data_ptr(), parts[-1].data_ptr()))
+                parts[-1].fill_(1.0)
+                torch.cuda.synchronize()
             for r in range(world):
-                nat.check(lib.accbpg_peer_sum_scalars(ranks[r].ctx, ranks[r].stream.cuda_stream, vals[r].data_ptr(), count,
-                                                      r, world, t_tab, t_flags, epoch))
+                nat.check(lib.accbpg_peer_sum_scalars(ranks[r].ctx, ranks[r].stream.cuda_stream, parts[r].data_ptr(),
+                                                      vals[r].data_ptr(), count, r, world, t_tab, t_flags, epoch))
             torch.cuda.synchronize()
             ref = np.zeros(count)
             for r in range(world):                           # rank order, as the kernel adds them
                 ref = ref + parts[r].cpu().numpy()
+            hb = (ctypes.c_double * 4)()
             for r in range(world):
                 assert np.array_equal(vals[r].cpu().numpy(), ref), (epoch, r)
+                st = ctypes.c_uint32(0)
+                nat.check(lib.accbpg_ctx_read(ranks[r].ctx, ranks[r].stream.cuda_stream, None, 0, None, ctypes.byref(st)))
+                assert st.value == (nat.ST["ARG_NOT_POS"] if epoch == 3 else 0), (epoch, r, st.value)
     finally:
         torch.cuda.synchronize()
         for rk in ranks:

@@ -113,7 +113,7 @@ if "c5" in which:
     os.environ["ACCBPG_OVERLAP"] = "1"
     (res, ms) = timed(lambda: acc.ABPG_gain(f, h, 1.0, x0, gamma=2, maxitrs=iters, verbose=False))
     x, F, Gain, Gdiv, Gavg, T = res
-    syrk, trmm = kern.get("syrk_dmma_kernel"), kern.get("trmm_colnorm_kernel")
+    syrk, trmm = kern.get("syrk_tma_kernel"), kern.get("trmm_persistent_kernel")
     flops_kernel = float(m) * m * n
     # executed oracle work of the run: every SYRK and every triangular GEMM is m^2 n, every factorisation m^3/3 (x2 with the inverse)
     executed = (syrk["launches"] + trmm["launches"]) * flops_kernel
