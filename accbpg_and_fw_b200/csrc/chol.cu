@@ -15,6 +15,7 @@
 // and no serial chain beyond the factorisation's.  Tiles are written by exactly one CTA and the block column J that a
 // launch reads is never written in it, so the trailing matrix is updated in place.
 #include <functional>
+#include <map>
 #include "dmma.cuh"
 
 namespace accbpg {
@@ -526,6 +527,475 @@ __global__ void __launch_bounds__(256, 1) chol_inv_step_kernel(CholStep p) {
     acc_to_global<true>(tmp, p.Linv, p.mp, j0, r * CB, p.mp, p.mp, wm, wn, g, t);
 }
 
+
+// ==================================================================================================================
+// Data-flow form of the same chain: TWO launches for the whole factorisation + inverse instead of one per block column.
+//
+//   spine kernel (one CTA)   for J = 0 .. nb-1:  [J > 0: L[J,J-1] = W[J,J-1] X_{J-1}^T,  W[J,J] -= L[J,J-1] L[J,J-1]^T]
+//                            then the serial part: L_JJ and X_J = L_JJ^{-1} (the same in-warp 32x32 pieces as above).
+//                            The critical path of the factorisation never leaves this CTA's shared memory.
+//   worker kernel            every other 64x64 tile job, claimed from a counter in topological order:
+//        T(J,R)    L[R,J]   = W[R,J] X_J^T                      R > J+1
+//        U(J;R,C)  W[R,C]  -= L[R,J] L[C,J]^T                   J < C <= R, (R,C) != (J+1,J+1)
+//        F(J,r)    Linv[J,r] = X_J Y[J,r]                       r < J
+//        V(K;C,r)  Y[C,r]  -= L[C,K] Linv[K,r]                  r <= K < C
+//   Each job waits for its operands on per-tile progress counters in global memory (ld.acquire / st.release at GPU
+//   scope): every tile's updates are applied in the fixed order J = 0, 1, 2, ..., so the result does not depend on
+//   which CTA runs which job or when (bit-reproducible, and bit-identical to the launch-per-column kernel above, which
+//   does the same arithmetic in the same order).  A job only ever waits for jobs with a lower number or for the spine,
+//   and jobs are claimed in increasing order by CTAs that are running, so the scheme cannot deadlock whatever share of
+//   the GPU the workers get; the worker launch is programmatically dependent on the spine launch, which releases it
+//   with its first instruction, so the spine is resident before any worker can wait for it.
+//   Counters carry the call's epoch in their upper bits (kept per aux block on the host; the last worker to leave
+//   re-arms the job counter): no memset between calls.  The aux block and Linv must be zero when first used (the
+//   workspace is zero-initialised once by its owner); Linv's strictly upper part is never written, so it stays zero
+//   from call to call.  The triangular GEMM reads the same counters to start on row blocks of L^-1 as they become final.
+constexpr int DF_MAXNB = 64;
+constexpr int DF_AUX_HEAD = 16;                 // ints: [1] job counter, [2] workers that have left, [3] spine done
+constexpr int DF_WORKER_SMEM = 2 * CBUF * 8;
+constexpr int DF_SPINE_SMEM = (5 * CBUF + 64 + 96) * 8;      // > half an SM's shared memory: the spine has its SM alone
+
+struct DfParams {
+    const double* M;     // input matrix (only read)
+    double* W;           // trailing matrix / L panels, ld = m
+    double* L;           // optional output
+    double* Y;           // ld = mp
+    double* Linv;        // ld = mp
+    double* X;           // nb blocks of 64 x 64 (ld 64): X_J as published by the spine
+    double* d_out;
+    uint32_t* status;
+    int* aux;            // DF_AUX_HEAD ints, then cW[nb*nb], cY[nb*nb], fLi[nb*nb], fX[nb]
+    int m, mp, nb, want_inv, njobs, nworkers, epoch;
+    int step_off[DF_MAXNB + 1];
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// wait until the counter at p carries this call's epoch and a count >= want; bounded (a protocol error traps after 2 s
+// instead of hanging the GPU)
+__device__ __forceinline__ void df_wait(const int* p, int epoch, int want) {
+    if (want <= 0) return;
+    unsigned long long t0 = 0;
+    unsigned spin = 0;
+    for (;;) {
+        const int v = ld_acquire_gpu(p);
+        if ((v >> 8) == epoch && (v & 255) >= want) return;
+        if ((++spin & 0x3ffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ULL) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void df_post(int* p, int epoch, int count) { st_release_gpu(p, (epoch << 8) | count); }
+
+// 64 x 64 block with leading dimension 64 (the X buffer) -> smem [64][CLD]
+__device__ __forceinline__ void stage_x_async(double* dst, const double* src, int tid) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        int e = tid + q * 256;
+        int r = e >> 5, c = (e & 31) * 2;
+        cp_async16(dst + r * CLD + c, src + r * CB + c, 16);
+    }
+}
+
+// Tiles that other CTAs rewrite during the kernel must never be served from this SM's L1: the 16-byte cp.async is .cg,
+// the unaligned path falls back to ld.global.cg + st.shared (the 8-byte cp.async exists only as .ca).
+template <bool AL16>
+__device__ __forceinline__ void df_stage(double* dst, const double* src, int64_t ld, int r0, int c0, int rows, int cols,
+                                         int tid) {
+    if (AL16) stage_block_async<true>(dst, src, ld, r0, c0, rows, cols, tid);
+    else stage_block(dst, src, ld, r0, c0, rows, cols, tid);
+}
+
+// the serial part on the staged diagonal block: sD -> L_JJ, sX <- X = L_JJ^{-1}.  scratch: one more block (sLt in its
+// first 16 rows, T = L10 X00 in its lower-left quadrant).  All 256 threads; returns sum(log pivot) on warp 0.
+__device__ __forceinline__ double diag_factor_inverse(double* sD, double* sX, double* scratch, double* rinv, double* colbuf,
+                                                       bool* bad, int tid, int warp, int g, int t) {
+    double* sLt = scratch;                     // 32 x 34 doubles = 16 rows of the block
+    double* sT = scratch;                      // rows 32..63, cols 0..31
+    double logsum = 0.0;
+    if (warp == 0) {
+        logsum = factor32(sD, 0, rinv, colbuf, sLt, bad);
+        __syncwarp();
+        invert32(sLt, 0, rinv, sX);
+    } else {
+        for (int e = tid - 32; e < 32 * 32; e += 224) {
+            int rr = e >> 5, cc = 32 + (e & 31);
+            sX[rr * CLD + cc] = 0.0;
+            sD[rr * CLD + cc] = 0.0;
+        }
+    }
+    __syncthreads();
+    const int sr = (warp >> 1) * 8 + g, sc = (warp & 1) * 16 + 2 * t;
+    {   // L10 = D10 X00^T, then D11 -= L10 L10^T
+        double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        mma32<true, false>(o, sD + 32 * CLD, sX, warp, g, t);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<double2*>(sD + (32 + sr) * CLD + sc + j * 8) = make_double2(o[j][0], o[j][1]);
+        __syncthreads();
+        double d[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double2 dd = *reinterpret_cast<const double2*>(sD + (32 + sr) * CLD + 32 + sc + j * 8);
+            d[j][0] = dd.x; d[j][1] = dd.y;
+        }
+        mma32<true, true>(d, sD + 32 * CLD, sD + 32 * CLD, warp, g, t);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<double2*>(sD + (32 + sr) * CLD + 32 + sc + j * 8) = make_double2(d[j][0], d[j][1]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        logsum += factor32(sD, 32, rinv, colbuf, sLt, bad);
+        __syncwarp();
+        invert32(sLt, 32, rinv, sX);
+    }
+    __syncthreads();
+    {   // X10 = -X11 (L10 X00)
+        double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        mma32<false, false>(o, sD + 32 * CLD, sX, warp, g, t);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<double2*>(sT + (32 + sr) * CLD + sc + j * 8) = make_double2(o[j][0], o[j][1]);
+        __syncthreads();
+        double x[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        mma32<false, true>(x, sX + 32 * CLD + 32, sT + 32 * CLD, warp, g, t);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<double2*>(sX + (32 + sr) * CLD + sc + j * 8) = make_double2(x[j][0], x[j][1]);
+    }
+    __syncthreads();
+    return logsum;
+}
+
+template <bool AL16>
+__global__ void __launch_bounds__(256, 1) chol_spine_kernel(DfParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sD = reinterpret_cast<double*>(smem_raw);   // diagonal block -> L_JJ
+    double* sX = sD + CBUF;                             // X_J (kept for the next step's panel product)
+    double* sA = sX + CBUF;                             // W[J,J-1]
+    double* sP = sA + CBUF;                             // L[J,J-1]
+    double* sS = sP + CBUF;                             // scratch of the serial part
+    double* rinv = sS + CBUF;
+    double* colbuf = rinv + 64;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int m = p.m, nb = p.nb;
+    // the worker grid may start now (it never waits for this grid to finish, only for its counters)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int epoch = p.epoch;
+    int* cW = p.aux + DF_AUX_HEAD;
+    int* fX = cW + 3 * nb * nb;
+    double logtot = 0.0;
+    bool bad = false;
+    for (int J = 0; J < nb; ++J) {
+        const int j0 = J * CB;
+        if (J == 0) {
+            df_stage<AL16>(sD, p.M, m, 0, 0, m, m, tid);
+            cp_async_commit();
+            cp_async_wait<0>();
+            // identity on the padding of a ragged last block (nb == 1)
+            __syncthreads();
+            for (int e = tid; e < CB; e += 256) if (e >= m) sD[e * CLD + e] = 1.0;
+            __syncthreads();
+        } else {
+            const double* src = (J == 1) ? p.M : p.W;       // tiles of block column J-1 .. have had J-1 updates
+            if (tid == 0) df_wait(cW + J * nb + (J - 1), epoch, J - 1);
+            if (tid == 32) df_wait(cW + J * nb + J, epoch, J - 1);
+            __syncthreads();
+            df_stage<AL16>(sA, src, m, j0, j0 - CB, m, m, tid);
+            cp_async_commit();
+            double acc[4][2][2];
+            acc_from_global<AL16>(acc, src, m, j0, j0, m, m, wm, wn, g, t);
+            cp_async_wait<0>();
+            __syncthreads();
+            double tmp[4][2][2];
+            acc_zero(tmp);
+            mma64<true, false>(tmp, sA, sX, 0, wn * 16 + 16, wm, wn, g, t);       // L[J,J-1] = W[J,J-1] X^T
+            acc_to_smem(tmp, sP, wm, wn, g, t);
+            acc_to_global<AL16>(tmp, p.W, m, j0, j0 - CB, m, m, wm, wn, g, t);
+            if (p.L) acc_to_global<AL16>(tmp, p.L, m, j0, j0 - CB, m, m, wm, wn, g, t);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) df_post(cW + J * nb + (J - 1), epoch, J);               // L[J,J-1] is final
+            mma64<true, true>(acc, sP, sP, 0, CB, wm, wn, g, t);                  // W[J,J] -= L[J,J-1] L[J,J-1]^T
+            acc_to_smem(acc, sD, wm, wn, g, t);
+            __syncthreads();
+            // ragged last block: identity on the padding (rows / columns >= m are zero after the product)
+            for (int e = tid; e < CB; e += 256) if (j0 + e >= m) sD[e * CLD + e] = 1.0;
+            __syncthreads();
+        }
+        const double ls = diag_factor_inverse(sD, sX, sS, rinv, colbuf, &bad, tid, warp, g, t);
+        if (warp == 0) logtot += ls;
+        // publish X_J (workers read it from the X buffer; Linv[J,J] = X_J) and L_JJ
+        {
+            double* xdst = p.X + (size_t)J * CB * CB;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                int e = tid + q * 256;
+                int r = e >> 5, c = (e & 31) * 2;
+                *reinterpret_cast<double2*>(xdst + r * CB + c) = *reinterpret_cast<const double2*>(sX + r * CLD + c);
+            }
+            if (p.want_inv) smem_to_global(sX, p.Linv, p.mp, j0, j0, m, m, tid);
+            if (p.L) smem_to_global(sD, p.L, m, j0, j0, m, m, tid);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) df_post(fX + J, epoch, 1);
+    }
+    if (tid == 0) {
+        p.d_out[0] = -logtot;
+        if (bad) atomicOr(p.status, ACCBPG_ST_NOT_PD);
+        __threadfence();
+        df_post(p.aux + 3, epoch, 1);          // the last worker leaves only after this: the pair of launches is complete
+    }
+}
+
+template <bool AL16>
+__global__ void __launch_bounds__(256, 2) chol_worker_kernel(DfParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    double* sB = sA + CBUF;
+    __shared__ int s_job[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int m = p.m, mp = p.mp, nb = p.nb;
+    const int epoch = p.epoch;
+    int* cW = p.aux + DF_AUX_HEAD;
+    int* cY = cW + nb * nb;
+    int* fLi = cY + nb * nb;
+    int* fX = fLi + nb * nb;
+    enum { JOB_T = 0, JOB_U, JOB_F, JOB_V };
+    for (;;) {
+        if (tid == 0) {
+            const int jb = atomicAdd(p.aux + 1, 1);
+            int type = -1, a = 0, b = 0, c = 0;
+            if (jb < p.njobs) {
+                int J = 0;
+                while (p.step_off[J + 1] <= jb) ++J;
+                int i = jb - p.step_off[J];
+                const int below = nb - 1 - J;
+                const int nT = below > 1 ? below - 1 : 0;
+                const int nF = p.want_inv ? J : 0;
+                const int nV1 = (p.want_inv && below >= 1) ? J + 1 : 0;
+                const int nU2 = below > 1 ? (below - 1) * below / 2 : 0;
+                if (i < nT) { type = JOB_T; a = J; b = J + 2 + i; }
+                else if ((i -= nT) < nT) { type = JOB_U; a = J; b = J + 2 + i; c = J + 1; }          // column J+1
+                else if ((i -= nT) < nF) { type = JOB_F; a = J; b = i; }
+                else if ((i -= nF) < nV1) { type = JOB_V; a = J; b = J + 1; c = i; }                  // row block J+1
+                else if ((i -= nV1) < nU2) {                                                          // columns >= J+2
+                    // column-major over the lower triangle of the (below-1) x (below-1) trailing blocks
+                    int cc = 0, left = i, len = below - 1;
+                    while (left >= len) { left -= len; --len; ++cc; }
+                    type = JOB_U; a = J; c = J + 2 + cc; b = c + left;
+                } else {                                                                              // V, rows >= J+2
+                    i -= nU2;
+                    type = JOB_V; a = J; b = J + 2 + i / (J + 1); c = i % (J + 1);
+                }
+            }
+            s_job[0] = type; s_job[1] = a; s_job[2] = b; s_job[3] = c;
+        }
+        __syncthreads();
+        const int type = s_job[0], ja = s_job[1], jb2 = s_job[2], jc = s_job[3];
+        __syncthreads();
+        if (type < 0) break;
+        double acc[4][2][2];
+        if (type == JOB_T) {
+            const int J = ja, R = jb2;
+            if (tid == 0) df_wait(fX + J, epoch, 1);
+            if (tid == 32) df_wait(cW + R * nb + J, epoch, J);
+            __syncthreads();
+            df_stage<AL16>(sA, J == 0 ? p.M : p.W, m, R * CB, J * CB, m, m, tid);
+            stage_x_async(sB, p.X + (size_t)J * CB * CB, tid);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            acc_zero(acc);
+            mma64<true, false>(acc, sA, sB, 0, wn * 16 + 16, wm, wn, g, t);
+            acc_to_global<AL16>(acc, p.W, m, R * CB, J * CB, m, m, wm, wn, g, t);
+            if (p.L) acc_to_global<AL16>(acc, p.L, m, R * CB, J * CB, m, m, wm, wn, g, t);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) df_post(cW + R * nb + J, epoch, J + 1);
+        } else if (type == JOB_U) {
+            const int J = ja, R = jb2, C = jc;
+            if (tid == 0) df_wait(cW + R * nb + J, epoch, J + 1);
+            if (tid == 32) df_wait(cW + C * nb + J, epoch, J + 1);
+            if (tid == 64) df_wait(cW + R * nb + C, epoch, J);
+            __syncthreads();
+            df_stage<AL16>(sA, p.W, m, R * CB, J * CB, m, m, tid);
+            if (R != C) df_stage<AL16>(sB, p.W, m, C * CB, J * CB, m, m, tid);
+            cp_async_commit();
+            acc_from_global<AL16>(acc, J == 0 ? p.M : p.W, m, R * CB, C * CB, m, m, wm, wn, g, t);
+            cp_async_wait<0>();
+            __syncthreads();
+            mma64<true, true>(acc, sA, R != C ? sB : sA, 0, CB, wm, wn, g, t);
+            acc_to_global<AL16>(acc, p.W, m, R * CB, C * CB, m, m, wm, wn, g, t);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) df_post(cW + R * nb + C, epoch, J + 1);
+        } else if (type == JOB_F) {
+            const int J = ja, r = jb2;
+            if (tid == 0) df_wait(fX + J, epoch, 1);
+            if (tid == 32) df_wait(cY + J * nb + r, epoch, J - r);
+            __syncthreads();
+            stage_x_async(sA, p.X + (size_t)J * CB * CB, tid);
+            stage_block_async<true>(sB, p.Y, mp, J * CB, r * CB, mp, mp, tid);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            acc_zero(acc);
+            mma64<false, false>(acc, sA, sB, 0, wm * 32 + 32, wm, wn, g, t);      // Linv[J,r] = X Y[J,r]
+            acc_to_global<true>(acc, p.Linv, mp, J * CB, r * CB, mp, mp, wm, wn, g, t);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) df_post(fLi + J * nb + r, epoch, 1);
+        } else {
+            const int K = ja, C = jb2, r = jc;
+            if (tid == 0) df_wait(cW + C * nb + K, epoch, K + 1);
+            if (tid == 32) { if (r < K) df_wait(fLi + K * nb + r, epoch, 1); else df_wait(fX + K, epoch, 1); }
+            if (tid == 64) df_wait(cY + C * nb + r, epoch, K - r);
+            __syncthreads();
+            df_stage<AL16>(sA, p.W, m, C * CB, K * CB, m, m, tid);
+            if (r < K) stage_block_async<true>(sB, p.Linv, mp, K * CB, r * CB, mp, mp, tid);
+            else stage_x_async(sB, p.X + (size_t)K * CB * CB, tid);
+            cp_async_commit();
+            if (r < K) acc_from_global<true>(acc, p.Y, mp, C * CB, r * CB, mp, mp, wm, wn, g, t);
+            else acc_zero(acc);
+            cp_async_wait<0>();
+            __syncthreads();
+            mma64<false, true>(acc, sA, sB, r < K ? 0 : wn * 16, CB, wm, wn, g, t);   // Y[C,r] -= L[C,K] Linv[K,r]
+            acc_to_global<true>(acc, p.Y, mp, C * CB, r * CB, mp, mp, wm, wn, g, t);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) df_post(cY + C * nb + r, epoch, K - r + 1);
+        }
+        __syncthreads();         // sA / sB are free again
+    }
+    // leave: the last worker re-arms the counters for the next call on this aux block
+    if (tid == 0) {
+        __threadfence();
+        const int left = atomicAdd(p.aux + 2, 1);
+        if (left == p.nworkers - 1) {
+            df_wait(p.aux + 3, epoch, 1);      // the spine's last stores (d_out, status) are done
+            p.aux[2] = 0;
+            p.aux[1] = 0;
+        }
+    }
+}
+
+size_t chol_df_aux_bytes(int m) {
+    const int nb = (m + CB - 1) / CB;
+    size_t ints = DF_AUX_HEAD + (size_t)3 * nb * nb + nb;
+    size_t a = (ints * 4 + 255) / 256 * 256;
+    return a + (size_t)nb * CB * CB * 8;
+}
+
+bool chol_df_enabled(int m) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ACCBPG_CHOL_DF"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1 && (m + CB - 1) / CB <= DF_MAXNB && m > CB;
+}
+
+static bool g_df_attr[kMaxDevices] = {};
+static int ensure_df_attrs() {
+    int dev = 0;
+    ACCBPG_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < kMaxDevices && g_df_attr[dev]) return ACCBPG_OK;
+    ACCBPG_CUDA(cudaFuncSetAttribute(chol_spine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SPINE_SMEM));
+    ACCBPG_CUDA(cudaFuncSetAttribute(chol_spine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SPINE_SMEM));
+    ACCBPG_CUDA(cudaFuncSetAttribute(chol_worker_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_WORKER_SMEM));
+    ACCBPG_CUDA(cudaFuncSetAttribute(chol_worker_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_WORKER_SMEM));
+    if (dev >= 0 && dev < kMaxDevices) g_df_attr[dev] = true;
+    return ACCBPG_OK;
+}
+
+// aux: chol_df_aux_bytes(m) bytes, zero when first used.  Linv (when wanted) must have been zero when first used and
+// only ever written by this function since.
+int chol_factor_inv_df(Ctx* c, cudaStream_t s, int m, int mp, const double* M, double* L, int want_inv, double* Linv,
+                       double* W, double* Y, void* aux, double* d_out, DfGate* gate_out) {
+    int rc = ensure_df_attrs();
+    if (rc) return rc;
+    if (L) ACCBPG_CUDA(cudaMemsetAsync(L, 0, (size_t)m * m * sizeof(double), s));
+    ProfScope ps(P_CHOL, s);
+    DfParams p;
+    p.M = M; p.W = W; p.L = L; p.Y = Y; p.Linv = Linv; p.d_out = d_out; p.status = c->d_status;
+    p.m = m; p.mp = mp; p.want_inv = want_inv ? 1 : 0;
+    const int nb = (m + CB - 1) / CB;
+    p.nb = nb;
+    p.aux = (int*)aux;
+    {   // the epoch of this call on this aux block (1, 2, 3, ...: zero-filled memory never matches)
+        static std::map<void*, int> epochs;
+        int& e = epochs[aux];
+        e = (e >= (1 << 22)) ? 1 : e + 1;
+        p.epoch = e;
+    }
+    if (gate_out) {
+        gate_out->fX = p.aux + DF_AUX_HEAD + 3 * nb * nb;
+        gate_out->fLi = p.aux + DF_AUX_HEAD + 2 * nb * nb;
+        gate_out->nb = nb;
+        gate_out->epoch = p.epoch;
+    }
+    size_t ints = DF_AUX_HEAD + (size_t)3 * nb * nb + nb;
+    p.X = (double*)((char*)aux + (ints * 4 + 255) / 256 * 256);
+    int off = 0;
+    for (int J = 0; J < nb; ++J) {
+        p.step_off[J] = off;
+        const int below = nb - 1 - J;
+        const int nT = below > 1 ? below - 1 : 0;
+        const int nF = want_inv ? J : 0;
+        const int nV1 = (want_inv && below >= 1) ? J + 1 : 0;
+        const int nU2 = below > 1 ? (below - 1) * below / 2 : 0;
+        const int nV2 = (want_inv && below > 1) ? (below - 1) * (J + 1) : 0;
+        off += nT + nT + nF + nV1 + nU2 + nV2;
+    }
+    for (int J = nb; J <= DF_MAXNB; ++J) p.step_off[J] = off;
+    p.njobs = off;
+    static int wcap = -1;
+    if (wcap < 0) { const char* e = getenv("ACCBPG_CHOL_WORKERS"); wcap = e ? atoi(e) : 0; }
+    // enough CTAs to keep one block column's jobs in flight, at most two per SM
+    int widest = 0;
+    for (int J = 0; J < nb; ++J) widest = max(widest, p.step_off[J + 1] - p.step_off[J]);
+    int nworkers = widest + widest / 2 + 4;
+    if (nworkers > 2 * (c->sm_count - 1)) nworkers = 2 * (c->sm_count - 1);
+    if (wcap > 0 && nworkers > wcap) nworkers = wcap;
+    if (nworkers > p.njobs) nworkers = p.njobs;
+    if (nworkers < 1) nworkers = 1;
+    p.nworkers = nworkers;
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool al16 = (m % 2 == 0) && al(M) && al(W) && (!L || al(L));
+    if (al16) chol_spine_kernel<true><<<1, 256, DF_SPINE_SMEM, s>>>(p);
+    else      chol_spine_kernel<false><<<1, 256, DF_SPINE_SMEM, s>>>(p);
+    ACCBPG_LAUNCHED("chol_spine_kernel");
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nworkers, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = DF_WORKER_SMEM;
+    cfg.stream = s;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (al16) ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, chol_worker_kernel<true>, p));
+    else      ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, chol_worker_kernel<false>, p));
+    ACCBPG_LAUNCHED("chol_worker_kernel");
+    return ACCBPG_OK;
+}
+
 #ifdef CHOL_TRACE
 long long* g_chol_trace = nullptr;
 #endif
@@ -547,7 +1017,10 @@ static int ensure_attrs() {
 // Launches are chained with programmatic dependent launch: launch J+1 is resident and past its prologue when
 // launch J retires, so the ~4 us launch gap drops out of the critical path.
 int chol_factor_inv(Ctx* c, cudaStream_t s, int m, int mp, const double* M, double* L, int want_inv, double* Linv,
-                    double* W, double* Y, double* acc, double* d_out, const std::function<int(int)>* after_step) {
+                    double* W, double* Y, double* acc, double* d_out, const std::function<int(int)>* after_step, void* aux,
+                    DfGate* gate) {
+    if (aux && !after_step && chol_df_enabled(m))
+        return chol_factor_inv_df(c, s, m, mp, M, L, want_inv, Linv, W, Y, aux, d_out, gate);
     int rc = ensure_attrs();
     if (rc) return rc;
     if (L) ACCBPG_CUDA(cudaMemsetAsync(L, 0, (size_t)m * m * sizeof(double), s));

@@ -133,7 +133,15 @@ __device__ __forceinline__ void mma_nn_slab(double (&acc)[MI][NI][2], const doub
 #endif  // __CUDACC__
 
 // defined in chol.cu (host side, stream ordered)
+// progress flags of the data-flow chain, for consumers of L^-1 that start before the chain has finished: block row J of
+// L^-1 is final once fX[J] and fLi[J*nb + r], r < J, carry `epoch` in their upper 24 bits and a count >= 1
+struct DfGate { const int* fX; const int* fLi; int nb; int epoch; };
 int chol_factor_inv(Ctx* c, cudaStream_t s, int m, int mp, const double* M, double* L, int want_inv, double* Linv,
-                    double* W, double* Y, double* acc, double* d_out, const std::function<int(int)>* after_step = nullptr);
+                    double* W, double* Y, double* acc, double* d_out, const std::function<int(int)>* after_step = nullptr,
+                    void* aux = nullptr, DfGate* gate = nullptr);
+// data-flow form (two launches for the whole chain): used by chol_factor_inv when `aux` is given, no hook is asked
+// for and chol_df_enabled(m)
+size_t chol_df_aux_bytes(int m);
+bool chol_df_enabled(int m);
 
 }  // namespace accbpg

@@ -487,6 +487,11 @@ struct TrmmParams {
     double* part;         // [nib][npad] partial column sums of squares
     int m, mp, nib;
     int64_t n, ldh, npad;
+    // optional gate (persistent kernel only): tiles of a row block start once its rows of L^-1 are final in the data-flow
+    // Cholesky chain that is still running (DfGate of dmma.cuh); ascending: walk row blocks lightest (= earliest) first
+    const int* gate_fX = nullptr;
+    const int* gate_fLi = nullptr;
+    int gate_nb = 0, gate_epoch = 0, ascending = 0;
 };
 
 template <bool ALIGNED16>
@@ -753,6 +758,23 @@ trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, in
     int pr_ib = 0, pr_panel = 0, pr_slab = 0, pr_KT = 0;      // current tile being issued (pr_slab == pr_KT: need a new one)
     int issued = 0;                                           // stages issued so far (data or the final marker)
     bool pr_done = false;
+    int pr_ready = -1;                                        // gated launch: row blocks <= pr_ready are known to be final
+    auto gate_wait = [&](const int* f) {
+        unsigned long long t0 = 0;
+        unsigned spin = 0;
+        for (;;) {
+            int v;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((v >> 8) == p.gate_epoch && (v & 255) >= 1) return;
+            __nanosleep(200);
+            if ((++spin & 0xffu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 2000000000ULL) __trap();
+            }
+        }
+    };
     auto produce_one = [&]() {
         const int st = issued % TRT_STAGES;
         if (issued >= TRT_STAGES) mbar_wait(bars + 8 * (TRT_STAGES + st), ((issued / TRT_STAGES) + 1) & 1);
@@ -766,8 +788,16 @@ trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, in
                 ++issued;
                 return;
             }
-            pr_ib = p.nib - 1 - (int)(tile / npanels);        // heaviest row blocks first
+            pr_ib = p.ascending ? (int)(tile / npanels) : p.nib - 1 - (int)(tile / npanels);   // default: heaviest first
             pr_panel = (int)(tile % npanels);
+            if (p.gate_fX != nullptr && pr_ib > pr_ready) {   // rows of this row block of L^-1 final?  (64-row block rows 2ib, 2ib+1)
+                for (int J = 2 * pr_ib; J <= 2 * pr_ib + 1 && J < p.gate_nb; ++J) {
+                    gate_wait(p.gate_fX + J);
+                    for (int r = 0; r < J; ++r) gate_wait(p.gate_fLi + J * p.gate_nb + r);
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy acquire before the TMA reads of L^-1
+                pr_ready = pr_ib;
+            }
             int kmax = (pr_ib + 1) * BM;
             if (kmax > m16) kmax = m16;
             pr_KT = kmax / BK;
@@ -885,7 +915,7 @@ struct DoptPlan {
     int mp, nt, n_off, nib;
     int s_off, s_diag, smax, diag_first;
     int64_t kchunk_off, kchunk_diag, npad;
-    size_t off_P, off_Linv, off_Y, off_part, off_M, off_L, off_W, off_M2, off_W2, total;
+    size_t off_P, off_Linv, off_Y, off_part, off_M, off_L, off_W, off_M2, off_W2, off_aux, off_aux2, total;
 };
 
 // Relative cost of a diagonal tile: 36/64 by DMMA count; its sub-partitions host only 2-3 active warps instead of 4,
@@ -958,6 +988,11 @@ static DoptPlan make_plan(int m, int64_t n, int sm_count) {
     pl.off_W2 = a;   a += mm;
     pl.off_Linv = a; a += (size_t)pl.mp * pl.mp * 8;
     pl.off_Y = a;    a += (size_t)pl.mp * pl.mp * 8;      // running sums of the block forward substitution
+    {   // progress counters + published diagonal inverses of the data-flow Cholesky chain, one set per concurrent chain
+        const size_t ab = (chol_df_aux_bytes(m) + 255) / 256 * 256;
+        pl.off_aux = a;  a += ab;
+        pl.off_aux2 = a; a += ab;
+    }
     pl.off_P = a;    a += (size_t)pl.smax * pl.mp * pl.mp * 8;
     pl.off_part = a; a += (size_t)pl.nib * pl.npad * 8;
     pl.total = a;
@@ -1170,7 +1205,7 @@ int accbpg_dopt_factor(void* ctx, void* stream, int m, const double* M, double* 
     double* W = (double*)((char*)ws + pl.off_W);
     if (M == W || L == W) return arg_err("dopt_factor: M / L alias the factor scratch");
     return chol_factor_inv(c, s, m, pl.mp, M, L, want_inverse ? 1 : 0, (double*)((char*)ws + pl.off_Linv), W,
-                           (double*)((char*)ws + pl.off_Y), c->d_slots + 248, d_out);
+                           (double*)((char*)ws + pl.off_Y), c->d_slots + 248, d_out, nullptr, (char*)ws + pl.off_aux);
 }
 
 int accbpg_dopt_grad(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh, void* ws, double* g) {
@@ -1287,6 +1322,28 @@ static int dopt_factor_grad(Ctx* c, cudaStream_t s, const double* H, int m, int6
     ACCBPG_CUDA(cudaEventRecord(c->ev_fork, s));
     ACCBPG_CUDA(cudaStreamWaitEvent(c->side2, c->ev_fork, 0));
     ProfScope ps_all(P_TRINV, s);                             // chain + triangular GEMM as one interval
+    if (chol_df_enabled(m)) {
+        // data-flow chain (two launches): the early row blocks are ONE gated persistent launch on the second stream that
+        // walks them lightest first and starts each as soon as the chain's counters say its rows of L^-1 are final
+        DfGate gate;
+        rc = chol_factor_inv(c, s, m, pl.mp, M, nullptr, 1, Linv, (double*)((char*)ws + pl.off_W),
+                             (double*)((char*)ws + pl.off_Y), c->d_slots + 248, d_f_out, nullptr, (char*)ws + pl.off_aux, &gate);
+        if (rc) return rc;
+        TrmmParams pe = p;
+        pe.gate_fX = gate.fX; pe.gate_fLi = gate.fLi; pe.gate_nb = gate.nb; pe.gate_epoch = gate.epoch; pe.ascending = 1;
+        trmm_persistent_kernel<<<early_grid, TRP_THREADS, TRP_SMEM, c->side2>>>(pe, tmL, counters + 1, 0, (int)(n_early * npanels));
+        ACCBPG_LAUNCHED("trmm_persistent_kernel");
+        ACCBPG_CUDA(cudaEventRecord(c->ev_early_done, c->side2));
+        const int limit = (int)((pl.nib - n_early) * npanels);
+        const int pgrid = (int)((int64_t)c->sm_count < (int64_t)limit ? c->sm_count : limit);
+        trmm_persistent_kernel<<<pgrid, TRP_THREADS, TRP_SMEM, s>>>(p, tmL, counters, 0, limit);
+        ACCBPG_LAUNCHED("trmm_persistent_kernel");
+        ACCBPG_CUDA(cudaStreamWaitEvent(s, c->ev_early_done, 0));
+        int fgd = grid_for(c, n, 256, 2, 8);
+        grad_finalize_kernel<<<fgd, 256, 0, s>>>(part, pl.nib, pl.npad, n, g);
+        ACCBPG_LAUNCHED("grad_finalize_kernel");
+        return ACCBPG_OK;
+    }
     std::function<int(int)> hook = [&](int J) -> int {
         if ((J & 1) == 0) return 0;
         const int ib = J >> 1;                                // rows of row block ib are final
@@ -1350,7 +1407,7 @@ int accbpg_dopt_pair(void* ctx, void* stream, const double* H, int m, int64_t n,
     ACCBPG_CUDA(cudaEventRecord(c->ev_fork, s));
     ACCBPG_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
     rc = chol_factor_inv(c, c->side, m, pl.mp, M2, NULL, 0, NULL, (double*)((char*)ws + pl.off_W2), NULL,
-                         c->d_slots + 246, d_fx_out);
+                         c->d_slots + 246, d_fx_out, nullptr, (char*)ws + pl.off_aux2);
     if (rc) return rc;
     ACCBPG_CUDA(cudaEventRecord(c->ev_join, c->side));
     rc = accbpg_dopt_gram(ctx, stream, H, m, n, ldh, yg, ws, M1);
@@ -1378,7 +1435,7 @@ int accbpg_dopt_pair_from_gram(void* ctx, void* stream, const double* H, int m, 
         ACCBPG_CUDA(cudaEventRecord(c->ev_fork, s));
         ACCBPG_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
         rc = chol_factor_inv(c, c->side, m, pl.mp, Mx, NULL, 0, NULL, (double*)((char*)ws + pl.off_W2), NULL,
-                             c->d_slots + 246, d_fx_out);
+                             c->d_slots + 246, d_fx_out, nullptr, (char*)ws + pl.off_aux2);
         if (rc) return rc;
         ACCBPG_CUDA(cudaEventRecord(c->ev_join, c->side));
     }

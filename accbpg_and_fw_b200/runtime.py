@@ -117,10 +117,11 @@ class Runtime:
 
     # ---- memory ------------------------------------------------------------------------
     def workspace(self, key, nbytes):
-        """Byte workspace cached per (key); grown on demand, never shrunk."""
+        """Byte workspace cached per (key); grown on demand, never shrunk.  Zero-filled when allocated: the D-opt
+        workspace keeps progress counters and the (never written) upper part of L^-1 there from call to call."""
         buf = self._ws.get(key)
         if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
             self._ws[key] = buf
         return buf
 

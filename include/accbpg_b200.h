@@ -210,6 +210,8 @@ int accbpg_lmo_box(void* ctx, void* stream, int64_t n, const double* d_g, const 
 
 /* ---- D-optimal design objective  f(x) = -log det(H diag(x) H^T)
  *      (DOptimalObj.func_grad, accbpg/functions.py:43-59).  H is m x n_local row-major. */
+/* The workspace must be ZERO-FILLED once after allocation and then left to the library (it keeps the progress
+ * counters of the data-flow Cholesky chain and the never-written upper part of L^{-1} there from call to call). */
 size_t accbpg_dopt_workspace_bytes(int m, int64_t n_local);
 /* K1: M = H diag(x) H^T as an FP64 DMMA SYRK (lower tiles, split over n, fixed-order reduce), written
  * as a full symmetric m x m matrix with leading dimension m.  Sets ST_X_NEGATIVE if some x < 0. */
@@ -234,7 +236,9 @@ int accbpg_dopt_gram_allreduce(void* ctx, void* stream, const double* d_H, int m
 int accbpg_dopt_vertex_gram(void* ctx, void* stream, const double* d_H, int m, int64_t n_local, int64_t ldh,
                             const double* d_G, double fill, const double* d_idx, int64_t col_offset, double radius,
                             double* d_out);
-/* K2 (+K3): blocked Cholesky M = L L^T, out of place (d_M symmetric m x m is only read); d_out[0] = -log det M =
+/* K2 (+K3): blocked Cholesky M = L L^T (right-looking over 64-wide block columns, two launches for the whole chain:
+ * one CTA walks the critical path - panel product, diagonal update, in-warp 64x64 factor and inverse - while a second
+ * grid does every other 64x64 tile job as its operands become final, on progress counters in global memory), out of place (d_M symmetric m x m is only read); d_out[0] = -log det M =
  * -sum log(pivot).  d_L (m x m, may be NULL) receives the lower factor, zero above the diagonal.  want_inverse != 0
  * also leaves L^{-1} in the workspace for accbpg_dopt_grad: the block forward substitution rides in the same launches
  * as the factorisation.  Sets ST_NOT_PD on a pivot <= 0.  d_ws is the dopt workspace (any n_local). */
@@ -282,7 +286,7 @@ int accbpg_linreg_rmatvec(void* ctx, void* stream, const double* d_A, int64_t m,
  * ACCBPG_FW_CTRL_DOUBLES float64 (layout: enum FwCtrl in csrc/fw.cu, mirrored by dopt_fw.py) and four
  * history arrays of maxitrs float64 (F, SP, SN, T; T holds %globaltimer nanoseconds). */
 #define ACCBPG_FW_CTRL_DOUBLES 32
-size_t accbpg_fw_workspace_bytes(int m, int64_t n);
+size_t accbpg_fw_workspace_bytes(int m, int64_t n);   /* zero-filled once by the caller, like the D-opt workspace it contains */
 /* setup (D_opt_alg.py:39-45 / :123-129): M = V diag(x0) V^T, Hinv = M^{-1}, w_j = v_j^T Hinv v_j,
  * ctrl <- {log det M, not stopped}.  Sets the ST_X_NEGATIVE / ST_NOT_PD status bits like func_grad. */
 int accbpg_fw_setup(void* ctx, void* stream, const double* d_V, int m, int64_t n, int64_t ldv,

@@ -120,7 +120,7 @@ def test_sharded_fw_building_blocks_on_one_gpu(acc, away, world):
     Vs = [torch.tensor(np.ascontiguousarray(V[:, offs[r]:offs[r + 1]]), device=dev) for r in range(world)]
     xs = [torch.tensor(x0[offs[r]:offs[r + 1]].copy(), device=dev) for r in range(world)]
     nl = [offs[r + 1] - offs[r] for r in range(world)]
-    wss = [torch.empty(lib.accbpg_fw_workspace_bytes(m, nl[r]), dtype=torch.uint8, device=dev) for r in range(world)]
+    wss = [torch.zeros(lib.accbpg_fw_workspace_bytes(m, nl[r]), dtype=torch.uint8, device=dev) for r in range(world)]
     M = torch.zeros(m, m, dtype=torch.float64, device=dev)
     Mr = torch.empty(m, m, dtype=torch.float64, device=dev)
     for r in range(world):

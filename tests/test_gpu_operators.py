@@ -60,7 +60,7 @@ def test_dopt_factor_entry_point(acc, m):
     Hd = torch.tensor(H, device="cuda")
     Ld = torch.full((m, m), 7.0, dtype=torch.float64, device="cuda")
     gd = torch.empty(n, dtype=torch.float64, device="cuda")
-    ws = torch.empty(lib.accbpg_dopt_workspace_bytes(m, n), dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(lib.accbpg_dopt_workspace_bytes(m, n), dtype=torch.uint8, device="cuda")
     for want_inv in (0, 1):
         nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, m, Md.data_ptr(), Ld.data_ptr(), want_inv, ws.data_ptr(),
                                          rt.slot(40)))

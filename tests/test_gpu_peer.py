@@ -48,7 +48,7 @@ def test_gram_allreduce_over_peer_buffers_two_emulated_ranks(acc, m, widths):
     try:
         recv = [torch.zeros(2 * world * m * m, dtype=F64, device=dev) for _ in range(world)]
         flags = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
-        ws = [torch.empty(lib.accbpg_dopt_workspace_bytes(m, w), dtype=torch.uint8, device=dev) for w in widths]
+        ws = [torch.zeros(lib.accbpg_dopt_workspace_bytes(m, w), dtype=torch.uint8, device=dev) for w in widths]
         M = [torch.empty(m, m, dtype=F64, device=dev) for _ in range(world)]
         t_recv, t_flags = _table(recv), _table(flags)
         torch.cuda.synchronize()
@@ -99,7 +99,7 @@ def test_fw_loop_over_peer_buffers_two_emulated_ranks(acc, away):
         st = []
         for r in range(world):
             nl = bounds[r + 1] - bounds[r]
-            d = {"ws": torch.empty(lib.accbpg_fw_workspace_bytes(m, nl), dtype=torch.uint8, device=dev),
+            d = {"ws": torch.zeros(lib.accbpg_fw_workspace_bytes(m, nl), dtype=torch.uint8, device=dev),
                  "Hinv": torch.empty(m, m, dtype=F64, device=dev), "w": torch.empty(nl, dtype=F64, device=dev),
                  "ctrl": torch.zeros(nat.MACROS["ACCBPG_FW_CTRL_DOUBLES"], dtype=F64, device=dev), "hist": torch.zeros(4, its, dtype=F64, device=dev)}
             nat.check(lib.accbpg_fw_setup_from_gram(ranks[r].ctx, ranks[r].stream.cuda_stream, Vd[r].data_ptr(), m, nl,
