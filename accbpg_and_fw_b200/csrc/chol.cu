@@ -550,10 +550,16 @@ __global__ void __launch_bounds__(256, 1) chol_inv_step_kernel(CholStep p) {
 //   re-arms the job counter): no memset between calls.  The aux block and Linv must be zero when first used (the
 //   workspace is zero-initialised once by its owner); Linv's strictly upper part is never written, so it stays zero
 //   from call to call.  The triangular GEMM reads the same counters to start on row blocks of L^-1 as they become final.
+#ifdef CHOL_TRACE
+__device__ long long* g_df_trace_dev = nullptr;
+#define DF_STAMP(i) do { if (threadIdx.x == 0 && g_df_trace_dev) g_df_trace_dev[df_trace_row * 16 + (i)] = clock64(); } while (0)
+#else
+#define DF_STAMP(i)
+#endif
 constexpr int DF_MAXNB = 64;
 constexpr int DF_AUX_HEAD = 16;                 // ints: [1] job counter, [2] workers that have left, [3] spine done
 constexpr int DF_WORKER_SMEM = 2 * CBUF * 8;
-constexpr int DF_SPINE_SMEM = (5 * CBUF + 64 + 96) * 8;      // > half an SM's shared memory: the spine has its SM alone
+constexpr int DF_SPINE_SMEM = (6 * CBUF + 64 + 128) * 8;     // > half an SM's shared memory: the spine has its SM alone
 
 struct DfParams {
     const double* M;     // input matrix (only read)
@@ -566,6 +572,7 @@ struct DfParams {
     uint32_t* status;
     int* aux;            // DF_AUX_HEAD ints, then cW[nb*nb], cY[nb*nb], fLi[nb*nb], fX[nb]
     int m, mp, nb, want_inv, njobs, nworkers, epoch;
+    int dbg;             // ACCBPG_DF_DBG (timing experiments only): 1 = the spine never waits and no workers run (results are garbage)
     int step_off[DF_MAXNB + 1];
 };
 
@@ -615,82 +622,71 @@ __device__ __forceinline__ void df_stage(double* dst, const double* src, int64_t
     else stage_block(dst, src, ld, r0, c0, rows, cols, tid);
 }
 
-// the serial part on the staged diagonal block: sD -> L_JJ, sX <- X = L_JJ^{-1}.  scratch: one more block (sLt in its
-// first 16 rows, T = L10 X00 in its lower-left quadrant).  All 256 threads; returns sum(log pivot) on warp 0.
-__device__ __forceinline__ double diag_factor_inverse(double* sD, double* sX, double* scratch, double* rinv, double* colbuf,
-                                                       bool* bad, int tid, int warp, int g, int t) {
-    double* sLt = scratch;                     // 32 x 34 doubles = 16 rows of the block
-    double* sT = scratch;                      // rows 32..63, cols 0..31
-    double logsum = 0.0;
-    if (warp == 0) {
-        logsum = factor32(sD, 0, rinv, colbuf, sLt, bad);
-        __syncwarp();
-        invert32(sLt, 0, rinv, sX);
-    } else {
-        for (int e = tid - 32; e < 32 * 32; e += 224) {
-            int rr = e >> 5, cc = 32 + (e & 31);
-            sX[rr * CLD + cc] = 0.0;
-            sD[rr * CLD + cc] = 0.0;
+// sub-tile product on the DMMA pipe: acc (MI_ x NJ_ mma tiles; acc[i][j][e] <-> row row0 + i*8 + g, col col0 + j*8 + 2t + e)
+// (+/-)= A[row0 .., k] * B, k in [kbeg, kend); B_T: B stored [n][k] (product A B^T), else [k][n]
+template <bool B_T, bool NEG, int MI_, int NJ_>
+__device__ __forceinline__ void mma_sub(double (&acc)[MI_][NJ_][2], const double* A, int row0, const double* B, int col0,
+                                        int kbeg, int kend, int g, int t) {
+    const double* ap = A + (row0 + g) * CLD + t;
+    const double* bp = B_T ? (B + (col0 + g) * CLD + t) : (B + t * CLD + col0 + g);
+#pragma unroll 4
+    for (int k = kbeg; k < kend; k += 4) {
+        double a[MI_], b[NJ_];
+#pragma unroll
+        for (int i = 0; i < MI_; ++i) {
+            a[i] = ap[i * 8 * CLD + k];
+            if (NEG) a[i] = -a[i];
         }
+#pragma unroll
+        for (int j = 0; j < NJ_; ++j) b[j] = B_T ? bp[j * 8 * CLD + k] : bp[k * CLD + j * 8];
+#pragma unroll
+        for (int i = 0; i < MI_; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ_; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
-    __syncthreads();
-    const int sr = (warp >> 1) * 8 + g, sc = (warp & 1) * 16 + 2 * t;
-    {   // L10 = D10 X00^T, then D11 -= L10 L10^T
-        double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-        mma32<true, false>(o, sD + 32 * CLD, sX, warp, g, t);
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-            *reinterpret_cast<double2*>(sD + (32 + sr) * CLD + sc + j * 8) = make_double2(o[j][0], o[j][1]);
-        __syncthreads();
-        double d[2][2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const double2 dd = *reinterpret_cast<const double2*>(sD + (32 + sr) * CLD + 32 + sc + j * 8);
-            d[j][0] = dd.x; d[j][1] = dd.y;
-        }
-        mma32<true, true>(d, sD + 32 * CLD, sD + 32 * CLD, warp, g, t);
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-            *reinterpret_cast<double2*>(sD + (32 + sr) * CLD + 32 + sc + j * 8) = make_double2(d[j][0], d[j][1]);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        logsum += factor32(sD, 32, rinv, colbuf, sLt, bad);
-        __syncwarp();
-        invert32(sLt, 32, rinv, sX);
-    }
-    __syncthreads();
-    {   // X10 = -X11 (L10 X00)
-        double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-        mma32<false, false>(o, sD + 32 * CLD, sX, warp, g, t);
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-            *reinterpret_cast<double2*>(sT + (32 + sr) * CLD + sc + j * 8) = make_double2(o[j][0], o[j][1]);
-        __syncthreads();
-        double x[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-        mma32<false, true>(x, sX + 32 * CLD + 32, sT + 32 * CLD, warp, g, t);
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-            *reinterpret_cast<double2*>(sX + (32 + sr) * CLD + sc + j * 8) = make_double2(x[j][0], x[j][1]);
-    }
-    __syncthreads();
-    return logsum;
 }
+template <int MI_, int NJ_>
+__device__ __forceinline__ void sub_load(double (&acc)[MI_][NJ_][2], const double* S, int row0, int col0, int g, int t) {
+#pragma unroll
+    for (int i = 0; i < MI_; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ_; ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(S + (row0 + i * 8 + g) * CLD + col0 + j * 8 + 2 * t);
+            acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+        }
+}
+template <int MI_, int NJ_>
+__device__ __forceinline__ void sub_store(const double (&acc)[MI_][NJ_][2], double* S, int row0, int col0, int g, int t) {
+#pragma unroll
+    for (int i = 0; i < MI_; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ_; ++j)
+            *reinterpret_cast<double2*>(S + (row0 + i * 8 + g) * CLD + col0 + j * 8 + 2 * t) =
+                make_double2(acc[i][j][0], acc[i][j][1]);
+}
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// The spine.  Within a step the critical path is  [P0 = rows 0..31 of L[J,J-1]] -> [D00 update] -> 32x32 factor + inverse ->
+// 32x32 products -> 32x32 factor + inverse -> 32x32 products; everything else of the step runs on warps 1..7 under the
+// first in-warp factorisation (rows 32..63 of the panel product, the other three quadrants of the diagonal update, the
+// global stores of L[J,J-1] and of the previous X with their fences and counter posts) and warp 7 fetches the next
+// step's two tiles into shared memory as soon as their counters allow (under the second factorisation).
 template <bool AL16>
 __global__ void __launch_bounds__(256, 1) chol_spine_kernel(DfParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sD = reinterpret_cast<double*>(smem_raw);   // diagonal block -> L_JJ
     double* sX = sD + CBUF;                             // X_J (kept for the next step's panel product)
-    double* sA = sX + CBUF;                             // W[J,J-1]
-    double* sP = sA + CBUF;                             // L[J,J-1]
-    double* sS = sP + CBUF;                             // scratch of the serial part
+    double* sA0 = sX + CBUF;                            // W[J,J-1] -> L[J,J-1], ping
+    double* sA1 = sA0 + CBUF;                           //                        pong (the next step's tile lands here)
+    double* sDN = sA1 + CBUF;                           // W[J,J] as fetched (the diagonal tile before this step's update)
+    double* sS = sDN + CBUF;                            // scratch of the serial part
     double* rinv = sS + CBUF;
     double* colbuf = rinv + 64;
+    __shared__ int s_pf;                                // the next step's tiles have been requested (cp.async by warp 7)
+    __shared__ volatile int s_w0;                       // serial phases warp 0 has finished (2J+1: first half, 2J+2: second)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;
     const int m = p.m, nb = p.nb;
     // the worker grid may start now (it never waits for this grid to finish, only for its counters)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -700,66 +696,282 @@ __global__ void __launch_bounds__(256, 1) chol_spine_kernel(DfParams p) {
     int* fX = cW + 3 * nb * nb;
     double logtot = 0.0;
     bool bad = false;
+    if (tid == 0) { s_pf = 0; s_w0 = 0; }
+
+    // warp 7: fetch the tiles of step Jn (panel tile (Jn,Jn-1) -> dstA, diagonal tile (Jn,Jn) -> sDN) as soon as their
+    // counters allow, watching them only for as long as warp 0 is busy with serial phase `phase` (never holds the CTA up)
+    auto try_prefetch = [&](int Jn, double* dstA, int phase) {
+        if (Jn >= nb || s_pf) return;
+        int ok = 0;
+        if (lane == 0) {
+            while (!ok) {
+                const int need = (p.dbg & 1) ? 0 : Jn - 1;
+                bool r1 = true, r2 = true;
+                if (need > 0) {
+                    const int v1 = ld_acquire_gpu(cW + Jn * nb + (Jn - 1)), v2 = ld_acquire_gpu(cW + Jn * nb + Jn);
+                    r1 = (v1 >> 8) == epoch && (v1 & 255) >= need;
+                    r2 = (v2 >> 8) == epoch && (v2 & 255) >= need;
+                }
+                ok = (r1 && r2) ? 1 : 0;
+                if (ok || s_w0 >= phase) break;
+                __nanosleep(40);
+            }
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) return;
+        const double* src = (Jn == 1) ? p.M : p.W;
+        if (AL16) {
+#pragma unroll 8
+            for (int q = 0; q < 64; ++q) {
+                const int e = lane + q * 32;
+                const int r = e >> 5, c = (e & 31) * 2;
+                const int gr = Jn * CB + r;
+                {
+                    const int gc = (Jn - 1) * CB + c;
+                    const bool in = gr < m && gc < m;
+                    cp_async16(dstA + r * CLD + c, in ? (src + (int64_t)gr * m + gc) : src, in ? 16 : 0);
+                }
+                {
+                    const int gc = Jn * CB + c;
+                    const bool in = gr < m && gc < m;
+                    cp_async16(sDN + r * CLD + c, in ? (src + (int64_t)gr * m + gc) : src, in ? 16 : 0);
+                }
+            }
+        } else {
+            for (int e = lane; e < CB * CB; e += 32) {
+                const int r = e >> 6, c = e & 63;
+                const int gr = Jn * CB + r, gc1 = (Jn - 1) * CB + c, gc2 = Jn * CB + c;
+                dstA[r * CLD + c] = (gr < m && gc1 < m) ? __ldcg(src + (int64_t)gr * m + gc1) : 0.0;
+                sDN[r * CLD + c] = (gr < m && gc2 < m) ? __ldcg(src + (int64_t)gr * m + gc2) : 0.0;
+            }
+        }
+        cp_async_commit();
+        if (lane == 0) s_pf = 1;
+    };
+
     for (int J = 0; J < nb; ++J) {
         const int j0 = J * CB;
+        const int df_trace_row = J;
+        (void)df_trace_row;
+        double* sA = (J & 1) ? sA1 : sA0;
+        double* sAn = (J & 1) ? sA0 : sA1;
+        DF_STAMP(0);
         if (J == 0) {
             df_stage<AL16>(sD, p.M, m, 0, 0, m, m, tid);
             cp_async_commit();
             cp_async_wait<0>();
-            // identity on the padding of a ragged last block (nb == 1)
             __syncthreads();
-            for (int e = tid; e < CB; e += 256) if (e >= m) sD[e * CLD + e] = 1.0;
+            for (int e = tid; e < 32 * 32; e += 256) {          // the upper right quadrants stay zero for the whole chain
+                const int rr = e >> 5, cc = 32 + (e & 31);
+                sX[rr * CLD + cc] = 0.0;
+                sD[rr * CLD + cc] = 0.0;
+            }
             __syncthreads();
         } else {
-            const double* src = (J == 1) ? p.M : p.W;       // tiles of block column J-1 .. have had J-1 updates
-            if (tid == 0) df_wait(cW + J * nb + (J - 1), epoch, J - 1);
-            if (tid == 32) df_wait(cW + J * nb + J, epoch, J - 1);
-            __syncthreads();
-            df_stage<AL16>(sA, src, m, j0, j0 - CB, m, m, tid);
-            cp_async_commit();
-            double acc[4][2][2];
-            acc_from_global<AL16>(acc, src, m, j0, j0, m, m, wm, wn, g, t);
+            // ---- the step's two tiles: already on their way (warp 7 asked for them during the last step), else now
+            if (!s_pf) {
+                const double* src = (J == 1) ? p.M : p.W;
+                if (!(p.dbg & 1)) {
+                    if (tid == 0) df_wait(cW + J * nb + (J - 1), epoch, J - 1);
+                    if (tid == 32) df_wait(cW + J * nb + J, epoch, J - 1);
+                }
+                __syncthreads();
+                df_stage<AL16>(sA, src, m, j0, j0 - CB, m, m, tid);
+                df_stage<AL16>(sDN, src, m, j0, j0, m, m, tid);
+                cp_async_commit();
+            }
             cp_async_wait<0>();
             __syncthreads();
-            double tmp[4][2][2];
-            acc_zero(tmp);
-            mma64<true, false>(tmp, sA, sX, 0, wn * 16 + 16, wm, wn, g, t);       // L[J,J-1] = W[J,J-1] X^T
-            acc_to_smem(tmp, sP, wm, wn, g, t);
-            acc_to_global<AL16>(tmp, p.W, m, j0, j0 - CB, m, m, wm, wn, g, t);
-            if (p.L) acc_to_global<AL16>(tmp, p.L, m, j0, j0 - CB, m, m, wm, wn, g, t);
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) df_post(cW + J * nb + (J - 1), epoch, J);               // L[J,J-1] is final
-            mma64<true, true>(acc, sP, sP, 0, CB, wm, wn, g, t);                  // W[J,J] -= L[J,J-1] L[J,J-1]^T
-            acc_to_smem(acc, sD, wm, wn, g, t);
-            __syncthreads();
-            // ragged last block: identity on the padding (rows / columns >= m are zero after the product)
-            for (int e = tid; e < CB; e += 256) if (j0 + e >= m) sD[e * CLD + e] = 1.0;
-            __syncthreads();
-        }
-        const double ls = diag_factor_inverse(sD, sX, sS, rinv, colbuf, &bad, tid, warp, g, t);
-        if (warp == 0) logtot += ls;
-        // publish X_J (workers read it from the X buffer; Linv[J,J] = X_J) and L_JJ
-        {
-            double* xdst = p.X + (size_t)J * CB * CB;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                int e = tid + q * 256;
-                int r = e >> 5, c = (e & 31) * 2;
-                *reinterpret_cast<double2*>(xdst + r * CB + c) = *reinterpret_cast<const double2*>(sX + r * CLD + c);
+            DF_STAMP(1);
+            {   // ---- P0: rows 0..31 of L[J,J-1] = W[J,J-1] X^T (X[n][k] = 0 for k > n), written over the tile in place
+                const int wr = warp >> 2, wc = warp & 3;
+                double a0[2][2][2] = {};
+                mma_sub<true, false, 2, 2>(a0, sA, wr * 16, sX, wc * 16, 0, wc * 16 + 16, g, t);
+                __syncthreads();
+                sub_store<2, 2>(a0, sA, wr * 16, wc * 16, g, t);
+                __syncthreads();
             }
-            if (p.want_inv) smem_to_global(sX, p.Linv, p.mp, j0, j0, m, m, tid);
-            if (p.L) smem_to_global(sD, p.L, m, j0, j0, m, m, tid);
+            DF_STAMP(2);
+            {   // ---- D00 = W[J,J][0:32,0:32] - P0 P0^T
+                const int wr = warp >> 1, wc = warp & 1;
+                double d0[1][2][2];
+                sub_load<1, 2>(d0, sDN, wr * 8, wc * 16, g, t);
+                mma_sub<true, true, 1, 2>(d0, sA, wr * 8, sA, wc * 16, 0, CB, g, t);
+                sub_store<1, 2>(d0, sD, wr * 8, wc * 16, g, t);
+            }
+            __syncthreads();
+            if (tid < 32 && j0 + tid >= m) sD[tid * CLD + tid] = 1.0;         // identity on the padding of a ragged last block
+            __syncwarp();
         }
-        __threadfence();
+        DF_STAMP(3);
+        // ---- warp 0: first in-warp factorisation; warps 1..7: the rest of the step's tile work
+        double* sLt = sS;
+        double lsum = 0.0;
+        if (warp == 0) {
+            lsum = factor32(sD, 0, rinv, colbuf, sLt, &bad);
+            __syncwarp();
+            DF_STAMP(4);
+            if (J > 0) bar_sync_n(2, 256);              // warps 1..7 have finished reading the previous X
+            invert32(sLt, 0, rinv, sX);
+            if (lane == 0) s_w0 = 2 * J + 1;
+            DF_STAMP(5);
+        } else {
+            const int w7 = warp - 1;
+            if (J > 0) {
+                // the previous step's X (and Linv / L diagonal blocks) were stored at its end: fence, then tell the workers
+                __threadfence();
+                bar_sync_n(3, 224);
+                if (tid == 32) df_post(fX + (J - 1), epoch, 1);
+                // P1: rows 32..63 of L[J,J-1], eight 16x16 sub-tiles over seven warps
+                double a1[2][2][2][2] = {};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int st = w7 + q * 7;
+                    if (st < 8) {
+                        const int r2 = st >> 2, c4 = st & 3;
+                        mma_sub<true, false, 2, 2>(a1[q], sA, 32 + r2 * 16, sX, c4 * 16, 0, c4 * 16 + 16, g, t);
+                    }
+                }
+                bar_arrive_n(2, 256);                   // done with the previous X: warp 0 may overwrite it
+                bar_sync_n(3, 224);                     // every read of the tile's rows 32..63 is done
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int st = w7 + q * 7;
+                    if (st < 8) sub_store<2, 2>(a1[q], sA, 32 + (st >> 2) * 16, (st & 3) * 16, g, t);
+                }
+                bar_sync_n(3, 224);
+                // L[J,J-1] to global memory, then fence and post
+                for (int e = tid - 32; e < CB * CB / 2; e += 224) {
+                    const int r = e >> 5, c = (e & 31) * 2;
+                    const int gr = j0 + r, gc = j0 - CB + c;
+                    if (gr < m) {
+                        const double2 v = *reinterpret_cast<const double2*>(sA + r * CLD + c);
+                        if (AL16) {
+                            *reinterpret_cast<double2*>(p.W + (int64_t)gr * m + gc) = v;
+                            if (p.L) *reinterpret_cast<double2*>(p.L + (int64_t)gr * m + gc) = v;
+                        } else {
+                            p.W[(int64_t)gr * m + gc] = v.x; p.W[(int64_t)gr * m + gc + 1] = v.y;
+                            if (p.L) { p.L[(int64_t)gr * m + gc] = v.x; p.L[(int64_t)gr * m + gc + 1] = v.y; }
+                        }
+                    }
+                }
+                __threadfence();
+                bar_sync_n(3, 224);
+                if (tid == 32) df_post(cW + J * nb + (J - 1), epoch, J);      // posted before the diagonal update: the workers' jobs on block column J start early
+                // D10 (four 16x16 sub-tiles) and the lower three of D11: one per warp
+                {
+                    int r0, c0;
+                    const double* Bp;
+                    int brow;
+                    if (w7 < 4) { r0 = 32 + (w7 >> 1) * 16; c0 = (w7 & 1) * 16; brow = c0; }
+                    else { const int q = w7 - 4; const int r2 = q == 0 ? 0 : 1, c2 = q == 2 ? 1 : 0; r0 = 32 + r2 * 16; c0 = 32 + c2 * 16; brow = c0; }
+                    Bp = sA;
+                    double d1[2][2][2];
+                    sub_load<2, 2>(d1, sDN, r0, c0, g, t);
+                    mma_sub<true, true, 2, 2>(d1, sA, r0, Bp, brow, 0, CB, g, t);
+                    sub_store<2, 2>(d1, sD, r0, c0, g, t);
+                    if (w7 == 4) {                      // the strictly upper sub-tile of D11 is never used: keep it finite
+                        double u[2][2][2];
+                        sub_load<2, 2>(u, sDN, 32, 48, g, t);
+                        sub_store<2, 2>(u, sD, 32, 48, g, t);
+                    }
+                }
+                bar_sync_n(3, 224);                     // every read of sDN is done: warp 7 may refill it
+                for (int e = tid - 32; e < 32; e += 224)
+                    if (j0 + 32 + e >= m) sD[(32 + e) * CLD + 32 + e] = 1.0;          // ragged last block
+            }
+            if (warp == 7) {
+                if (lane == 0) s_pf = 0;
+                __syncwarp();
+                try_prefetch(J + 1, sAn, 2 * J + 1);
+            }
+        }
         __syncthreads();
-        if (tid == 0) df_post(fX + J, epoch, 1);
+        const int sr = (warp >> 1) * 8 + g, sc = (warp & 1) * 16 + 2 * t;
+        {   // L10 = D10 X00^T, then D11 -= L10 L10^T
+            double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            mma32<true, false>(o, sD + 32 * CLD, sX, warp, g, t);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<double2*>(sD + (32 + sr) * CLD + sc + j * 8) = make_double2(o[j][0], o[j][1]);
+            __syncthreads();
+            double d[2][2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double2 dd = *reinterpret_cast<const double2*>(sD + (32 + sr) * CLD + 32 + sc + j * 8);
+                d[j][0] = dd.x; d[j][1] = dd.y;
+            }
+            mma32<true, true>(d, sD + 32 * CLD, sD + 32 * CLD, warp, g, t);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<double2*>(sD + (32 + sr) * CLD + 32 + sc + j * 8) = make_double2(d[j][0], d[j][1]);
+        }
+        __syncthreads();
+        DF_STAMP(6);
+        if (warp == 0) {
+            lsum += factor32(sD, 32, rinv, colbuf, sLt, &bad);
+            __syncwarp();
+            DF_STAMP(7);
+            invert32(sLt, 32, rinv, sX);
+            if (lane == 0) s_w0 = 2 * J + 2;
+            logtot += lsum;
+        } else if (warp == 7) {
+            try_prefetch(J + 1, sAn, 2 * J + 2);
+        }
+        __syncthreads();
+        DF_STAMP(8);
+        {   // X10 = -X11 (L10 X00); T = L10 X00 parks in the lower half of the scratch block
+            double* sT = sS;
+            double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            mma32<false, false>(o, sD + 32 * CLD, sX, warp, g, t);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<double2*>(sT + (32 + sr) * CLD + sc + j * 8) = make_double2(o[j][0], o[j][1]);
+            __syncthreads();
+            double x[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            mma32<false, true>(x, sX + 32 * CLD + 32, sT + 32 * CLD, warp, g, t);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<double2*>(sX + (32 + sr) * CLD + sc + j * 8) = make_double2(x[j][0], x[j][1]);
+        }
+        __syncthreads();
+        DF_STAMP(9);
+        // ---- warps 1..7 store X_J (workers read it from the X buffer; Linv[J,J] = X_J) and L_JJ; the fence and the post
+        //      follow at the start of the next step, under its first factorisation
+        if (warp > 0) {
+            double* xdst = p.X + (size_t)J * CB * CB;
+            for (int e = tid - 32; e < CB * CB / 2; e += 224) {
+                const int r = e >> 5, c = (e & 31) * 2;
+                const double2 v = *reinterpret_cast<const double2*>(sX + r * CLD + c);
+                *reinterpret_cast<double2*>(xdst + r * CB + c) = v;
+                const int gr = j0 + r, gc = j0 + c;
+                if (p.want_inv && gr < m) {
+                    if (gc + 1 < m) *reinterpret_cast<double2*>(p.Linv + (int64_t)gr * p.mp + gc) = v;
+                    else if (gc < m) p.Linv[(int64_t)gr * p.mp + gc] = v.x;
+                }
+                if (p.L && gr < m) {
+                    const double2 l = *reinterpret_cast<const double2*>(sD + r * CLD + c);
+                    if (gc < m) p.L[(int64_t)gr * m + gc] = l.x;
+                    if (gc + 1 < m) p.L[(int64_t)gr * m + gc + 1] = l.y;
+                }
+            }
+        }
+        DF_STAMP(10);
     }
-    if (tid == 0) {
-        p.d_out[0] = -logtot;
-        if (bad) atomicOr(p.status, ACCBPG_ST_NOT_PD);
+    if (warp > 0) {
         __threadfence();
-        df_post(p.aux + 3, epoch, 1);          // the last worker leaves only after this: the pair of launches is complete
+        bar_sync_n(3, 224);
+        if (tid == 32) df_post(fX + (nb - 1), epoch, 1);
+        bar_arrive_n(2, 256);
+    } else {
+        bar_sync_n(2, 256);                             // the last X has been posted
+        if (tid == 0) {
+            p.d_out[0] = -logtot;
+            if (bad) atomicOr(p.status, ACCBPG_ST_NOT_PD);
+            __threadfence();
+            df_post(p.aux + 3, epoch, 1);               // the last worker leaves only after this: the pair of launches is complete
+        }
     }
 }
 
@@ -975,11 +1187,15 @@ int chol_factor_inv_df(Ctx* c, cudaStream_t s, int m, int mp, const double* M, d
     if (nworkers > p.njobs) nworkers = p.njobs;
     if (nworkers < 1) nworkers = 1;
     p.nworkers = nworkers;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("ACCBPG_DF_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool al16 = (m % 2 == 0) && al(M) && al(W) && (!L || al(L));
     if (al16) chol_spine_kernel<true><<<1, 256, DF_SPINE_SMEM, s>>>(p);
     else      chol_spine_kernel<false><<<1, 256, DF_SPINE_SMEM, s>>>(p);
     ACCBPG_LAUNCHED("chol_spine_kernel");
+    if (dbg & 1) return ACCBPG_OK;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -441,6 +441,264 @@ __global__ void __launch_bounds__(kBurgThreads) burg_simplex_kernel(int64_t n, c
     }
 }
 
+// ---------------------------------------------------------------- Burg-simplex root-find, exchange form
+// The same recurrence (functions.py:341-356) with the iterate held in REGISTERS and the grid-wide reductions done by a
+// two-level exchange of partial sums through a slot table instead of grid.sync + a second pass over L2 (burgx_round):
+// blocks -> their rank's leader block -> all leaders (NVLink peer memory when the vector is column-sharded) -> one result
+// word per rank.  Sums are added in block order, then in rank order, so the multiplier c and the step counts are
+// bit-identical on every rank, per-rank work is O(n / world), and a Newton step costs three store -> poll hops (two on one
+// GPU) instead of a grid barrier plus an L2 round trip.
+// Launched as an ordinary kernel with at most as many blocks as are co-resident on an idle GPU: blocks that are not
+// resident yet are waited for by the others (nothing they wait for depends on this kernel), cooperative launches of
+// different streams would serialise against each other.
+constexpr int kMaxPeerRanks = 16;
+constexpr int kPeerScalars = 16;
+constexpr int kBurgSlot = 4;                           // doubles per slot: a, token, b, token
+constexpr int kBurgMaxG = kMaxBlocks / 4;              // 296 blocks per rank at most
+struct BurgX {
+    double* tab[kMaxPeerRanks];                        // every rank's table (layout at burgx_round)
+    int rank, world;
+    unsigned long long base;                           // token of round r is base + r (unique per call on these tables)
+};
+
+// a value and its round token travel together in one aligned 16-byte word (single transaction: the reader sees both or
+// neither), so a delivery needs no fence and a poll is one load
+__device__ __forceinline__ void st_pair(double* p, double v, unsigned long long tok) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(tok) : "memory");
+}
+__device__ __forceinline__ void ld_pair(const double* p, unsigned long long& v, unsigned long long& tok) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(tok) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_release_scope(unsigned long long* p, unsigned long long v, bool sys) {
+    if (sys) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    else asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_scope(const unsigned long long* p, bool sys) {
+    unsigned long long v;
+    if (sys) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// wait until the 16-byte word at p carries `token`; returns its value
+__device__ __forceinline__ double wait_pair(const double* p, unsigned long long token, bool sys) {
+    unsigned long long v, tk, t0 = 0;
+    unsigned spin = 0;
+    for (;;) {
+        ld_pair(p, v, tk);
+        if (tk == token) return __longlong_as_double((long long)v);
+        __nanosleep(32);
+        if ((++spin & 0x3ffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > (sys ? 120000000000ULL : 4000000000ULL)) __trap();
+        }
+    }
+}
+
+// gather `count` slots (a, b pairs) starting at `slots` in increasing index: the 32 lanes of one warp take slots
+// lane, lane + 32, ... (four in flight each), add them up in that order, then a fixed shuffle tree
+template <bool IS_MIN>
+__device__ __forceinline__ void gather_slots(const double* slots, int count, unsigned long long token, bool sys, double& ra,
+                                             double& rb) {
+    const int lane = threadIdx.x & 31;
+    double sa = IS_MIN ? kInf : 0.0, sb = 0.0;
+    for (int q0 = lane; q0 < count; q0 += 32 * 4) {
+        double va[4], vb[4];
+        unsigned done = 0, want = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (q0 + 32 * u < count) want |= 1u << u;
+        unsigned long long t0 = 0;
+        unsigned spin = 0;
+        while (done != want) {
+            unsigned long long wa[4], ta[4], wb[4], tb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((want & ~done) & (1u << u)) {
+                    const double* sl = slots + (size_t)(q0 + 32 * u) * kBurgSlot;
+                    ld_pair(sl, wa[u], ta[u]);
+                    ld_pair(sl + 2, wb[u], tb[u]);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (((want & ~done) & (1u << u)) && ta[u] == token && tb[u] == token) {
+                    va[u] = __longlong_as_double((long long)wa[u]);
+                    vb[u] = __longlong_as_double((long long)wb[u]);
+                    done |= 1u << u;
+                }
+            if (done != want && (++spin & 0x3ffu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > (sys ? 120000000000ULL : 4000000000ULL)) __trap();
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (want & (1u << u)) {
+                if (IS_MIN) sa = fmin(sa, va[u]);
+                else { sa += va[u]; sb += vb[u]; }
+            }
+    }
+    if (IS_MIN) { ra = warp_min(sa); rb = 0.0; }
+    else { ra = warp_sum(sa); rb = warp_sum(sb); }
+}
+
+// One exchange round; (a, b) are this thread's partial sums (IS_MIN: a is a partial minimum, b unused).  Two levels, so
+// that no cache line is polled by more than one block except the single result word:
+//   every block delivers its partials to its rank's leader (block 0), which adds them in block order;
+//   the leaders deliver the rank's sums to every rank's leader (NVLink) and add them in rank order;
+//   the leader publishes the total in one word that the other blocks of its rank wait for.
+// Every store carries its value and the round's token in one 16-byte word: no fences.  Table of a rank (kBurgSlot doubles
+// per slot):  A [2][kBurgMaxG] block partials, then B [2][kMaxPeerRanks] rank sums, then C [2] totals.
+constexpr int kBurgOffB = 2 * kBurgMaxG;
+constexpr int kBurgOffC = kBurgOffB + 2 * kMaxPeerRanks;
+constexpr int kBurgTableSlots = kBurgOffC + 2;
+template <bool IS_MIN>
+__device__ __forceinline__ void burgx_round(const BurgX& X, int round, double a, double b, double* sh, int& flip, double& ra,
+                                            double& rb) {
+    const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    const bool sys = X.world > 1;
+    double* s = sh + flip * 64;
+    flip ^= 1;
+    if (IS_MIN) {
+        a = warp_min(a);
+        if (lane == 0) s[wid] = a;
+    } else {
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) { s[wid] = a; s[32 + wid] = b; }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        double ba, bb = 0.0;
+        if (IS_MIN) ba = warp_min((lane < nw) ? s[lane] : kInf);
+        else { ba = warp_sum((lane < nw) ? s[lane] : 0.0); bb = warp_sum((lane < nw) ? s[32 + lane] : 0.0); }
+        const unsigned long long token = X.base + (unsigned long long)round;
+        const int par = round & 1;
+        double* tab = X.tab[X.rank];
+        if (lane == 0) {
+            double* dst = tab + ((size_t)par * kBurgMaxG + blockIdx.x) * kBurgSlot;
+            st_pair(dst, ba, token);
+            st_pair(dst + 2, bb, token);
+        }
+        double ta, tb;
+        if (blockIdx.x == 0) {
+            gather_slots<IS_MIN>(tab + (size_t)par * kBurgMaxG * kBurgSlot, G, token, false, ta, tb);
+            if (X.world > 1) {
+                if (lane < X.world) {
+                    double* dst = X.tab[lane] + ((size_t)kBurgOffB + par * kMaxPeerRanks + X.rank) * kBurgSlot;
+                    st_pair(dst, ta, token);
+                    st_pair(dst + 2, tb, token);
+                }
+                gather_slots<IS_MIN>(tab + ((size_t)kBurgOffB + par * kMaxPeerRanks) * kBurgSlot, X.world, token, true, ta, tb);
+            }
+            if (lane == 0) {
+                double* dst = tab + ((size_t)kBurgOffC + par) * kBurgSlot;
+                st_pair(dst, ta, token);
+                st_pair(dst + 2, tb, token);
+            }
+        } else {
+            const double* src = tab + ((size_t)kBurgOffC + par) * kBurgSlot;
+            ta = 0.0; tb = 0.0;
+            if (lane == 0) { ta = wait_pair(src, token, false); tb = wait_pair(src + 2, token, false); }
+        }
+        double* o = sh + flip * 64;                    // the other buffer: nobody reads it before the barrier below
+        if (lane == 0) { o[0] = ta; o[1] = tb; }
+    }
+    __syncthreads();
+    ra = sh[flip * 64];
+    rb = sh[flip * 64 + 1];
+    flip ^= 1;
+}
+
+// EPT > 0: each thread keeps EPT elements of gg in registers (n <= EPT * G * 512); EPT == 0: gg lives in `out` and is
+// re-read every round (any n)
+template <int EPT>
+__global__ void __launch_bounds__(kBurgThreads) burg_simplex_x_kernel(int64_t n, const double* y, const double* g, double L,
+                                                                      double eps, double* out, double* info,
+                                                                      uint32_t* status, BurgX X) {
+    __shared__ double sh[128];
+    const int tid = threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + tid;
+    uint32_t st = 0;
+    double gg[EPT > 0 ? EPT : 1];
+    double lo = kInf;
+    if (EPT > 0) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int64_t i = first + e * stride;
+            gg[e] = kInf;                               // padding drops out of the minimum and of both sums
+            if (i < n) { gg[e] = burg_shift(y, g, L, i, st) / L; lo = fmin(lo, gg[e]); }
+        }
+    } else {
+        for (int64_t i = first; i < n; i += stride) {
+            const double v = burg_shift(y, g, L, i, st) / L;
+            out[i] = v;
+            lo = fmin(lo, v);
+        }
+    }
+    int flip = 0, round = 0;
+    double s1, s2;
+    burgx_round<true>(X, round++, lo, 0.0, sh, flip, s1, s2);
+    const double cmin = -s1;
+    double c = cmin + 1.0;
+    int nbis = 0, nnewton = 0;
+    auto sums = [&](double cc, double& a, double& b) {
+        a = 0.0; b = 0.0;
+        if (EPT > 0) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const double t = gg[e] + cc;
+                a += 1.0 / t;
+                b += -1.0 / (t * t);
+            }
+        } else {
+            for (int64_t i = first; i < n; i += stride) {
+                const double t = out[i] + cc;
+                a += 1.0 / t;
+                b += -1.0 / (t * t);
+            }
+        }
+    };
+    // bisection: halve toward cmin until sum 1/(gg+c) - 1 >= 0   (functions.py:344-346)
+    for (;;) {
+        double a, b;
+        sums(c, a, b);
+        burgx_round<false>(X, round++, a, b, sh, flip, s1, s2);
+        if (s1 - 1.0 < 0.0 && nbis < 2000) { c = (cmin + c) / 2.0; ++nbis; }
+        else break;
+    }
+    double fc = s1 - 1.0;
+    // Newton  (functions.py:348-354); s2 already holds fpc at the current c
+    while (fabs(fc) > eps) {
+        const double fpc = s2;
+        const double cn = c - fc / fpc;
+        if (c - cn == 0.0) break;
+        c = cn;
+        double a, b;
+        sums(c, a, b);
+        burgx_round<false>(X, round++, a, b, sh, flip, s1, s2);
+        fc = s1 - 1.0;
+        if (++nnewton >= 200) { st |= ACCBPG_ST_NEWTON_MAXIT; break; }
+    }
+    if (EPT > 0) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int64_t i = first + e * stride;
+            if (i < n) out[i] = 1.0 / (gg[e] + c);
+        }
+    } else {
+        for (int64_t i = first; i < n; i += stride) out[i] = 1.0 / (out[i] + c);
+    }
+    if (st) atomicOr(status, st);
+    if (info != nullptr && blockIdx.x == 0 && tid == 0) {
+        info[0] = (double)nbis; info[1] = (double)nnewton; info[2] = c;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) burg_prepare_kernel(int64_t n, const double* y, const double* g,
                                                                 double L, double* gg, double* partials,
                                                                 unsigned int* counter, double* out,
@@ -467,8 +725,6 @@ __global__ void __launch_bounds__(kThreads) burg_prepare_kernel(int64_t n, const
 }
 
 // ---- exchanges over NVLink peer memory (column-sharded runs; buffers mapped into every rank) ----
-constexpr int kMaxPeerRanks = 16;
-constexpr int kPeerScalars = 16;
 struct PeerVec {
     double* buf[kMaxPeerRanks];                    // every rank's receive buffer, double-buffered on the epoch's parity
     unsigned long long* flags[kMaxPeerRanks];      // every rank's flag words, one per sender
@@ -621,6 +877,8 @@ int accbpg_ctx_create(void** out) {
     ACCBPG_CUDA(cudaMalloc(&c->d_partials, (size_t)kPartialRows * kPartialStride * sizeof(double)));
     ACCBPG_CUDA(cudaMalloc(&c->d_ipartials, (size_t)kPartialStride * sizeof(long long)));
     ACCBPG_CUDA(cudaMalloc(&c->d_counter, 256));
+    ACCBPG_CUDA(cudaMalloc(&c->d_burg_slots, (size_t)kBurgTableSlots * kBurgSlot * sizeof(double)));
+    ACCBPG_CUDA(cudaMemset(c->d_burg_slots, 0, (size_t)kBurgTableSlots * kBurgSlot * sizeof(double)));
     ACCBPG_CUDA(cudaMemset(c->d_slots, 0, kSlots * sizeof(double)));
     ACCBPG_CUDA(cudaMemset(c->d_status, 0, 256));
     ACCBPG_CUDA(cudaMemset(c->d_counter, 0, 256));
@@ -651,7 +909,7 @@ int accbpg_ctx_destroy(void* ctx) {
     if (!c) return ACCBPG_OK;
     ACCBPG_ON_DEVICE(c);
     cudaFree(c->d_slots); cudaFree(c->d_status); cudaFree(c->d_partials);
-    cudaFree(c->d_ipartials); cudaFree(c->d_counter);
+    cudaFree(c->d_ipartials); cudaFree(c->d_counter); cudaFree(c->d_burg_slots);
     cudaFreeHost(c->h_slots); cudaFreeHost(c->h_status);
     cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
     cudaStreamDestroy(c->side2); cudaEventDestroy(c->ev_early_done);
@@ -810,21 +1068,69 @@ int accbpg_burg_prox(void* ctx, void* stream, int64_t n, int kind, double lamda,
     double lamL = lamda / L;
     return launch_map(c, s, n, BurgProxF{kind, lamda, L, 4 * lamL, 2 * lamL, y, g, out}, "burg_prox");
 }
+static int burgx_launch(Ctx* c, cudaStream_t s, int64_t n, int64_t width, const double* y, const double* g, double L, double eps,
+                        double* out, double* info, const BurgX& X) {
+    // the grid depends on `width` only (the widest slice), so every rank uses the same slot layout
+    int64_t want = (width + kBurgThreads - 1) / kBurgThreads;
+    static int per_sm_x = 0;                           // co-resident blocks per SM of the exchange-form kernel (all variants)
+    if (per_sm_x == 0) {
+        int a = 0, b = 0;
+        ACCBPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, burg_simplex_x_kernel<8>, kBurgThreads, 0));
+        ACCBPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, burg_simplex_x_kernel<0>, kBurgThreads, 0));
+        per_sm_x = a < b ? a : b;
+        if (per_sm_x < 1) return arg_err("burg_simplex_x_kernel cannot be made resident");
+        if (per_sm_x > 2) per_sm_x = 2;
+    }
+    int cap = c->sm_count * per_sm_x;
+    if (cap > kBurgMaxG) cap = kBurgMaxG;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    const int64_t per = (width + (int64_t)grid * kBurgThreads - 1) / ((int64_t)grid * kBurgThreads);
+    ProfScope ps(P_BURG_SIMPLEX, s);
+    if (per <= 1) burg_simplex_x_kernel<1><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X);
+    else if (per <= 2) burg_simplex_x_kernel<2><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X);
+    else if (per <= 4) burg_simplex_x_kernel<4><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X);
+    else if (per <= 8) burg_simplex_x_kernel<8><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X);
+    else burg_simplex_x_kernel<0><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X);
+    ACCBPG_LAUNCHED("burg_simplex_x_kernel");
+    return ACCBPG_OK;
+}
+
 int accbpg_burg_simplex_prox(void* ctx, void* stream, int64_t n, const double* y, const double* g, double L,
                              double eps, double* out, double* info) {
     CTX_STREAM
     if (!(L > 0.0)) return arg_err("L must be positive");
     if (n < 1) return arg_err("n must be >= 1");
-    int64_t want = (n + kBurgThreads - 1) / kBurgThreads;
-    int grid = (int)(want < c->coop_blocks_burg ? want : c->coop_blocks_burg);
-    double* partials = c->d_partials;
-    uint32_t* status = c->d_status;
-    const double* gg_in = nullptr;
-    void* args[] = {&n, &y, &g, &L, &eps, &out, &info, &partials, &status, &gg_in};
-    ProfScope ps(P_BURG_SIMPLEX, s);
-    ACCBPG_CUDA(cudaLaunchCooperativeKernel((void*)burg_simplex_kernel, dim3(grid), dim3(kBurgThreads), args, 0, s));
-    ACCBPG_LAUNCHED("burg_simplex_prox");
-    return ACCBPG_OK;
+    BurgX X;
+    X.tab[0] = c->d_burg_slots;
+    X.rank = 0; X.world = 1;
+    X.base = (++c->burg_calls) << 12;                  // at most 2201 rounds per call
+    return burgx_launch(c, s, n, n, y, g, L, eps, out, info, X);
+}
+
+size_t accbpg_burg_simplex_peer_doubles(int world) {
+    return world < 1 ? 0 : (size_t)kBurgTableSlots * kBurgSlot;
+}
+
+int accbpg_burg_simplex_prox_peer(void* ctx, void* stream, int64_t n_local, int64_t width, const double* y, const double* g,
+                                  double L, double eps, int rank, int world, void* const* peer_slots, uint64_t epoch,
+                                  double* out, double* info) {
+    Ctx* c = (Ctx*)ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c) return arg_err("ctx is NULL");
+    ACCBPG_ON_DEVICE(c);
+    if (!g || !out || !peer_slots) return arg_err("burg_simplex_prox_peer: NULL pointer");
+    if (!(L > 0.0)) return arg_err("L must be positive");
+    if (n_local < 0 || width < n_local || width < 1) return arg_err("burg_simplex_prox_peer: width");
+    if (world < 1 || world > kMaxPeerRanks || rank < 0 || rank >= world || epoch < 1) return arg_err("burg_simplex_prox_peer: rank / world / epoch");
+    BurgX X;
+    for (int r = 0; r < world; ++r) {
+        X.tab[r] = (double*)peer_slots[r];
+        if (!X.tab[r]) return arg_err("burg_simplex_prox_peer: NULL peer pointer");
+    }
+    X.rank = rank; X.world = world;
+    X.base = (unsigned long long)epoch << 12;
+    return burgx_launch(c, s, n_local, width, y, g, L, eps, out, info, X);
 }
 int accbpg_burg_simplex_root(void* ctx, void* stream, int64_t n, const double* gg, double eps, double* d_info) {
     CTX_STREAM

@@ -122,8 +122,10 @@ int accbpg_burg_divergence(void* ctx, void* stream, int64_t n, const double* d_x
 /* prox_map(g, L) when d_y == NULL, div_prox_map(y, g, L) = prox_map(g - L*(-1/y), L) otherwise (:264-271) */
 int accbpg_burg_prox(void* ctx, void* stream, int64_t n, int kind, double lamda,
                      const double* d_y, const double* d_g, double L, double* d_out_vec);
-/* BurgEntropySimplex.prox_map / inherited div_prox_map (functions.py:336-356): one persistent
- * cooperative kernel replays cmin, bisection and Newton with grid-wide reductions.
+/* BurgEntropySimplex.prox_map / inherited div_prox_map (functions.py:336-356): one persistent kernel replays cmin,
+ * bisection and Newton with the iterate in registers; the grid-wide sums of a step go through a slot table (block
+ * partials to a leader block, total back in one word; value + round token per 16-byte store, fixed-order adds): no host
+ * round trip and no grid barrier per Newton step.
  * d_info (3 slots, may be NULL): bisection steps, Newton steps, final c. */
 int accbpg_burg_simplex_prox(void* ctx, void* stream, int64_t n, const double* d_y, const double* d_g,
                              double L, double eps, double* d_out_vec, double* d_info);
@@ -155,6 +157,16 @@ int accbpg_burg_simplex_push_peer(void* ctx, void* stream, int64_t n_local, int6
                                   void* const* peer_flags, uint64_t epoch, double* d_gg_local);
 int accbpg_burg_simplex_root_peer(void* ctx, void* stream, int64_t width, double eps, int rank, int world,
                                   void* const* peer_gg, void* const* peer_flags, uint64_t epoch, double* d_info);
+/* The column-sharded prox as ONE kernel per rank (functions.py:336-356 with the vector split over the ranks): the blocks
+ * of a rank deliver their partial (sum 1/(gg+c), sum -1/(gg+c)^2) of a step to the rank's leader block, the leaders
+ * exchange the rank sums over NVLink (one 16-byte store per value and peer, value and round token in one word) and add
+ * them in rank order: the multiplier and the step counts are bit-identical on every rank, per-rank work is O(n_local).  `width` = the widest slice (the same on every
+ * rank: it fixes the grid).  peer_slots: host array of `world` device pointers to every rank's symmetric table of
+ * accbpg_burg_simplex_peer_doubles(world) doubles, zeroed once; epoch 1, 2, 3, ... per call, the same on every rank. */
+size_t accbpg_burg_simplex_peer_doubles(int world);
+int accbpg_burg_simplex_prox_peer(void* ctx, void* stream, int64_t n_local, int64_t width, const double* d_y,
+                                  const double* d_g, double L, double eps, int rank, int world, void* const* peer_slots,
+                                  uint64_t epoch, double* d_out_vec, double* d_info);
 /* Sum `count` (<= 15) per-rank partial scalars at d_in over the ranks through peer memory, in rank order, into d_out
  * (may equal d_in) (the batched divergence / dot-product partials of a driver iteration, algorithms.py:53,153-154,...):
  * one small kernel instead of an NCCL all-reduce.  The exchange also carries every rank's status word and ORs them into

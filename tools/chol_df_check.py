@@ -28,7 +28,7 @@ for m in ms:
             nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, m, M.data_ptr(), None, want, ws.data_ptr(), rt.slot(40)))
         b.record(); torch.cuda.synchronize()
         us = a.elapsed_time(b) / reps * 1e3
-        f = rt.read(40, 1)[0]
+        f = rt.read_raw(40, 1)[0][0]
         Lt = torch.linalg.cholesky(M)
         fref = -2 * torch.log(torch.diagonal(Lt)).sum().item()
         eL = (L - Lt).abs().max().item() / Lt.abs().max().item()

@@ -47,5 +47,36 @@ int main(int argc, char** argv) {
             printf(" | %7.2f | %6.2f\n", (t[15] - t[14]) * 1e-3, J ? (t[14] - tr[(J - 1) * 16 + 15]) * 1e-3 : 0.0);
         }
     }
+    // ---- data-flow chain: phase stamps of the spine CTA
+    {
+        long long* dtr;
+        cudaMalloc(&dtr, nblk * 16 * 8);
+        cudaMemset(dtr, 0, nblk * 16 * 8);
+        cudaMemcpyToSymbol(g_df_trace_dev, &dtr, sizeof(dtr));
+        void* aux;
+        size_t ab = chol_df_aux_bytes(m);
+        cudaMalloc(&aux, ab); cudaMemset(aux, 0, ab);
+        cudaMemset(dLinv, 0, (size_t)mp * mp * 8);
+        c.sm_count = 148;
+        for (int want = 1; want >= 0; --want) {
+            for (int rep = 0; rep < 3; ++rep) {
+                cudaEventRecord(e0, s);
+                int rc = chol_factor_inv(&c, s, m, mp, dM, nullptr, want, dLinv, dW, dY, dacc, dacc + 1, nullptr, aux);
+                cudaEventRecord(e1, s);
+                cudaStreamSynchronize(s);
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                printf("DF m %d want_inv %d rc %d  total %.1f us  (%s)\n", m, want, rc, ms * 1e3, cudaGetErrorString(cudaGetLastError()));
+            }
+            std::vector<long long> tr(nblk * 16);
+            cudaMemcpy(tr.data(), dtr, nblk * 16 * 8, cudaMemcpyDeviceToHost);
+            printf(" J | tiles  P0  D00  fac0  inv0  sync+prod1  fac1  inv1+sync  prod2  stores | step cycles\n");
+            for (int J = 0; J < nblk; ++J) {
+                long long* t = &tr[J * 16];
+                printf("%2d |", J);
+                for (int i = 1; i <= 10; ++i) printf(" %6lld", (t[i] && t[i - 1]) ? t[i] - t[i - 1] : 0LL);
+                printf(" | %7lld\n", t[10] - t[0]);
+            }
+        }
+    }
     return 0;
 }
