@@ -79,7 +79,7 @@ constexpr int kMaxDevices = 64;      // per-device once-flags (function attribut
 
 // optional cudaEvent bracketing of selected launches (prof.cu); a no-op unless accbpg_prof_enable(1)
 enum ProfId { P_SYRK = 0, P_SYRK_REDUCE, P_CHOL, P_TRINV, P_TRMM, P_GRAD_FIN, P_BURG_SIMPLEX, P_MATVEC, P_RMATVEC,
-              P_FW_PASS, P_FW_ITER, P_GRAM_PUSH, P_GRAM_SUM, P_GG_PUSH, P_GG_WAIT, P_SCAL_SUM, P_COUNT };
+              P_FW_PASS, P_FW_ITER, P_GRAM_PUSH, P_GRAM_SUM, P_GG_PUSH, P_GG_WAIT, P_SCAL_SUM, P_FW_BATCH, P_COUNT };
 struct ProfScope {
     ProfScope(int id, cudaStream_t s);
     ~ProfScope();

@@ -153,7 +153,8 @@ struct FwParams {
 
 // The decision of iteration p.k from the merged candidates (thread 0 of the last CTA), then the gather of the chosen
 // column by the whole CTA.  D_opt_alg.py:52-82 / :136-179.
-__device__ __forceinline__ void fw_decide(const FwParams& p, const FwCand& cd, int* sh_go, long long* sh_idx) {
+__device__ __forceinline__ void fw_decide(const FwParams& p, const FwCand& cd, int* sh_go, long long* sh_idx, int k_it = -1) {
+    const int kk = k_it >= 0 ? k_it : p.k;          // the persistent loop passes its iteration explicitly
     if (threadIdx.x == 0) {
         double* c = p.ctrl;
         const double md = (double)p.m;
@@ -170,18 +171,18 @@ __device__ __forceinline__ void fw_decide(const FwParams& p, const FwCand& cd, i
         const double logdet = c[C_LOGDET_HI] + c[C_LOGDET_LO];
         const double eps_pos = wmax / md - 1.0;
         const double eps_neg = 1.0 - wj / md;
-        p.hist_F[p.k] = -logdet;                   // D_opt_alg.py:52 (-log det M) / :136 (log det Hinv)
-        p.hist_SP[p.k] = eps_pos;
-        p.hist_SN[p.k] = eps_neg;
+        p.hist_F[kk] = -logdet;                   // D_opt_alg.py:52 (-log det M) / :136 (log det Hinv)
+        p.hist_SP[kk] = eps_pos;
+        p.hist_SN[kk] = eps_neg;
         unsigned long long ns;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-        p.hist_T[p.k] = (double)ns;
+        p.hist_T[kk] = (double)ns;
         c[C_WMAX] = wmax; c[C_IMAX] = (double)imax;
         c[C_WMIN] = wj; c[C_JMIN] = (double)jmin;
-        c[C_NITER] = (double)(p.k + 1);
+        c[C_NITER] = (double)(kk + 1);
         int go = 1;
         if (eps_pos <= p.eps && eps_neg <= p.eps) {   // :72-73 / :159-160
-            c[C_STOP] = 1.0; c[C_KSTOP] = (double)p.k;
+            c[C_STOP] = 1.0; c[C_KSTOP] = (double)kk;
             go = 0;
         } else {
             double t, cs, den, inc, tsign;
@@ -425,13 +426,21 @@ __global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(FwParams p) {
                     s1 += uq * a[q].y;
                 }
             }
-            for (; r < r1; ++r) {
-                double2 a;
-                asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
-                             : "=d"(a.x), "=d"(a.y) : "l"(col + (int64_t)r * p.ldv));
-                double uq = us[r];
-                s0 += uq * a.x;
-                s1 += uq * a.y;
+            const int rem = r1 - r;                      // < 16 rows left: one more batch, predicated
+            if (rem > 0) {
+                double2 a[FWP_UNROLL];
+#pragma unroll
+                for (int q = 0; q < FWP_UNROLL; ++q)
+                    if (q < rem)
+                        asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                                     : "=d"(a[q].x), "=d"(a[q].y) : "l"(col + (int64_t)(r + q) * p.ldv));
+#pragma unroll
+                for (int q = 0; q < FWP_UNROLL; ++q)
+                    if (q < rem) {
+                        double uq = us[r + q];
+                        s0 += uq * a[q].x;
+                        s1 += uq * a[q].y;
+                    }
             }
         } else {
             const bool two = (j + 1 < p.n);
@@ -466,6 +475,410 @@ __global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(FwParams p) {
     }
     if (!p.decide) return;
     fw_select_tail(p, cd, blk, p.nblk, sh_c, &sh_last, &sh_go, &sh_idx);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same loop as ONE persistent launch per batch of iterations (one GPU): one CTA per SM owns a fixed block of columns
+// of V for the whole batch and keeps part of it in shared memory, so an iteration reads less than all of V from HBM and
+// costs no kernel launches.  Per iteration k (the leader is CTA 0):
+//   every CTA gathers all CTAs' selection records, merges them and takes the decision of iteration k with the step rule of
+//            fw_decide on its own copy of the log-det accumulator (the same inputs give the same decision everywhere;
+//            CTA 0 writes the history entry and the control block), then gathers the chosen column v itself
+//   u_r = Hinv[r,:] v for the rows r = CTA + i G a CTA owns (warp per row), delivered as (value, token) words that
+//            every CTA collects: u is complete everywhere after one store -> poll hop
+//   rank-one update of the own rows of Hinv; the pass over the own columns (p_j = u^T v_j with the same four row groups
+//            and the same summation order as fw_pass_kernel, w_j and x_j updates); selection record of the updated
+//            slice published for the next decision
+// The arithmetic is that of the five-kernel iteration above, operation for operation: histories, vertex sequences and
+// iterates are bit-identical.  Exchanges are stores followed by a release of a token word that the consumer polls; tokens
+// are unique per launch and iteration, buffers alternate on the iteration's parity.
+constexpr int FWQ_THREADS = 512;
+constexpr int FWQ_TEAM = 256;
+constexpr int FWQ_REPL = 16;                            // replicas of the merged record (one line each)
+constexpr int FWQ_REC_DOUBLES = 16;                     // a selection record: 8 (value, token) words of 16 bytes = one 128-byte line
+
+struct FwPersist {
+    double* ux;                    // [2][m] (value, token) pairs: the entries of u, each written by the CTA that owns the row
+    double* bcast;                 // [2][FWQ_REPL][FWQ_REC_DOUBLES] the merged record of an iteration, replicated
+    double* recs;                  // [2][G][FWQ_REC_DOUBLES]
+    unsigned long long* tok;       // (unused)
+    unsigned long long base;
+    int G, k_start, k_count;
+    int per;                       // columns per CTA (even)
+    int rc4;                       // rows of every row group kept in shared memory
+    int dbg;                       // ACCBPG_FW_DBG: 1 print phase times of one iteration (CTA 0 and 1), 3 all CTAs via dbg_buf
+    unsigned long long* dbg_buf;
+};
+
+__device__ __forceinline__ void fwq_wait(const unsigned long long* p, unsigned long long token) {
+    unsigned long long t0 = 0;
+    unsigned spin = 0;
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (v == token) return;
+        __nanosleep(32);
+        if ((++spin & 0x3ffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ULL) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fwq_post(unsigned long long* p, unsigned long long token) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(token) : "memory");
+}
+__device__ __forceinline__ void fwq_st_pair(double* p, double v, unsigned long long tok) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(tok) : "memory");
+}
+__device__ __forceinline__ double fwq_wait_pair(const double* p, unsigned long long token) {
+    unsigned long long v, tk, t0 = 0;
+    unsigned spin = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(tk) : "l"(p) : "memory");
+        if (tk == token) return __longlong_as_double((long long)v);
+        __nanosleep(64);
+        if ((++spin & 0x3ffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ULL) __trap();
+        }
+    }
+}
+
+// rows [r, r1) of a column pair streamed from HBM, sixteen 16-byte loads in flight per thread; accumulates in row order.
+// Kept out of line so that its schedule (all sixteen loads issued before the first use) does not depend on the register
+// pressure of the exchange code around it.
+__device__ __noinline__ void fwq_stream(const double* col, int64_t ldv, const double* us, int r, int r1, double& s0, double& s1) {
+    double a0 = s0, a1 = s1;
+    for (; r + FWP_UNROLL <= r1; r += FWP_UNROLL) {
+        double2 a[FWP_UNROLL];
+#pragma unroll
+        for (int e = 0; e < FWP_UNROLL; ++e)
+            asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                         : "=d"(a[e].x), "=d"(a[e].y) : "l"(col + (int64_t)(r + e) * ldv));
+#pragma unroll
+        for (int e = 0; e < FWP_UNROLL; ++e) {
+            const double uq = us[r + e];
+            a0 += uq * a[e].x;
+            a1 += uq * a[e].y;
+        }
+    }
+    const int rem = r1 - r;                              // < 16 rows left: one more batch, predicated (a rolled loop would pay
+    if (rem > 0) {                                       // the HBM latency once per row)
+        double2 a[FWP_UNROLL];
+#pragma unroll
+        for (int e = 0; e < FWP_UNROLL; ++e)
+            if (e < rem)
+                asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                             : "=d"(a[e].x), "=d"(a[e].y) : "l"(col + (int64_t)(r + e) * ldv));
+#pragma unroll
+        for (int e = 0; e < FWP_UNROLL; ++e)
+            if (e < rem) {
+                const double uq = us[r + e];
+                a0 += uq * a[e].x;
+                a1 += uq * a[e].y;
+            }
+    }
+    s0 = a0; s1 = a1;
+}
+
+// the step rule of fw_decide on a copy of the log-det accumulator kept by every CTA (all CTAs take the same decision from
+// the same records; only the writer touches the control block and the histories)
+struct FwDec { double cs, den, tsign; long long idx; int go; };
+__device__ __forceinline__ void fwq_decide(const FwParams& p, const FwCand& cd, int kk, double& hi_state, double& lo_state,
+                                           bool writer, FwDec& d) {
+    double* c = p.ctrl;
+    const double md = (double)p.m;
+    const double wmax = -cd.amax;
+    const long long imax = cd.imax;
+    long long jmin = cd.imin;
+    double wj = cd.smin, xj = cd.xmin;
+    if (p.away && !(cd.imin != FW_NOIDX && cd.smin < wmax) && cd.fmask < cd.imin) {
+        jmin = cd.fmask; wj = cd.wmask; xj = cd.xmask;
+    }
+    if (jmin == FW_NOIDX) { jmin = 0; wj = wmax; xj = 1.0; }
+    const double logdet = hi_state + lo_state;
+    const double eps_pos = wmax / md - 1.0;
+    const double eps_neg = 1.0 - wj / md;
+    if (writer) {
+        p.hist_F[kk] = -logdet;
+        p.hist_SP[kk] = eps_pos;
+        p.hist_SN[kk] = eps_neg;
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        p.hist_T[kk] = (double)ns;
+        c[C_WMAX] = wmax; c[C_IMAX] = (double)imax;
+        c[C_WMIN] = wj; c[C_JMIN] = (double)jmin;
+        c[C_NITER] = (double)(kk + 1);
+    }
+    d.go = 1;
+    if (eps_pos <= p.eps && eps_neg <= p.eps) {
+        if (writer) { c[C_STOP] = 1.0; c[C_KSTOP] = (double)kk; }
+        d.go = 0;
+        return;
+    }
+    double t, cs, den, inc, tsign;
+    long long chosen;
+    int mode;
+    if (!p.away) {
+        t = (wmax / md - 1.0) / (wmax - 1.0);
+        double qq = 1.0 + t * (wmax - 1.0);
+        cs = t / qq; den = 1.0 - t; chosen = imax; mode = 0; tsign = t;
+        inc = (md - 1.0) * log(1.0 - t) + log(qq);
+    } else if (eps_pos >= eps_neg) {
+        t = (wmax / md - 1.0) / (wmax - 1.0);
+        double qq = 1.0 - t + t * wmax;
+        cs = t / qq; den = 1.0 - t; chosen = imax; mode = 0; tsign = t;
+        inc = (md - 1.0) * log1p(-t) + log(qq);
+    } else {
+        t = fmin((1.0 - wj / md) / (wj - 1.0), xj / (1.0 - xj));
+        double qq = 1.0 + t - t * wj;
+        cs = -(t / qq); den = 1.0 + t; chosen = jmin; mode = 1; tsign = -t;
+        inc = (md - 1.0) * log1p(t) + log(qq);
+    }
+    const double hi = hi_state;
+    const double sv = hi + inc;
+    const double bb = sv - hi;
+    const double err = (hi - (sv - bb)) + (inc - bb);
+    hi_state = sv;
+    lo_state += err;
+    if (writer) {
+        c[C_LOGDET_HI] = sv;
+        c[C_LOGDET_LO] = lo_state;
+        c[C_MODE] = (double)mode; c[C_T] = t; c[C_CS] = cs; c[C_DEN] = den;
+        c[C_IDX] = (double)chosen; c[C_TSIGN] = tsign;
+    }
+    d.cs = cs; d.den = den; d.tsign = tsign; d.idx = chosen;
+}
+
+__global__ void __launch_bounds__(FWQ_THREADS, 1) fw_persistent_kernel(FwParams p, FwPersist q) {
+    extern __shared__ __align__(16) double fsm[];
+    const int m = p.m;
+    const int mpad = (m + 1) / 2 * 2;
+    double* us = fsm;                                   // u
+    double* vs = us + mpad;                             // v (the chosen column)
+    double* part = vs + mpad;                           // [2 teams][4 row groups][128]
+    double* vc = part + 2 * 4 * FWP_COLS;               // [4 row groups][rc4][per]: rows kept from HBM
+    __shared__ FwCand sh_c[32];
+    __shared__ FwDec sh_dec;
+    __shared__ double sh_logdet[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = q.G, cta = blockIdx.x;
+    if (ld_cg(&p.ctrl[C_STOP]) != 0.0) return;          // stopped in an earlier batch: uniform over the grid
+    if (tid == 0) { sh_logdet[0] = ld_cg(&p.ctrl[C_LOGDET_HI]); sh_logdet[1] = ld_cg(&p.ctrl[C_LOGDET_LO]); }
+    const int64_t c0 = (int64_t)cta * q.per;
+    const int64_t c1 = c0 + q.per < p.n ? c0 + q.per : p.n;
+    const int ncol = c1 > c0 ? (int)(c1 - c0) : 0;
+    const int rows_per = (m + 3) / 4;
+    const double thr = p.away ? 1.0e-8 : 0.0;
+    const int team = tid >> 8, tt = tid & 255, rg = tt >> 6, ct = tt & 63;
+    const int r0 = rg * rows_per, r1 = min(m, r0 + rows_per);
+    const int rcn = min(q.rc4, max(r1 - r0, 0));        // cached rows of this row group
+    const int nown = cta < m ? (m - cta + G - 1) / G : 0;      // rows of Hinv / entries of u this CTA owns: cta + i G
+    // ---- the cached rows of the own column block
+    for (int g2 = 0; g2 < 4; ++g2) {
+        const int rr0 = g2 * rows_per, rrn = min(q.rc4, max(min(m, rr0 + rows_per) - rr0, 0));
+        for (int e = tid; e < rrn * (q.per / 2); e += FWQ_THREADS) {
+            const int rr = e / (q.per / 2), cp = (e - rr * (q.per / 2)) * 2;
+            double2 a = make_double2(0.0, 0.0);
+            if (c0 + cp < p.n) {
+                if (c0 + cp + 1 < p.n) a = *reinterpret_cast<const double2*>(p.V + (int64_t)(rr0 + rr) * p.ldv + c0 + cp);
+                else a.x = p.V[(int64_t)(rr0 + rr) * p.ldv + c0 + cp];
+            }
+            *reinterpret_cast<double2*>(vc + ((size_t)g2 * q.rc4 + rr) * q.per + cp) = a;
+        }
+    }
+    // ---- the record of the first decision: candidates of the own columns from (w, x) as they are
+    FwCand cd;
+    fw_cand_init(cd);
+    for (int64_t j = c0 + tid; j < c1; j += FWQ_THREADS) fw_cand_add(cd, p.w[j], p.x[j], j, thr);
+    auto deliver_record = [&](int it) {                 // record for the decision of batch iteration `it`
+        fw_cand_block(cd, sh_c);
+        if (tid < 8) {                                   // warp 0 holds the merged record in every lane: one word per lane
+            double* dst = q.recs + ((size_t)(it & 1) * G + cta) * FWQ_REC_DOUBLES;
+            const double f8[8] = {cd.amax, __longlong_as_double(cd.imax), cd.smin, __longlong_as_double(cd.imin), cd.xmin,
+                                  __longlong_as_double(cd.fmask), cd.wmask, cd.xmask};
+            double val = f8[0];
+#pragma unroll
+            for (int e = 1; e < 8; ++e) if (tid == e) val = f8[e];
+            fwq_st_pair(dst + 2 * tid, val, q.base + 4ULL * (unsigned long long)it);
+        }
+    };
+    deliver_record(0);
+    unsigned long long ts[10];
+#define FWQ_STAMP(i) do { if (q.dbg && tid == 0 && (cta < 2 || q.dbg == 3) && it == 5) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[i])); } while (0)
+    for (int it = 0; it < q.k_count; ++it) {
+        const int par = it & 1;
+        const unsigned long long tokD = q.base + 4ULL * it, tokB = tokD + 2;
+        FWQ_STAMP(0);
+        // ---- CTA 0 gathers the records (one private line per CTA) and merges them; the merged record goes out in
+        //      FWQ_REPL replicas so that no line is polled by more than a handful of CTAs
+        const unsigned long long tokA = tokD + 1;
+        auto read_record = [&](const double* src, unsigned long long token, int sleep_ns, FwCand& o) {
+            double f8[8];
+            unsigned done = 0;
+            unsigned long long t0 = 0;
+            unsigned spin = 0;
+            while (done != 0xffu) {                      // eight loads in flight; a word counts once it carries the token
+                unsigned long long v[8], tk[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (!(done & (1u << e)))
+                        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v[e]), "=l"(tk[e]) : "l"(src + 2 * e) : "memory");
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (!(done & (1u << e)) && tk[e] == token) { f8[e] = __longlong_as_double((long long)v[e]); done |= 1u << e; }
+                if (done != 0xffu) {
+                    __nanosleep(sleep_ns);
+                    if ((++spin & 0x3ffu) == 0) {
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > 4000000000ULL) __trap();
+                    }
+                }
+            }
+            o.amax = f8[0]; o.imax = __double_as_longlong(f8[1]);
+            o.smin = f8[2]; o.imin = __double_as_longlong(f8[3]); o.xmin = f8[4];
+            o.fmask = __double_as_longlong(f8[5]); o.wmask = f8[6]; o.xmask = f8[7];
+        };
+        if (cta == 0) {
+            fw_cand_init(cd);
+            for (int b = tid; b < G; b += FWQ_THREADS) {
+                FwCand o;
+                read_record(q.recs + ((size_t)par * G + b) * FWQ_REC_DOUBLES, tokD, 40, o);
+                fw_cand_merge(cd, o);
+            }
+            fw_cand_block(cd, sh_c);                      // merged record in every lane of warp 0
+                    if (wid == 0 && lane == 0) sh_c[0] = cd;
+            __syncthreads();
+            if (tid < 8 * FWQ_REPL) {
+                const FwCand mc = sh_c[0];
+                const int e = tid & 7, rep = tid >> 3;
+                const double f8[8] = {mc.amax, __longlong_as_double(mc.imax), mc.smin, __longlong_as_double(mc.imin), mc.xmin,
+                                      __longlong_as_double(mc.fmask), mc.wmask, mc.xmask};
+                double val = f8[0];
+#pragma unroll
+                for (int k2 = 1; k2 < 8; ++k2) if (e == k2) val = f8[k2];
+                fwq_st_pair(q.bcast + ((size_t)par * FWQ_REPL + rep) * FWQ_REC_DOUBLES + 2 * e, val, tokA);
+            }
+        }
+        // ---- every CTA: the merged record (its replica), then the decision of iteration k (CTA 0 records it)
+        fw_cand_init(cd);
+        if (tid == 0) {
+            FwCand o;
+            read_record(q.bcast + ((size_t)par * FWQ_REPL + (cta % FWQ_REPL)) * FWQ_REC_DOUBLES, tokA, 100, o);
+            sh_c[1] = o;
+        }
+        __syncthreads();
+        cd = sh_c[1];
+        FWQ_STAMP(1);
+        if (tid == 0) {
+            FwDec d;
+            d.cs = d.den = d.tsign = 0.0; d.idx = 0; d.go = 0;
+            fwq_decide(p, cd, q.k_start + it, sh_logdet[0], sh_logdet[1], cta == 0, d);
+            sh_dec = d;
+        }
+        __syncthreads();
+        if (!sh_dec.go) return;                          // the optimality test fired at this iteration: uniform
+        const double cs = sh_dec.cs, den = sh_dec.den, tsign = sh_dec.tsign;
+        const int64_t idx = sh_dec.idx;
+        for (int r = tid; r < m; r += FWQ_THREADS) vs[r] = __ldg(p.V + (int64_t)r * p.ldv + idx);      // the chosen column
+        __syncthreads();
+        FWQ_STAMP(2);
+        // ---- u_r = Hinv[r,:] v for the own rows (warp per row, as fw_hv_kernel), delivered to every CTA's view
+        for (int i = wid; i < nown; i += FWQ_THREADS / 32) {
+            const int r = cta + i * G;
+            const double* hr = p.Hinv + (size_t)r * m;
+            double sacc = 0.0;
+            for (int c = lane; c < m; c += 32) sacc += __ldcg(hr + c) * vs[c];
+            sacc = warp_sum(sacc);
+            if (lane == 0) fwq_st_pair(q.ux + ((size_t)par * m + r) * 2, sacc, tokB);
+        }
+        FWQ_STAMP(3);
+        for (int r = tid; r < m; r += FWQ_THREADS) us[r] = fwq_wait_pair(q.ux + ((size_t)par * m + r) * 2, tokB);
+        __syncthreads();
+        FWQ_STAMP(4);
+        // ---- Hinv <- (Hinv - cs u u^T)/den on the own rows      D_opt_alg.py:79 / :166 / :175
+        for (int e0 = tid; e0 < nown * m; e0 += FWQ_THREADS * 4) {
+            double hv[4];
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+                const int e = e0 + u4 * FWQ_THREADS;
+                if (e < nown * m) { const int i = e / m, c = e - i * m; hv[u4] = __ldcg(p.Hinv + (size_t)(cta + i * G) * m + c); }
+            }
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+                const int e = e0 + u4 * FWQ_THREADS;
+                if (e < nown * m) {
+                    const int i = e / m, c = e - i * m, r = cta + i * G;
+                    const double o = us[r] * us[c];
+                    p.Hinv[(size_t)r * m + c] = (hv[u4] - cs * o) / den;
+                }
+            }
+        }
+        // ---- the pass over the own columns: two teams of 256 threads take alternate 128-column sub-blocks
+        FWQ_STAMP(5);
+        fw_cand_init(cd);
+        const int nsub = (ncol + FWP_COLS - 1) / FWP_COLS;
+        const int nsub2 = (nsub + 1) / 2 * 2;             // both teams run the same number of rounds
+        for (int sb = team; sb < nsub2; sb += 2) {
+            const int jrel = sb * FWP_COLS + ct * 2;
+            const int64_t j = c0 + jrel;
+            const bool owns = (sb < nsub) && (jrel < ncol);
+            double s0 = 0.0, s1 = 0.0;
+            if (owns) {
+                const bool two = (j + 1 < p.n) && (jrel + 1 < ncol);
+                const double* vcr = vc + (size_t)rg * q.rc4 * q.per + jrel;
+                for (int rr = 0; rr < rcn; ++rr) {
+                    const double2 a = *reinterpret_cast<const double2*>(vcr + (size_t)rr * q.per);
+                    const double uq = us[r0 + rr];
+                    s0 += uq * a.x;
+                    s1 += uq * a.y;
+                }
+                const double* col = p.V + j;
+                int r = r0 + rcn;
+                if (two) {
+                    fwq_stream(col, p.ldv, us, r, r1, s0, s1);
+                } else {
+                    for (; r < r1; ++r) s0 += us[r] * __ldcs(col + (int64_t)r * p.ldv);
+                }
+            }
+            double* pt = part + (size_t)team * 4 * FWP_COLS;
+            pt[rg * FWP_COLS + 2 * ct] = s0;
+            pt[rg * FWP_COLS + 2 * ct + 1] = s1;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(FWQ_TEAM) : "memory");
+            if (rg == 0 && owns) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (j + e < p.n && jrel + e < ncol) {
+                        const double pj = ((pt[2 * ct + e] + pt[FWP_COLS + 2 * ct + e]) + pt[2 * FWP_COLS + 2 * ct + e]) +
+                                          pt[3 * FWP_COLS + 2 * ct + e];
+                        const double wn = (p.w[j + e] - cs * (pj * pj)) / den;
+                        double xn = p.x[j + e] * den;
+                        if (j + e == idx) xn = xn + tsign;
+                        p.w[j + e] = wn;
+                        p.x[j + e] = xn;
+                        fw_cand_add(cd, wn, xn, j + e, thr);
+                    }
+                }
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(FWQ_TEAM) : "memory");
+        }
+        __syncthreads();
+        FWQ_STAMP(6);
+        deliver_record(it + 1);
+        FWQ_STAMP(7);
+        if (q.dbg == 3 && tid == 0 && it == 5 && q.dbg_buf) {
+            for (int i = 0; i < 8; ++i) q.dbg_buf[cta * 8 + i] = ts[i];
+        }
+        if (q.dbg == 1 && tid == 0 && cta < 2 && it == 5)
+            printf("fw persistent cta %d: records %llu ns, decide + column %llu, u rows %llu, u gather %llu, Hinv rows %llu, pass %llu, record %llu | iteration %llu ns\n",
+                   cta, ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], ts[6] - ts[5], ts[7] - ts[6], ts[7] - ts[0]);
+    }
 }
 
 // Hinv = Linv^T Linv  (setup only; Linv lower triangular, zero padded, leading dimension mp)
@@ -521,7 +934,8 @@ size_t accbpg_fw_workspace_bytes(int m, int64_t n_local) {
     // dopt workspace (gram / factor / Linv / gradient partials) + v and u vectors
     size_t base = accbpg_dopt_workspace_bytes(m, n_local);
     const size_t nparts = (size_t)((n_local + 127) / 128) + 4096;        // selection candidates, one per selecting CTA
-    return base + 2 * (((size_t)m + 31) / 32 * 32 * 8) + nparts * 64 + 256;
+    // + the exchange tables of the persistent loop: u parts (2 x m pairs), u (2 x m), records (2 x 256 CTAs x 128 B), tokens
+    return base + 2 * (((size_t)m + 31) / 32 * 32 * 8) + nparts * 64 + 256 + (size_t)6 * m * 8 + 2 * 256 * 128 + 2 * 16 * 128 + 512;
 }
 
 // D_opt_alg.py:39-45 / :123-129:  M = V diag(x0) V^T, Hinv = M^{-1}, w_j = v_j^T Hinv v_j, log det M
@@ -555,6 +969,7 @@ struct FwLaunch {
     int sel_grid, hv_grid, nblk, r1_ctas;
     size_t pass_smem;
     bool pass_vec;
+    double* persist_mem;       // exchange tables of the persistent loop (inside the workspace)
 };
 
 static int fw_prepare(Ctx* c, const double* V, int m, int64_t n, int64_t ldv, int away, double eps, void* ws, double* Hinv,
@@ -565,7 +980,16 @@ static int fw_prepare(Ctx* c, const double* V, int m, int64_t n, int64_t ldv, in
     double* v = (double*)((char*)ws + base);
     double* u = v + ((size_t)m + 31) / 32 * 32;
     FwCand* parts = (FwCand*)(u + ((size_t)m + 31) / 32 * 32);
-    // block width: the smallest number of whole waves of (3 CTAs per SM) that covers n with <= 128 columns per CTA
+    {
+        const size_t nparts = (size_t)((n + 127) / 128) + 4096;
+        uintptr_t a = reinterpret_cast<uintptr_t>(parts + nparts);
+        L->persist_mem = reinterpret_cast<double*>((a + 127) / 128 * 128);
+    }
+    // block width: the smallest number of whole waves of (3 CTAs per SM) that covers n with <= 128 columns per CTA.
+    // (Measured at 500 x 50000, round 2: sizing the waves by the kernel's real occupancy - 2 CTAs per SM at 110 registers, or
+    // 3 with __launch_bounds__(256, 3) - gives 18.3 k / 18.6 k iterations per second against 19.2 k with this rule: the
+    // iteration is bound by its serial chain - decision, column gather, u = Hinv v, tail - not by wave quantisation.)
+    L->r1_ctas = c->sm_count / 4 < 1 ? 1 : c->sm_count / 4;
     int64_t per_wave = (int64_t)c->sm_count * 3;
     int64_t waves = (n + per_wave * FWP_COLS - 1) / (per_wave * FWP_COLS);
     int64_t width = (n + waves * per_wave - 1) / (waves * per_wave);
@@ -578,7 +1002,6 @@ static int fw_prepare(Ctx* c, const double* V, int m, int64_t n, int64_t ldv, in
     L->p.width = (int)width;
     L->sel_grid = grid_for(c, n, FW_THREADS, 4, 2);
     L->hv_grid = (m + 7) / 8;
-    L->r1_ctas = c->sm_count / 4 < 1 ? 1 : c->sm_count / 4;
     L->pass_smem = (size_t)m * sizeof(double);
     if (L->pass_smem > 160 * 1024) return arg_err("fw: m too large for the shared-memory copy of u");
     L->pass_vec = ((reinterpret_cast<uintptr_t>(V) & 15u) == 0) && (ldv % 2 == 0);
@@ -676,6 +1099,70 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
         if (rc) return rc;
         fw_zero_lo_kernel<<<1, 1, 0, s>>>(ctrl);
         ACCBPG_LAUNCHED("fw_zero_lo_kernel");
+    }
+    // ---- one persistent launch for the whole batch: OPT-IN (ACCBPG_FW_PERSIST=1).  Results are bit-identical to the launch
+    //      chain below (tests/test_gpu_fw.py passes either way), but at 500 x 50000 it reaches 11-14 k iterations per second
+    //      against 19.2 k: its exchanges (records -> merge -> replicas, u all-gather) cost 13 us per iteration and a
+    //      statically partitioned CTA streams its strip of V at 3.0-4.9 TB/s only (tried and dropped)
+    {
+        static int persist = -1;
+        if (persist < 0) { const char* e = getenv("ACCBPG_FW_PERSIST"); persist = (e && e[0] == '1') ? 1 : 0; }
+        const int G = c->sm_count < 256 ? c->sm_count : 256;
+        int64_t per = (n + G - 1) / G;
+        per = (per + 1) / 2 * 2;
+        const int mpad = (m + 1) / 2 * 2;
+        const size_t fixed = ((size_t)2 * mpad + 2 * 4 * FWP_COLS) * sizeof(double);
+        const size_t budget = 200 * 1024;
+        if (persist && L.pass_vec && !l2.on && m <= 4096 && per >= 2 && per < (1 << 28) && fixed + 1024 < budget) {
+            const int rows_per = (m + 3) / 4;
+            int64_t rc4 = (int64_t)((budget - fixed) / ((size_t)32 * per));
+            if (rc4 > rows_per) rc4 = rows_per;
+            if (rc4 < 0) rc4 = 0;
+            const size_t smem = fixed + (size_t)4 * rc4 * per * sizeof(double);
+            static bool attr_done[kMaxDevices] = {};
+            if (c->device >= 0 && c->device < kMaxDevices && !attr_done[c->device]) {
+                ACCBPG_CUDA(cudaFuncSetAttribute(fw_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+                attr_done[c->device] = true;
+            }
+            FwPersist q;
+            q.ux = L.persist_mem;
+            q.recs = q.ux + (size_t)4 * m;
+            q.recs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(q.recs) + 127) / 128 * 128);
+            q.bcast = q.recs + (size_t)2 * 256 * FWQ_REC_DOUBLES;
+            q.tok = nullptr;
+            static unsigned long long calls = 0;
+            q.base = (++calls) << 24;
+            q.G = G; q.k_start = k_start; q.k_count = k_count; q.per = (int)per; q.rc4 = (int)rc4;
+            static int fdbg = -1;
+            if (fdbg < 0) { const char* e = getenv("ACCBPG_FW_DBG"); fdbg = e ? atoi(e) : 0; }
+            q.dbg = fdbg;
+            q.dbg_buf = nullptr;
+            static unsigned long long* dbg_dev = nullptr;
+            if (fdbg == 3) {
+                if (!dbg_dev) { cudaMalloc(&dbg_dev, 256 * 8 * 8); }
+                cudaMemsetAsync(dbg_dev, 0, 256 * 8 * 8, s);
+                q.dbg_buf = dbg_dev;
+            }
+            p.k = k_start; p.decide = 1; p.reverse = 0;
+            ProfScope ps(P_FW_BATCH, s);
+            fw_persistent_kernel<<<G, FWQ_THREADS, smem, s>>>(p, q);
+            ACCBPG_LAUNCHED("fw_persistent_kernel");
+            if (fdbg == 3 && k_count > 6) {              // timing experiment only: per-CTA stamps of batch iteration 5
+                static unsigned long long h[256 * 8];
+                cudaStreamSynchronize(s);
+                cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+                unsigned long long t0 = ~0ULL;
+                for (int b = 0; b < G; ++b) if (h[b * 8] && h[b * 8] < t0) t0 = h[b * 8];
+                const char* nm[8] = {"loop top", "records gathered", "decided + column", "u rows sent", "u gathered", "Hinv rows done",
+                                     "pass done", "record posted"};
+                for (int i = 0; i < 8; ++i) {
+                    unsigned long long lo = ~0ULL, hi = 0; int amax = 0;
+                    for (int b = 0; b < G; ++b) { unsigned long long v = h[b * 8 + i] - t0; if (v < lo) lo = v; if (v > hi) { hi = v; amax = b; } }
+                    fprintf(stderr, "[fw dbg] %-18s min %7llu ns  max %7llu ns (cta %d)\n", nm[i], lo, hi, amax);
+                }
+            }
+            return ACCBPG_OK;
+        }
     }
     // the first decision of the batch
     p.k = k_start; p.decide = 1; p.reverse = 0;

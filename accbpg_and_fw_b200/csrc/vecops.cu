@@ -548,10 +548,10 @@ __device__ __forceinline__ void gather_slots(const double* slots, int count, uns
 // One exchange round; (a, b) are this thread's partial sums (IS_MIN: a is a partial minimum, b unused).  Two levels, so
 // that no cache line is polled by more than one block except the single result word:
 //   every block delivers its partials to its rank's leader (block 0), which adds them in block order;
-//   the leaders deliver the rank's sums to every rank's leader (NVLink) and add them in rank order;
-//   the leader publishes the total in one word that the other blocks of its rank wait for.
+//   the leader delivers the rank's sums into every rank's table (NVLink when column-sharded);
+//   every block waits for the `world` rank sums in its own rank's table and adds them in rank order.
 // Every store carries its value and the round's token in one 16-byte word: no fences.  Table of a rank (kBurgSlot doubles
-// per slot):  A [2][kBurgMaxG] block partials, then B [2][kMaxPeerRanks] rank sums, then C [2] totals.
+// per slot):  A [2][kBurgMaxG] block partials, then B [2][kMaxPeerRanks] rank sums.
 constexpr int kBurgOffB = 2 * kBurgMaxG;
 constexpr int kBurgOffC = kBurgOffB + 2 * kMaxPeerRanks;
 constexpr int kBurgTableSlots = kBurgOffC + 2;
@@ -584,25 +584,27 @@ __device__ __forceinline__ void burgx_round(const BurgX& X, int round, double a,
             st_pair(dst + 2, bb, token);
         }
         double ta, tb;
-        if (blockIdx.x == 0) {
+        if (blockIdx.x == 0) {                         // the leader adds its rank's block partials and tells every rank
             gather_slots<IS_MIN>(tab + (size_t)par * kBurgMaxG * kBurgSlot, G, token, false, ta, tb);
-            if (X.world > 1) {
-                if (lane < X.world) {
-                    double* dst = X.tab[lane] + ((size_t)kBurgOffB + par * kMaxPeerRanks + X.rank) * kBurgSlot;
-                    st_pair(dst, ta, token);
-                    st_pair(dst + 2, tb, token);
-                }
-                gather_slots<IS_MIN>(tab + ((size_t)kBurgOffB + par * kMaxPeerRanks) * kBurgSlot, X.world, token, true, ta, tb);
-            }
-            if (lane == 0) {
-                double* dst = tab + ((size_t)kBurgOffC + par) * kBurgSlot;
+            if (lane < X.world) {
+                double* dst = X.tab[lane] + ((size_t)kBurgOffB + par * kMaxPeerRanks + X.rank) * kBurgSlot;
                 st_pair(dst, ta, token);
                 st_pair(dst + 2, tb, token);
             }
-        } else {
-            const double* src = tab + ((size_t)kBurgOffC + par) * kBurgSlot;
-            ta = 0.0; tb = 0.0;
-            if (lane == 0) { ta = wait_pair(src, token, false); tb = wait_pair(src + 2, token, false); }
+        }
+        // every block (the leader included) waits for the `world` rank sums in its own table and adds them in rank order
+        double va = 0.0, vb = 0.0;
+        if (lane < X.world) {
+            const double* src = tab + ((size_t)kBurgOffB + par * kMaxPeerRanks + lane) * kBurgSlot;
+            va = wait_pair(src, token, sys);
+            vb = wait_pair(src + 2, token, sys);
+        }
+        ta = IS_MIN ? kInf : 0.0;
+        tb = 0.0;
+        for (int r = 0; r < X.world; ++r) {
+            const double ar = __shfl_sync(0xffffffffu, va, r), br = __shfl_sync(0xffffffffu, vb, r);
+            if (IS_MIN) ta = fmin(ta, ar);
+            else { ta += ar; tb += br; }
         }
         double* o = sh + flip * 64;                    // the other buffer: nobody reads it before the barrier below
         if (lane == 0) { o[0] = ta; o[1] = tb; }

@@ -464,9 +464,21 @@ def extra_c2(B):
         out["fw_away_it_per_s"] = (len(Ta) - 1) / (Ta[-1] - Ta[0])
     lib.accbpg_prof_enable(1)
     B.prof_read()
-    acc.D_opt_FW_away(f._Hd, x0, 1e-12, 300, verbose=False)
+    res300 = acc.D_opt_FW_away(f._Hd, x0, 1e-12, 300, verbose=False)
     kfw = B.prof_read()
     lib.accbpg_prof_enable(0)
+    pb = kfw.get("fw_persistent_kernel(batch)")
+    if pb:
+        # one persistent launch per batch of 64 iterations: the per-iteration time includes the decision, u = Hinv v,
+        # the rank-one update and the three exchanges next to the pass over V
+        ms_it = pb["ms_total"] / max(len(res300[1]), 1)
+        gbs = 8.0 * m * n / (ms_it * 1e-3) / 1e9
+        out["fw_pass_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": B.hbm, "unit": "GB/s", "frac": gbs / B.hbm,
+                                   "ms_avg": ms_it, "bytes_per_launch": 8 * m * n, "peak_source": B.hbm_source,
+                                   "kernel": "fw_persistent_kernel (whole iterations, one launch per batch of 64; algorithmic "
+                                             "bytes 8mn per iteration, part of V stays in shared memory)",
+                                   "launches": pb["launches"], "iterations": len(res300[1])}
+        out["fw_iteration_ms_avg"] = ms_it
     p = kfw.get("fw_pass_kernel")
     if p:
         gbs = 8.0 * m * n / (p["ms_avg"] * 1e-3) / 1e9
