@@ -9,7 +9,7 @@ include/accbpg_b200.h (libaccbpg_b200.so).  Importing this package fails if that
 not been built; there is no CPU fallback.
 """
 from . import _native                                         # noqa: F401  (raises if the library is missing)
-from .objectives import RSmoothFunction, DOptimalObj, PoissonRegression, KLdivRegression
+from .objectives import RSmoothFunction, DOptimalObj, SparseDOptimalObj, PoissonRegression, KLdivRegression
 from .bregman import (LegendreFunction, BurgEntropy, BurgEntropyL1, BurgEntropyL2, BurgEntropySimplex,
                       ShannonEntropy, ShannonEntropyL1, ShannonEntropySimplex, SquaredL2Norm)
 from .lmo import (lmo_simplex, lmo_matrix_simplex, lmo_l2_ball, lmo_l2_ball_positive_orthant, lmo_linf_ball,
@@ -19,12 +19,12 @@ from .drivers_fw import (FW_alg_div_step, FW_alg_descent_step, FW_alg_L0_L1_shor
                          FW_l0l1_log_and_linear_step, FW_l0l1_log_only)
 from .dopt_fw import D_opt_FW, D_opt_FW_away
 from .problems import (D_opt_libsvm, D_opt_design, D_opt_KYinit, Poisson_regrL1, Poisson_regrL2, KL_nonneg_regr,
-                       load_libsvm_dense)
+                       load_libsvm_dense, load_libsvm_sparse)
 from .dist import ColumnShard
 from .runtime import Runtime
 
 __all__ = [
-    "RSmoothFunction", "DOptimalObj", "PoissonRegression", "KLdivRegression",
+    "RSmoothFunction", "DOptimalObj", "SparseDOptimalObj", "PoissonRegression", "KLdivRegression",
     "LegendreFunction", "BurgEntropy", "BurgEntropyL1", "BurgEntropyL2", "BurgEntropySimplex",
     "ShannonEntropy", "ShannonEntropyL1", "ShannonEntropySimplex", "SquaredL2Norm",
     "lmo_simplex", "lmo_matrix_simplex", "lmo_l2_ball", "lmo_l2_ball_positive_orthant", "lmo_linf_ball",
@@ -33,5 +33,5 @@ __all__ = [
     "FW_alg_div_step", "FW_alg_descent_step", "FW_alg_L0_L1_shortest_step", "FW_l0l1_log_and_linear_step",
     "FW_l0l1_log_only", "D_opt_FW", "D_opt_FW_away",
     "D_opt_libsvm", "D_opt_design", "D_opt_KYinit", "Poisson_regrL1", "Poisson_regrL2", "KL_nonneg_regr",
-    "load_libsvm_dense", "ColumnShard", "Runtime",
+    "load_libsvm_dense", "load_libsvm_sparse", "ColumnShard", "Runtime",
 ]

@@ -25,6 +25,7 @@ SOURCES = {
     "fw.cu": ["-fmad=false"],
     "dopt.cu": [],
     "chol.cu": [],
+    "sparse.cu": [],
     "prof.cu": [],
 }
 

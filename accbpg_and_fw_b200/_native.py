@@ -25,6 +25,8 @@ _CTYPES = {
     "int*": ctypes.POINTER(ctypes.c_int),
     "int64_t": ctypes.c_int64,
     "int64_t*": ctypes.POINTER(ctypes.c_int64),
+    "const int64_t*": ctypes.c_void_p,    # device address
+    "const int*": ctypes.c_void_p,        # device address
     "uint64_t": ctypes.c_uint64,
     "size_t": ctypes.c_size_t,
     "double": ctypes.c_double,

@@ -571,6 +571,11 @@ __device__ __forceinline__ void burgx_round(const BurgX& X, int round, double a,
         if (lane == 0) { s[wid] = a; s[32 + wid] = b; }
     }
     __syncthreads();
+    if (G == 1 && X.world == 1) {                      // one block holds the whole vector (n <= 4096): no exchange at all
+        if (IS_MIN) { ra = warp_min((lane < nw) ? s[lane] : kInf); rb = 0.0; }
+        else { ra = warp_sum((lane < nw) ? s[lane] : 0.0); rb = warp_sum((lane < nw) ? s[32 + lane] : 0.0); }
+        return;                                        // (the buffers alternate, so the next round needs no second barrier)
+    }
     if (wid == 0) {
         double ba, bb = 0.0;
         if (IS_MIN) ba = warp_min((lane < nw) ? s[lane] : kInf);
@@ -1087,6 +1092,7 @@ static int burgx_launch(Ctx* c, cudaStream_t s, int64_t n, int64_t width, const 
     if (cap > kBurgMaxG) cap = kBurgMaxG;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
+    if (width <= 8 * kBurgThreads && X.world == 1) grid = 1;      // small vectors: one block, no exchange (shared memory only)
     const int64_t per = (width + (int64_t)grid * kBurgThreads - 1) / ((int64_t)grid * kBurgThreads);
     ProfScope ps(P_BURG_SIMPLEX, s);
     if (per <= 1) burg_simplex_x_kernel<1><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X);

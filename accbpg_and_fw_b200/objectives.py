@@ -165,6 +165,86 @@ class DOptimalObj(RSmoothFunction):
             nat.check(lib.accbpg_dopt_grad(rt.ctx, rt.stream, H.data_ptr(), self.m, self.n_local, H.stride(0), ws, gp))
 
 
+class SparseDOptimalObj(RSmoothFunction):
+    """f(x) = -log det(H diag(x) H^T) with H (m x n) SPARSE, held in compressed-column form on the device: column j of
+    H is the j-th sample of a LIBSVM file (accbpg/applications.py:17-33 densifies the same data with .toarray('C');
+    accbpg/functions.py:43-59 is the oracle).  The Gram matrix and the gradient read only the stored entries
+    (accbpg_dopt_sparse_gram / accbpg_dopt_sparse_grad); the m x m factorisation is the dense chain.  m <= 128, one GPU.
+
+    indptr / indices / values: the CSC arrays of H (= the CSR arrays of the samples-by-features matrix X), or pass a
+    scipy.sparse matrix H as the first argument.  `f.H` is the scipy CSC matrix (host); `f.toarray()` the dense H."""
+
+    _lin_capable = True
+
+    def __init__(self, indptr, indices=None, values=None, m=None, device=None):
+        self.rt = Runtime.get(device)
+        self.shard = None
+        if indices is None:                                   # a scipy.sparse matrix
+            Hs = indptr.tocsc()
+            Hs.sort_indices()
+            indptr, indices, values, m = Hs.indptr, Hs.indices, Hs.data, Hs.shape[0]
+        self._indptr_h = np.ascontiguousarray(indptr, dtype=np.int64)
+        self._indices_h = np.ascontiguousarray(indices, dtype=np.int32)
+        self._values_h = np.ascontiguousarray(values, dtype=np.float64)
+        self.m = int(m)
+        self.n = self.n_local = int(self._indptr_h.size - 1)
+        assert self.m < self.n, "DOptimalObj: need m < n"
+        assert self.m <= 128, "SparseDOptimalObj: m <= 128 (use DOptimalObj on the dense matrix beyond)"
+        assert self._indices_h.size == self._values_h.size == int(self._indptr_h[-1])
+        dev = self.rt.device
+        self._colptr = torch.from_numpy(self._indptr_h).to(dev)
+        self._rowidx = torch.from_numpy(self._indices_h).to(dev)
+        self._vals = torch.from_numpy(self._values_h).to(dev)
+        with self.rt.on_device():
+            self._ws = self.rt.workspace(("dopt_sparse", self.m, id(self)), lib.accbpg_dopt_sparse_workspace_bytes(self.m))
+        self._M = torch.empty(self.m, self.m, dtype=torch.float64, device=dev)
+
+    @property
+    def H(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self._values_h, self._indices_h, self._indptr_h), shape=(self.m, self.n))
+
+    def toarray(self):
+        return np.ascontiguousarray(self.H.toarray())
+
+    def _gram(self, xd, M):
+        rt = self.rt
+        nat.check(lib.accbpg_dopt_sparse_gram(rt.ctx, rt.stream, self._colptr.data_ptr(), self._rowidx.data_ptr(),
+                                              self._vals.data_ptr(), self.m, self.n, xd.data_ptr(), self._ws.data_ptr(),
+                                              M.data_ptr()))
+
+    def _factor_grad(self, M, flag, slot, g):
+        rt = self.rt
+        nat.check(lib.accbpg_dopt_factor(rt.ctx, rt.stream, self.m, M.data_ptr(), None, int(flag >= 1),
+                                         self._ws.data_ptr(), rt.slot(slot)))
+        if flag >= 1:
+            nat.check(lib.accbpg_dopt_sparse_grad(rt.ctx, rt.stream, self._colptr.data_ptr(), self._rowidx.data_ptr(),
+                                                  self._vals.data_ptr(), self.m, self.n, self._ws.data_ptr(),
+                                                  g.data_ptr()))
+
+    def _enqueue(self, xd, flag, slot, g):
+        self._gram(xd, self._M)
+        self._factor_grad(self._M, flag, slot, g)
+
+    # ---- linear image M(x) (config.linear_images), as DOptimalObj
+    def _img_compute(self, xd):
+        M = torch.empty(self.m, self.m, dtype=torch.float64, device=self.rt.device)
+        self._gram(xd, M)
+        return M
+
+    def _img_axpby(self, a, Ia, b, Ib):
+        rt = self.rt
+        out = torch.empty_like(Ia)
+        nat.check(lib.accbpg_vec_axpby(rt.ctx, rt.stream, Ia.numel(), float(a), Ia.data_ptr(), float(b),
+                                       Ib.data_ptr(), out.data_ptr()))
+        return out
+
+    def _enqueue_img_pair(self, Ix, slot_x, Iy, flag_y, slot_y, g):
+        if Ix is not None:
+            self._factor_grad(Ix, 0, slot_x, None)
+        self._factor_grad(Iy, flag_y, slot_y, g)
+
+
 class _LinearInverse(RSmoothFunction):
     """Shared body of PoissonRegression / KLdivRegression: Ax, value + residual, A^T r."""
     _kind = None

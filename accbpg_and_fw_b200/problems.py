@@ -9,15 +9,14 @@ import os
 
 import numpy as np
 
-from .objectives import DOptimalObj, PoissonRegression, KLdivRegression
+from .objectives import SparseDOptimalObj, DOptimalObj, PoissonRegression, KLdivRegression
 from .bregman import BurgEntropySimplex, BurgEntropyL1, BurgEntropyL2, ShannonEntropyL1
 
 
-def load_libsvm_dense(filename, zero_based="auto"):
-    """Parse a LIBSVM / svmlight text file into a dense (n_samples, n_features) float64 array and labels.
-
-    Same conventions as accbpg/utils.py:22-95 ('#' comments, sorted unique 1-based indices by
-    default, feature count from the largest index)."""
+def _parse_libsvm(filename, zero_based="auto"):
+    """Rows of a LIBSVM / svmlight text file as lists of (feature index, value), the labels, the index shift and the
+    feature count.  Same conventions as accbpg/utils.py:22-95 ('#' comments, sorted unique 1-based indices by default,
+    feature count from the largest index)."""
     rows, labels = [], []
     opener = open
     if filename.endswith(".gz"):
@@ -48,15 +47,49 @@ def load_libsvm_dense(filename, zero_based="auto"):
                 max_idx = max(max_idx, k)
             rows.append(feats)
     shift = 1 if (zero_based is False or (zero_based == "auto" and min_idx is not None and min_idx > 0)) else 0
-    X = np.zeros((len(rows), max_idx + 1 - shift))
+    return rows, np.array(labels), shift, max_idx + 1 - shift
+
+
+def load_libsvm_dense(filename, zero_based="auto"):
+    """Parse a LIBSVM / svmlight text file into a dense (n_samples, n_features) float64 array and labels
+    (accbpg/utils.py:22-95 followed by .toarray, as accbpg/applications.py:21-25 does)."""
+    rows, labels, shift, nfeat = _parse_libsvm(filename, zero_based)
+    X = np.zeros((len(rows), nfeat))
     for i, feats in enumerate(rows):
         for k, v in feats:
             X[i, k - shift] = v
-    return X, np.array(labels)
+    return X, labels
 
 
-def D_opt_libsvm(filename, device=None):
-    """D-optimal design instance from a LIBSVM regression data set.   applications.py:17-33."""
+def load_libsvm_sparse(filename, zero_based="auto"):
+    """The same file as compressed sparse ROWS of X (= compressed columns of H = X^T, one column per sample, in file
+    order): (indptr int64 [n_samples + 1], indices int32 [nnz], values float64 [nnz], n_features, labels).  Explicit
+    zeros of the file are kept as stored entries, as scipy's csr_matrix keeps them."""
+    rows, labels, shift, nfeat = _parse_libsvm(filename, zero_based)
+    indptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    for i, feats in enumerate(rows):
+        indptr[i + 1] = indptr[i] + len(feats)
+    indices = np.empty(int(indptr[-1]), dtype=np.int32)
+    values = np.empty(int(indptr[-1]), dtype=np.float64)
+    q = 0
+    for feats in rows:
+        for k, v in feats:
+            indices[q] = k - shift
+            values[q] = v
+            q += 1
+    return indptr, indices, values, nfeat, labels
+
+
+def D_opt_libsvm(filename, device=None, sparse=False):
+    """D-optimal design instance from a LIBSVM regression data set.   applications.py:17-33.
+    sparse=True keeps H = X^T in compressed-column form on the device (SparseDOptimalObj) instead of densifying it as the
+    reference does with .toarray('C'); it needs more samples than features (otherwise the dense path is taken)."""
+    if sparse:
+        indptr, indices, values, nfeat, _ = load_libsvm_sparse(filename)
+        n = indptr.size - 1
+        if n > nfeat:
+            f = SparseDOptimalObj(indptr, indices, values, nfeat, device=device)
+            return f, BurgEntropySimplex(device=device), 1.0, (1.0 / n) * np.ones(n)
     X, _ = load_libsvm_dense(filename)
     H = np.ascontiguousarray(X.T) if X.shape[0] > X.shape[1] else np.ascontiguousarray(X)
     n = H.shape[1]

@@ -279,6 +279,19 @@ int accbpg_dopt_pair_from_gram(void* ctx, void* stream, const double* d_H, int m
                                const double* d_Mx, const double* d_My, int flag_y, void* d_ws, double* d_fx_out,
                                double* d_fy_out, double* d_g);
 
+/* ---- the same objective on a SPARSE design matrix (D_opt_libsvm, accbpg/applications.py:17-33, which densifies the
+ *      LIBSVM data with .toarray('C'); parser accbpg/utils.py:22-95).  H (m x n, one column per sample) stays in
+ *      compressed-column form: d_colptr[n+1], d_rowidx[nnz] (feature index, 0-based), d_vals[nnz]; m <= 128.
+ *      K1 and K4 read the sparse columns; K2 / K3 are accbpg_dopt_factor on the dense m x m Gram matrix, with the
+ *      workspace of accbpg_dopt_sparse_workspace_bytes(m) (zero-filled once, like the dense one). */
+size_t accbpg_dopt_sparse_workspace_bytes(int m);
+int accbpg_dopt_sparse_gram(void* ctx, void* stream, const int64_t* d_colptr, const int* d_rowidx, const double* d_vals,
+                            int m, int64_t n, const double* d_x, void* d_ws, double* d_M);
+/* g_j = -|| L^{-1} h_j ||^2 over the nonzeros of column j, with the L^{-1} the last accbpg_dopt_factor(want_inverse = 1)
+ * left in d_ws */
+int accbpg_dopt_sparse_grad(void* ctx, void* stream, const int64_t* d_colptr, const int* d_rowidx, const double* d_vals,
+                            int m, int64_t n, void* d_ws, double* d_g);
+
 /* ---- Poisson / KL regression objectives (accbpg/functions.py:102-120, :140-158).  A is m x n_local. */
 #define ACCBPG_LINREG_POISSON 0   /* f = sum b log(b/Ax) + Ax - b ; r = 1 - b/Ax   */
 #define ACCBPG_LINREG_KL      1   /* f = sum Ax log(Ax/b) - Ax + b ; r = log(Ax/b) */

@@ -200,3 +200,18 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == ("reference" if ref_loader.locate() else "port")
     assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)      # set explicitly, whatever the launcher exported
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0
+
+
+@pytest.mark.parametrize("name", ["housing", "abalone", "bodyfat", "mpg"])
+def test_libsvm_sparse_loader_matches_dense(name):
+    """The compressed-column form of H = X^T (one column per sample, file order) densifies to exactly what the dense
+    loader builds (which the reference's own loader + .toarray('C') reproduces bit for bit, test_oracle_golden.py)."""
+    import scipy.sparse as sp
+    from accbpg_and_fw_b200.problems import load_libsvm_dense, load_libsvm_sparse
+    path = os.path.join(GOLDEN, name + "_libsvm.txt")
+    X, y = load_libsvm_dense(path)
+    indptr, indices, values, nfeat, y2 = load_libsvm_sparse(path)
+    assert indptr.dtype == np.int64 and indices.dtype == np.int32 and nfeat == X.shape[1] and np.array_equal(y, y2)
+    H = sp.csc_matrix((values, indices, indptr), shape=(nfeat, indptr.size - 1)).toarray()
+    assert np.array_equal(H, X.T)
+    assert np.all(np.diff(indptr) >= 0) and indptr[-1] == values.size

@@ -447,3 +447,39 @@ def test_host_results_are_fresh_arrays_and_can_be_passed_back(acc):
         a = f.gradient(x0)
         b = h.div_prox_map(x0, a, 0.9)
         assert np.array_equal(a, g2) and np.array_equal(b, z_copy)
+
+
+# ---- sparse design matrix (D_opt_libsvm without densifying): the four LIBSVM regression sets the reference ships ------
+_LIBSVM = {"housing": "-4.137e+01", "abalone": "3.978e+01", "bodyfat": "-3.475e+01", "mpg": "-3.416e+01"}     # F(x0), SURVEY 8c
+
+
+@pytest.mark.parametrize("name", sorted(_LIBSVM))
+def test_sparse_dopt_libsvm_matches_dense_and_oracle(acc, name):
+    """SparseDOptimalObj (compressed columns on the device, accbpg_dopt_sparse_gram / _grad) against the dense operator,
+    the NumPy oracle on the densified matrix (accbpg/applications.py:17-33, functions.py:43-59) and the reference's
+    4-digit F(x0); then 60 BPG iterations with line search: F to 1e-9, identical L_k."""
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, name + "_libsvm.txt")
+    fs, hs, Ls, x0 = acc.D_opt_libsvm(path, sparse=True)
+    fd, hd, Ld, x0d = acc.D_opt_libsvm(path)
+    assert type(fs).__name__ == "SparseDOptimalObj" and (fs.m, fs.n) == (fd.m, fd.n)
+    H = fd.H
+    assert np.array_equal(fs.toarray(), H)
+    fo = orc.make_dopt(H)
+    ho = orc.make_burg("simplex")
+    assert f"{fs(x0):.3e}" == _LIBSVM[name]
+    rng = np.random.RandomState(7)
+    for x in (x0, rng.rand(fs.n) / fs.n + 1e-4):
+        v, g = fs.func_grad(x)
+        vo, go = fo.func_grad(x)
+        vd, gd = fd.func_grad(x)
+        assert abs(v - vo) <= 1e-10 * abs(vo) and abs(v - vd) <= 1e-10 * abs(vd)
+        assert relerr(g, go) <= 1e-9 and relerr(g, gd) <= 1e-9
+        assert abs(fs(x) - vo) <= 1e-10 * abs(vo) and relerr(fs.gradient(x), go) <= 1e-9
+    xs, Fs, Lss, Ts = acc.BPG(fs, hs, 1.0, x0, maxitrs=60, linesearch=True, ls_ratio=1.2, verbose=False)
+    xo, Fo, Lso, To = orc.BPG(fo, ho, 1.0, x0, maxitrs=60, linesearch=True, ls_ratio=1.2)
+    assert np.array_equal(Lss, Lso)
+    assert float(np.max(np.abs(Fs - Fo) / np.abs(Fo))) <= 1e-9
+    with pytest.raises(AssertionError):
+        fs(-x0)
