@@ -196,11 +196,13 @@ class BurgEntropySimplex(BurgEntropy):
             nat.check(lib.accbpg_burg_simplex_prox(rt.ctx, rt.stream, n, yp, gd.data_ptr(), L, float(self.eps),
                                                    out.data_ptr(), info))
             return
-        # column-sharded.  Over NVLink peer memory: ONE kernel per rank keeps its slice of gg = (g [+ L/y]) / L in registers
-        # and exchanges the two partial sums of every bisection / Newton step with all ranks through a slot table
-        # (accbpg_burg_simplex_prox_peer): the multiplier c and the step counts are bit-identical on every rank, per-rank
-        # work is O(n / world), no host round trip.  Without peer memory: all-gather of gg (padding +inf), the recurrence
-        # replayed on the gathered vector by every rank, a finishing map per slice.
+        # column-sharded: every rank gathers all slices of gg = (g [+ L/y]) / L (padding +inf) - pushed straight into every
+        # rank's gathered vector over NVLink peer memory, else an NCCL all-gather - and replays the whole recurrence on
+        # the gathered vector, so there is ONE exchange per prox call, no host round trip, and the multiplier c is
+        # bit-identical on every rank (and independent of the sharding).  (config.burg_exchange switches to the fully
+        # distributed form, accbpg_burg_simplex_prox_peer: per-rank work O(n / world), but one NVLink exchange per Newton
+        # step - measured slower on 2 and 8 B200: 85 / 130 us against 74 / 94 us per prox at 50000 columns per GPU.)
+        from . import config
         sh = self.shard
         key = (n, sh.width, sh.world)
         if getattr(self, "_gg_key", None) != key:
@@ -208,16 +210,32 @@ class BurgEntropySimplex(BurgEntropy):
             self._gg_key = key
             self._gg_loc = torch.full((sh.width,), float("inf"), dtype=torch.float64, device=rt.device)
             self._gg_all = torch.empty(sh.width * sh.world, dtype=torch.float64, device=rt.device)
-            self._gg_peer = peer_buffers(sh, rt.device, [(lib.accbpg_burg_simplex_peer_doubles(sh.world), torch.float64)],
-                                         cache_key=("burg_slots", sh.world), reset=False)
+            # gathered vector in NVLink peer memory (double-buffered) + one flag word per rank; None -> NCCL all-gather
+            self._gg_peer = peer_buffers(sh, rt.device, [(2 * sh.world * sh.width, torch.float64),
+                                                         (sh.world, torch.int64)],
+                                         cache_key=("burg_gg", sh.width), reset=False)
+            self._slot_peer = None
+            if config.burg_exchange:
+                self._slot_peer = peer_buffers(sh, rt.device, [(lib.accbpg_burg_simplex_peer_doubles(sh.world), torch.float64)],
+                                               cache_key=("burg_slots", sh.world), reset=False)
         info = rt.slot(rt.S_AUX1)
-        if self._gg_peer is not None:
-            pb = self._gg_peer
+        if self._slot_peer is not None:
+            pb = self._slot_peer
             nat.check(lib.accbpg_burg_simplex_prox_peer(rt.ctx, rt.stream, n, sh.width, yp, gd.data_ptr(), L,
                                                         float(self.eps), sh.rank, sh.world, pb.tables[0], pb.next_epoch(),
                                                         out.data_ptr(), info))
             return
         gg = self._gg_loc
+        if self._gg_peer is not None:
+            pb = self._gg_peer
+            ep = pb.next_epoch()
+            nat.check(lib.accbpg_burg_simplex_push_peer(rt.ctx, rt.stream, n, sh.width, yp, gd.data_ptr(), L, sh.rank,
+                                                        sh.world, pb.tables[0], pb.tables[1], ep, gg.data_ptr()))
+            nat.check(lib.accbpg_burg_simplex_root_peer(rt.ctx, rt.stream, sh.width, float(self.eps), sh.rank, sh.world,
+                                                        pb.tables[0], pb.tables[1], ep, info))
+            nat.check(lib.accbpg_burg_simplex_finish_dev(rt.ctx, rt.stream, n, gg.data_ptr(), info + 16,
+                                                         out.data_ptr()))
+            return
         s0 = rt.S_TMP + 8
         nat.check(lib.accbpg_burg_simplex_prepare(rt.ctx, rt.stream, n, yp, gd.data_ptr(), L, gg.data_ptr(),
                                                   rt.slot(s0)))

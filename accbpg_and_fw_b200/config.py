@@ -21,8 +21,15 @@ peer_allreduce
     them (buffers from torch.distributed._symmetric_memory): the ranks' Gram matrices are summed behind the SYRK
     (accbpg_dopt_gram_allreduce), and D_opt_FW(_away) exchanges its selection records and the chosen column
     (accbpg_fw_run_peer).  Falls back to NCCL when symmetric memory cannot be set up.
+
+burg_exchange
+    Column-sharded Burg-simplex prox as ONE kernel per rank that exchanges the two partial sums of every bisection /
+    Newton step with all ranks (accbpg_burg_simplex_prox_peer) instead of gathering gg once and replaying the recurrence
+    on the gathered vector on every rank.  Off by default: an NVLink exchange per Newton step costs more than the
+    replicated arithmetic at the shapes measured (85 / 130 us against 74 / 94 us per prox on 2 / 8 B200).
 """
 linear_images = True
 reanchor_every = 64
 pipeline = True
 peer_allreduce = __import__('os').environ.get('ACCBPG_PEER_ALLREDUCE', '1') != '0'
+burg_exchange = __import__('os').environ.get('ACCBPG_BURG_EXCHANGE', '0') == '1'

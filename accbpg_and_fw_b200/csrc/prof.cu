@@ -12,7 +12,7 @@ static std::vector<EvPair> g_prof_pool;
 
 static const char* kProfNames[P_COUNT] = {
     "syrk_tma_kernel", "syrk_reduce_kernel", "chol_inv_step_kernel(all block columns)", "factor+gradient interval (chain with overlapped triangular GEMM)",
-    "trmm_persistent_kernel", "grad_finalize_kernel", "burg_simplex_kernel", "matvec_kernel", "rmatvec_kernel",
+    "trmm_persistent_kernel", "grad_finalize_kernel", "burg_simplex_x_kernel", "matvec_kernel", "rmatvec_kernel",
     "fw_pass_kernel", "fw_iteration", "syrk_reduce_push_kernel", "gram_sum_received_kernel(wait+sum)",
     "burg_prepare_push_kernel", "peer_wait_kernel(gg)", "peer_sum_scalars_kernel", "fw_persistent_kernel(batch)"};
 

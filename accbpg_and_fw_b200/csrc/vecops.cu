@@ -2,10 +2,7 @@
 // HBM-bound elementwise + reduction kernels; every reduction is a fixed tree (per-thread grid-stride
 // partial -> warp shuffle -> block -> ordered sum of block partials by the last block to finish).
 // Compiled with -fmad=false: expressions are rounded exactly as NumPy rounds them (no contraction).
-#include <cooperative_groups.h>
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace accbpg {
 thread_local char g_err[512] = "";
@@ -347,99 +344,7 @@ __global__ void __launch_bounds__(kThreads) argext_kernel(int64_t n, const doubl
     }
 }
 
-// ---------------------------------------------------------------- Burg-simplex persistent root-find
-// One cooperative kernel replays accbpg/functions.py:341-356 without leaving the device:
-//   gg = (g [- L*(-1/y)]) / L ; cmin = -min gg ; c = cmin+1 ; bisection while sum 1/(gg+c) - 1 < 0 ;
-//   Newton on fc = sum 1/(gg+c) - 1 with fpc = sum -1/(gg+c)^2 ; x = 1/(gg+c).
-// gg lives in the output buffer; each pass reads it back (L2 resident for n <= 10^6) and produces both
-// sums, so one grid-wide sync per pass.  Block partials are double buffered across passes.
 constexpr int kBurgThreads = 512;
-
-__device__ __forceinline__ void grid_sum2(cg::grid_group& grid, double a, double b, double* partials,
-                                          int parity, double* sh, double& ra, double& rb) {
-    a = block_sum(a, sh);
-    b = block_sum(b, sh);
-    double* pa = partials + (size_t)parity * kPartialStride;
-    double* pb = partials + (size_t)(2 + parity) * kPartialStride;
-    if (threadIdx.x == 0) { pa[blockIdx.x] = a; pb[blockIdx.x] = b; }
-    grid.sync();
-    double sa = 0.0, sb = 0.0;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) { sa += ld_cg(&pa[k]); sb += ld_cg(&pb[k]); }
-    ra = block_sum(sa, sh);
-    rb = block_sum(sb, sh);
-}
-
-// gg_in != NULL: root-find only, on a ready vector gg (the column-sharded path gathers every rank's slice; padding
-// entries are +inf and drop out of the minimum and of both sums); the kernel then writes nothing but `info`.
-__global__ void __launch_bounds__(kBurgThreads) burg_simplex_kernel(int64_t n, const double* y, const double* g,
-                                                                    double L, double eps, double* out,
-                                                                    double* info, double* partials,
-                                                                    uint32_t* status, const double* gg_in) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double sh[32];
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t st = 0;
-    double lo = kInf;
-    const double* ggp = gg_in ? gg_in : out;
-    if (gg_in) {
-        for (int64_t i = first; i < n; i += stride) lo = fmin(lo, gg_in[i]);
-    } else {
-        for (int64_t i = first; i < n; i += stride) {
-            double gg = burg_shift(y, g, L, i, st) / L;
-            out[i] = gg;
-            lo = fmin(lo, gg);
-        }
-    }
-    lo = block_min(lo, sh);
-    if (threadIdx.x == 0) partials[blockIdx.x] = lo;
-    grid.sync();
-    lo = kInf;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) lo = fmin(lo, ld_cg(&partials[k]));
-    lo = block_min(lo, sh);
-    const double cmin = -lo;
-    double c = cmin + 1.0;
-    int parity = 1, nbis = 0, nnewton = 0;
-    double s1, s2;
-    // bisection: halve toward cmin until sum 1/(gg+c) - 1 >= 0   (functions.py:344-346)
-    for (;;) {
-        double a = 0.0, b = 0.0;
-        for (int64_t i = first; i < n; i += stride) {
-            double t = ggp[i] + c;
-            a += 1.0 / t;
-            b += -1.0 / (t * t);
-        }
-        grid_sum2(grid, a, b, partials, parity, sh, s1, s2);
-        parity ^= 1;
-        if (s1 - 1.0 < 0.0 && nbis < 2000) { c = (cmin + c) / 2.0; ++nbis; }
-        else break;
-    }
-    double fc = s1 - 1.0;
-    // Newton  (functions.py:348-354); s2 already holds fpc at the current c
-    while (fabs(fc) > eps) {
-        double fpc = s2;
-        double cn = c - fc / fpc;
-        if (c - cn == 0.0) break;
-        c = cn;
-        double a = 0.0, b = 0.0;
-        for (int64_t i = first; i < n; i += stride) {
-            double t = ggp[i] + c;
-            a += 1.0 / t;
-            b += -1.0 / (t * t);
-        }
-        grid_sum2(grid, a, b, partials, parity, sh, s1, s2);
-        parity ^= 1;
-        fc = s1 - 1.0;
-        if (++nnewton >= 200) { st |= ACCBPG_ST_NEWTON_MAXIT; break; }
-    }
-    // the grid.sync inside the last grid_sum2 came after every block's read loop: gg may be overwritten
-    if (!gg_in)
-        for (int64_t i = first; i < n; i += stride) out[i] = 1.0 / (out[i] + c);
-    if (st) atomicOr(status, st);
-    if (info != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
-        info[0] = (double)nbis; info[1] = (double)nnewton; info[2] = c;
-    }
-}
 
 // ---------------------------------------------------------------- Burg-simplex root-find, exchange form
 // The same recurrence (functions.py:341-356) with the iterate held in REGISTERS and the grid-wide reductions done by a
@@ -625,7 +530,7 @@ __device__ __forceinline__ void burgx_round(const BurgX& X, int round, double a,
 template <int EPT>
 __global__ void __launch_bounds__(kBurgThreads) burg_simplex_x_kernel(int64_t n, const double* y, const double* g, double L,
                                                                       double eps, double* out, double* info,
-                                                                      uint32_t* status, BurgX X) {
+                                                                      uint32_t* status, BurgX X, const double* gg_in) {
     __shared__ double sh[128];
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -633,13 +538,18 @@ __global__ void __launch_bounds__(kBurgThreads) burg_simplex_x_kernel(int64_t n,
     uint32_t st = 0;
     double gg[EPT > 0 ? EPT : 1];
     double lo = kInf;
+    // gg_in != NULL: root-find only, on a ready vector gg (the gathered slices of a column-sharded run; padding entries are
+    // +inf and drop out of the minimum and of both sums); nothing but `info` is written then
+    const double* ggsrc = gg_in ? gg_in : out;
     if (EPT > 0) {
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int64_t i = first + e * stride;
             gg[e] = kInf;                               // padding drops out of the minimum and of both sums
-            if (i < n) { gg[e] = burg_shift(y, g, L, i, st) / L; lo = fmin(lo, gg[e]); }
+            if (i < n) { gg[e] = gg_in ? gg_in[i] : burg_shift(y, g, L, i, st) / L; lo = fmin(lo, gg[e]); }
         }
+    } else if (gg_in) {
+        for (int64_t i = first; i < n; i += stride) lo = fmin(lo, gg_in[i]);
     } else {
         for (int64_t i = first; i < n; i += stride) {
             const double v = burg_shift(y, g, L, i, st) / L;
@@ -664,7 +574,7 @@ __global__ void __launch_bounds__(kBurgThreads) burg_simplex_x_kernel(int64_t n,
             }
         } else {
             for (int64_t i = first; i < n; i += stride) {
-                const double t = out[i] + cc;
+                const double t = ggsrc[i] + cc;
                 a += 1.0 / t;
                 b += -1.0 / (t * t);
             }
@@ -691,7 +601,9 @@ __global__ void __launch_bounds__(kBurgThreads) burg_simplex_x_kernel(int64_t n,
         fc = s1 - 1.0;
         if (++nnewton >= 200) { st |= ACCBPG_ST_NEWTON_MAXIT; break; }
     }
-    if (EPT > 0) {
+    if (gg_in) {
+        // root-find only
+    } else if (EPT > 0) {
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int64_t i = first + e * stride;
@@ -900,12 +812,8 @@ int accbpg_ctx_create(void** out) {
     ACCBPG_CUDA(cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) ACCBPG_CUDA(cudaEventCreateWithFlags(&c->ev_rows[i], cudaEventDisableTiming));
     ACCBPG_CUDA(cudaEventCreateWithFlags(&c->ev_early_done, cudaEventDisableTiming));
-    int per_sm = 0;
-    ACCBPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, burg_simplex_kernel, kBurgThreads, 0));
-    if (per_sm < 1) { snprintf(g_err, sizeof(g_err), "burg_simplex_kernel cannot be made resident"); return ACCBPG_E_CUDA; }
-    if (per_sm > 2) per_sm = 2;
-    c->coop_blocks_burg = c->sm_count * per_sm;
-    if (c->coop_blocks_burg > kMaxBlocks) c->coop_blocks_burg = kMaxBlocks;
+    c->coop_blocks_burg = 0;
+    c->burg_calls = 0;
     ACCBPG_CUDA(cudaDeviceSynchronize());
     *out = c;
     return ACCBPG_OK;
@@ -1076,7 +984,7 @@ int accbpg_burg_prox(void* ctx, void* stream, int64_t n, int kind, double lamda,
     return launch_map(c, s, n, BurgProxF{kind, lamda, L, 4 * lamL, 2 * lamL, y, g, out}, "burg_prox");
 }
 static int burgx_launch(Ctx* c, cudaStream_t s, int64_t n, int64_t width, const double* y, const double* g, double L, double eps,
-                        double* out, double* info, const BurgX& X) {
+                        double* out, double* info, const BurgX& X, const double* gg_in = nullptr) {
     // the grid depends on `width` only (the widest slice), so every rank uses the same slot layout
     int64_t want = (width + kBurgThreads - 1) / kBurgThreads;
     static int per_sm_x = 0;                           // co-resident blocks per SM of the exchange-form kernel (all variants)
@@ -1095,11 +1003,11 @@ static int burgx_launch(Ctx* c, cudaStream_t s, int64_t n, int64_t width, const 
     if (width <= 8 * kBurgThreads && X.world == 1) grid = 1;      // small vectors: one block, no exchange (shared memory only)
     const int64_t per = (width + (int64_t)grid * kBurgThreads - 1) / ((int64_t)grid * kBurgThreads);
     ProfScope ps(P_BURG_SIMPLEX, s);
-    if (per <= 1) burg_simplex_x_kernel<1><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X);
-    else if (per <= 2) burg_simplex_x_kernel<2><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X);
-    else if (per <= 4) burg_simplex_x_kernel<4><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X);
-    else if (per <= 8) burg_simplex_x_kernel<8><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X);
-    else burg_simplex_x_kernel<0><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X);
+    if (per <= 1) burg_simplex_x_kernel<1><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
+    else if (per <= 2) burg_simplex_x_kernel<2><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
+    else if (per <= 4) burg_simplex_x_kernel<4><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
+    else if (per <= 8) burg_simplex_x_kernel<8><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
+    else burg_simplex_x_kernel<0><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
     ACCBPG_LAUNCHED("burg_simplex_x_kernel");
     return ACCBPG_OK;
 }
@@ -1144,19 +1052,11 @@ int accbpg_burg_simplex_root(void* ctx, void* stream, int64_t n, const double* g
     CTX_STREAM
     if (!gg || !d_info) return arg_err("burg_simplex_root: NULL pointer");
     if (n < 1) return arg_err("n must be >= 1");
-    int64_t want = (n + kBurgThreads - 1) / kBurgThreads;
-    int grid = (int)(want < c->coop_blocks_burg ? want : c->coop_blocks_burg);
-    double* partials = c->d_partials;
-    uint32_t* status = c->d_status;
-    const double* y = nullptr;
-    const double* g = nullptr;
-    double* out = nullptr;
-    double L = 1.0;
-    void* args[] = {&n, &y, &g, &L, &eps, &out, &d_info, &partials, &status, &gg};
-    ProfScope ps(P_BURG_SIMPLEX, s);
-    ACCBPG_CUDA(cudaLaunchCooperativeKernel((void*)burg_simplex_kernel, dim3(grid), dim3(kBurgThreads), args, 0, s));
-    ACCBPG_LAUNCHED("burg_simplex_root");
-    return ACCBPG_OK;
+    BurgX X;
+    X.tab[0] = c->d_burg_slots;
+    X.rank = 0; X.world = 1;
+    X.base = (++c->burg_calls) << 12;
+    return burgx_launch(c, s, n, n, nullptr, nullptr, 1.0, eps, nullptr, d_info, X, gg);
 }
 
 // Column-sharded prox over NVLink peer memory, in two calls.  push: the prepare kernel stores this rank's (padded) slice
@@ -1209,21 +1109,13 @@ int accbpg_burg_simplex_root_peer(void* ctx, void* stream, int64_t width, double
         peer_wait_kernel<<<1, 32, 0, s>>>(pv.flags[rank], world, epoch);
         ACCBPG_LAUNCHED("peer_wait_kernel");
     }
-    int64_t n = width * world;
-    int64_t want = (n + kBurgThreads - 1) / kBurgThreads;
-    int grid = (int)(want < c->coop_blocks_burg ? want : c->coop_blocks_burg);
-    double* partials = c->d_partials;
-    uint32_t* status = c->d_status;
-    const double* yy = nullptr;
-    const double* gg0 = nullptr;
-    double* out = nullptr;
-    double one = 1.0;
+    const int64_t n = width * world;
     const double* gg = pv.buf[rank] + (size_t)(epoch & 1ULL) * (size_t)n;
-    void* args[] = {&n, &yy, &gg0, &one, &eps, &out, &d_info, &partials, &status, &gg};
-    ProfScope ps(P_BURG_SIMPLEX, s);
-    ACCBPG_CUDA(cudaLaunchCooperativeKernel((void*)burg_simplex_kernel, dim3(grid), dim3(kBurgThreads), args, 0, s));
-    ACCBPG_LAUNCHED("burg_simplex_root");
-    return ACCBPG_OK;
+    BurgX X;
+    X.tab[0] = c->d_burg_slots;
+    X.rank = 0; X.world = 1;
+    X.base = (++c->burg_calls) << 12;
+    return burgx_launch(c, s, n, n, nullptr, nullptr, 1.0, eps, nullptr, d_info, X, gg);
 }
 
 // Sum `count` (<= 15) per-rank partial scalars over the ranks through peer memory, in rank order: one CTA stores its
