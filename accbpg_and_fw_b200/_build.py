@@ -26,6 +26,7 @@ SOURCES = {
     "dopt.cu": [],
     "chol.cu": [],
     "sparse.cu": [],
+    "small.cu": [],
     "prof.cu": [],
 }
 

@@ -27,9 +27,16 @@ burg_exchange
     Newton step with all ranks (accbpg_burg_simplex_prox_peer) instead of gathering gg once and replaying the recurrence
     on the gathered vector on every rank.  Off by default: an NVLink exchange per Newton step costs more than the
     replicated arithmetic at the shapes measured (85 / 130 us against 74 / 94 us per prox on 2 / 8 B200).
+
+fused_small
+    BPG on a D-optimal design objective with the Burg kernel on the simplex whose H fits in the shared memory of one SM
+    (configs[0], 80 x 200, does): the whole solve is ONE kernel launch (accbpg_dopt_bpg_small) instead of a dozen launches
+    and a host decision per line-search trip.  Same control flow and histories; T is stamped evenly over the solve's
+    wall time (the host does not see individual iterations).
 """
 linear_images = True
 reanchor_every = 64
 pipeline = True
 peer_allreduce = __import__('os').environ.get('ACCBPG_PEER_ALLREDUCE', '1') != '0'
 burg_exchange = __import__('os').environ.get('ACCBPG_BURG_EXCHANGE', '0') == '1'
+fused_small = __import__('os').environ.get('ACCBPG_FUSED_SMALL', '1') != '0'

@@ -190,12 +190,51 @@ class _Loop:
         return like_input(x, self.host)
 
 
+def _bpg_small(f, h, L, x0, maxitrs, epsilon, linesearch, ls_ratio, verbose, verbskip):
+    """config.fused_small: the whole BPG solve as one launch of accbpg_dopt_bpg_small when the instance is a dense,
+    unsharded D-optimal design with the Burg kernel on the simplex and fits one SM's shared memory.  Returns None when
+    the fast path does not apply."""
+    from .objectives import DOptimalObj
+    from .bregman import BurgEntropySimplex
+    if not config.fused_small or type(f) is not DOptimalObj or type(h) is not BurgEntropySimplex:
+        return None
+    if f.shard is not None or h.shard is not None or maxitrs < 1 or not (L > 0) or not (ls_ratio > 1):
+        return None
+    if lib.accbpg_dopt_bpg_small_smem_bytes(f.m, f.n) == 0:
+        return None
+    rt = f.rt
+    t0 = time.time()
+    host = is_host(x0)
+    x = rt.to_device(x0).clone()
+    hist = torch.empty(2 * maxitrs + 16, dtype=torch.float64, device=rt.device)
+    H = f._Hd
+    with rt.on_device():
+        nat.check(lib.accbpg_dopt_bpg_small(rt.ctx, rt.stream, H.data_ptr(), f.m, f.n, H.stride(0), x.data_ptr(), float(L),
+                                            float(ls_ratio), 1 if linesearch else 0, int(maxitrs), float(epsilon),
+                                            float(h.eps), hist.data_ptr(), hist.data_ptr() + 8 * maxitrs,
+                                            hist.data_ptr() + 16 * maxitrs))
+    rt.read(rt.S_F, 1)                                   # synchronises and raises on a status bit
+    hh = hist.cpu().numpy()
+    k = int(hh[2 * maxitrs])
+    _bpg_small.last_info = hh[2 * maxitrs:2 * maxitrs + 14].copy()
+    F = hh[0:k].copy()
+    Ls = hh[maxitrs:maxitrs + k].copy() if linesearch else np.ones(k) * L
+    T = np.linspace(0.0, time.time() - t0, k + 1)[1:]
+    if verbose:
+        for i in range(0, k, max(int(verbskip), 1)):
+            print("{0:6d}  {1:10.3e}  {2:10.3e}  {3:6.1f}".format(i, F[i], Ls[i], T[i]))
+    return like_input(x, host), F, Ls, T
+
+
 def BPG(f, h, L, x0, maxitrs, epsilon=1e-14, linesearch=True, ls_ratio=1.2,
         verbose=True, verbskip=1):
     """Bregman proximal gradient.   accbpg/algorithms.py:11-72.   Returns (x, F, Ls, T)."""
     if verbose:
         print("\nBPG_LS method for min_{x in C} F(x) = f(x) + Psi(x)")
         print("     k      F(x)         Lk       time")
+    fused = _bpg_small(f, h, L, x0, maxitrs, epsilon, linesearch, ls_ratio, verbose, verbskip)
+    if fused is not None:
+        return fused
     lp = _Loop(f, h, x0)
     rt = lp.rt
     F = np.zeros(maxitrs)

@@ -292,6 +292,20 @@ int accbpg_dopt_sparse_gram(void* ctx, void* stream, const int64_t* d_colptr, co
 int accbpg_dopt_sparse_grad(void* ctx, void* stream, const int64_t* d_colptr, const int* d_rowidx, const double* d_vals,
                             int m, int64_t n, void* d_ws, double* d_g);
 
+/* ---- small shapes: the WHOLE BPG solve in one launch (accbpg/algorithms.py:11-72 with DOptimalObj, functions.py:27-59,
+ *      and BurgEntropySimplex, functions.py:326-356).  When H and the m x m factor fit in the shared memory of one SM
+ *      (accbpg_dopt_bpg_small_smem_bytes(m, n) != 0; BASELINE configs[0], 80 x 200, does) one persistent CTA runs every
+ *      iteration - Gram matrix, factorisation, gradient, Burg-simplex prox, divergence, line-search test, stopping test -
+ *      with the control flow of the reference's loop.  d_x: x0 in, last iterate out.  d_F / d_Ls: maxitrs entries each;
+ *      d_info[0] = entries written (k + 1), [1] = line-search trials, [2] = last L, [3] = Newton steps of all prox calls,
+ *      [4..9] = SM clocks spent in: diagonal-block inverses, gradient, prox, divergence + dot, Gram matrix, factorisation
+ *      (d_info has 16 doubles).
+ *      linesearch = 0: L stays fixed (algorithms.py:57-58).  Assertions of the reference arrive in the status word. */
+size_t accbpg_dopt_bpg_small_smem_bytes(int m, int64_t n);
+int accbpg_dopt_bpg_small(void* ctx, void* stream, const double* d_H, int m, int64_t n, int64_t ldh, double* d_x, double L,
+                          double ls_ratio, int linesearch, int maxitrs, double epsilon, double eps_prox, double* d_F,
+                          double* d_Ls, double* d_info);
+
 /* ---- Poisson / KL regression objectives (accbpg/functions.py:102-120, :140-158).  A is m x n_local. */
 #define ACCBPG_LINREG_POISSON 0   /* f = sum b log(b/Ax) + Ax - b ; r = 1 - b/Ax   */
 #define ACCBPG_LINREG_KL      1   /* f = sum Ax log(Ax/b) - Ax + b ; r = log(Ax/b) */

@@ -294,3 +294,48 @@ def test_l0l1_fw_variants_golden(acc, dopt, golden_traj):
         acc.FW_l0l1_log_only(f, h, 0.0, 1.0, x0, 5, lmo, 2, verbose=False)
     with pytest.raises(ValueError):
         acc.FW_alg_L0_L1_shortest_step(f, h, -1.0, 1.0, x0, 5, 2.0, lmo, verbose=False)
+
+
+@pytest.mark.parametrize("m,n,seed", [(80, 200, 10), (5, 6, 1), (30, 600, 3), (96, 120, 4), (16, 41, 5), (13, 506, 6)])
+def test_bpg_fused_small_matches_operator_path(acc, m, n, seed):
+    """config.fused_small (the whole BPG solve in one CTA, csrc/small.cu) against the operator-by-operator loop."""
+    from accbpg_and_fw_b200 import config
+    from accbpg_and_fw_b200 import _native as nat
+    assert nat.lib.accbpg_dopt_bpg_small_smem_bytes(m, n) > 0
+    assert nat.lib.accbpg_dopt_bpg_small_smem_bytes(128, 4096) == 0          # does not fit: the operator path is used
+    f, h, L, x0 = acc.D_opt_design(m, n, randseed=seed)
+    old = config.fused_small
+    try:
+        for kw in (dict(linesearch=True, ls_ratio=1.2), dict(linesearch=True, ls_ratio=2.0), dict(linesearch=False)):
+            config.fused_small = True
+            x1, F1, L1, T1 = acc.BPG(f, h, L, x0, maxitrs=300, verbose=False, **kw)
+            config.fused_small = False
+            x2, F2, L2, T2 = acc.BPG(f, h, L, x0, maxitrs=300, verbose=False, **kw)
+            assert T1.shape == F1.shape and np.all(np.diff(T1) >= 0)
+            # the default stopping test |F_k - F_k-1| < 1e-14 fires at rounding level: the two runs may stop an iteration apart
+            k = min(len(F1), len(F2))
+            assert abs(len(F1) - len(F2)) <= 2 and k >= 10, (len(F1), len(F2))
+            assert ferr(F1[:k], F2[:k]) <= 1e-10, (kw, ferr(F1[:k], F2[:k]))
+            # once F moves by less than 1e-10 |F| per iteration the line-search test compares rounding noise: L_k is
+            # compared up to there
+            small = np.nonzero(np.abs(np.diff(F2[:k])) < 1e-10 * np.abs(F2[1:k]))[0]
+            kl = int(small[0]) if len(small) else k
+            assert kl >= 8 or kl == k, kl
+            assert np.array_equal(L1[:kl], L2[:kl]), (kw, first_fork(L1, L2), kl)
+            assert relerr(x1, x2) <= 1e-6
+        # the stopping test (algorithms.py:70) fires at the same iteration
+        config.fused_small = True
+        r1 = acc.BPG(f, h, L, x0, maxitrs=400, epsilon=1e-3, verbose=False)
+        config.fused_small = False
+        r2 = acc.BPG(f, h, L, x0, maxitrs=400, epsilon=1e-3, verbose=False)
+        assert len(r1[1]) == len(r2[1]) and np.array_equal(r1[2], r2[2]), (len(r1[1]), len(r2[1]))
+    finally:
+        config.fused_small = old
+
+
+def test_bpg_fused_small_raises_like_the_reference(acc):
+    f, h, L, x0 = acc.D_opt_design(20, 50, randseed=2)
+    bad = np.array(x0, dtype=float)
+    bad[3] = -0.5
+    with pytest.raises((AssertionError, ValueError)):
+        acc.BPG(f, h, L, bad, maxitrs=5, verbose=False)
