@@ -28,15 +28,23 @@ def ferr(F, Fref):
     return float(np.max(np.abs(F - Fref) / np.maximum(np.abs(Fref), 1e-3)))
 
 
-def test_bpg_golden(acc, dopt, golden_traj):
+@pytest.mark.parametrize("fused", [True, False])
+def test_bpg_golden(acc, dopt, golden_traj, fused):
+    """fused: the whole solve in one CTA (config.fused_small, csrc/small.cu); not fused: the operator-by-operator loop."""
+    from accbpg_and_fw_b200 import config
     f, h, L, x0 = dopt
-    x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=1000, linesearch=True, ls_ratio=1.2, verbose=False)
-    assert ferr(F, golden_traj["bpg_ls_F"]) <= FTOL
-    assert np.array_equal(Ls, golden_traj["bpg_ls_Ls"])
-    assert relerr(x, golden_traj["bpg_ls_x"]) <= 1e-6
-    assert T.shape == F.shape and np.all(np.diff(T) >= 0)
-    x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=300, linesearch=False, verbose=False)
-    assert ferr(F, golden_traj["bpg_F"]) <= FTOL and np.all(Ls == L)
+    old = config.fused_small
+    config.fused_small = fused
+    try:
+        x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=1000, linesearch=True, ls_ratio=1.2, verbose=False)
+        assert ferr(F, golden_traj["bpg_ls_F"]) <= FTOL
+        assert np.array_equal(Ls, golden_traj["bpg_ls_Ls"])
+        assert relerr(x, golden_traj["bpg_ls_x"]) <= 1e-6
+        assert T.shape == F.shape and np.all(np.diff(T) >= 0)
+        x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=300, linesearch=False, verbose=False)
+        assert ferr(F, golden_traj["bpg_F"]) <= FTOL and np.all(Ls == L)
+    finally:
+        config.fused_small = old
 
 
 def test_abpg_golden(acc, dopt, golden_traj):
