@@ -56,7 +56,7 @@ struct SmallParams {
     const double* H; int m, n; int64_t ldh;
     double* x;                       // in: x0, out: the last iterate
     double L, ls_ratio, epsilon, eps_prox;
-    int linesearch, maxitrs, dbg;
+    int linesearch, maxitrs;
     double* F; double* Ls;           // histories, maxitrs entries each
     double* info;                    // [0] entries written (k + 1), [1] line-search trials, [2] last L, [3] Newton steps in total, [4..9] clocks per phase
     uint32_t* status;
@@ -67,7 +67,6 @@ struct SmallCtx {
     int m, n, MP, NP, ldn, lda;
     int tid, lane, warp, g, t;
     int flip;
-    int dbg;
     long long tf0, tf1, tf2, tf3;        // clocks inside the factorisation: diagonal tile, its inverse, panel, trailing update
 };
 
@@ -476,7 +475,6 @@ __global__ void __launch_bounds__(SM_THREADS, 1) dopt_bpg_small_kernel(SmallPara
     c.m = p.m; c.n = p.n; c.MP = pl.MP; c.NP = pl.NP; c.ldn = pl.ldn; c.lda = pl.lda;
     c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5; c.g = c.lane >> 2; c.t = c.lane & 3;
     c.flip = 0;
-    c.dbg = p.dbg;
     c.tf0 = c.tf1 = c.tf2 = c.tf3 = 0;
     const bool vec = ((reinterpret_cast<uintptr_t>(p.H) & 15u) == 0) && (p.ldh % 2 == 0) && (p.n % 2 == 0);
     uint32_t st = 0;
@@ -589,7 +587,6 @@ int accbpg_dopt_bpg_small(void* ctx, void* stream, const double* H, int m, int64
     p.H = H; p.m = m; p.n = (int)n; p.ldh = ldh; p.x = x; p.L = L; p.ls_ratio = ls_ratio; p.epsilon = epsilon;
     p.eps_prox = eps_prox; p.linesearch = linesearch; p.maxitrs = maxitrs; p.F = F_out; p.Ls = Ls_out; p.info = info_out;
     p.status = c->d_status;
-    { const char* e = getenv("ACCBPG_SMALL_DBG"); p.dbg = e ? atoi(e) : 0; }
     dopt_bpg_small_kernel<<<1, SM_THREADS, smem, s>>>(p);
     ACCBPG_LAUNCHED("dopt_bpg_small_kernel");
     return ACCBPG_OK;

@@ -1005,7 +1005,9 @@ static int burgx_launch(Ctx* c, cudaStream_t s, int64_t n, int64_t width, const 
     ProfScope ps(P_BURG_SIMPLEX, s);
     if (per <= 1) burg_simplex_x_kernel<1><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
     else if (per <= 2) burg_simplex_x_kernel<2><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
+    else if (per <= 3) burg_simplex_x_kernel<3><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
     else if (per <= 4) burg_simplex_x_kernel<4><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
+    else if (per <= 6) burg_simplex_x_kernel<6><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
     else if (per <= 8) burg_simplex_x_kernel<8><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
     else burg_simplex_x_kernel<0><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
     ACCBPG_LAUNCHED("burg_simplex_x_kernel");
