@@ -304,7 +304,8 @@ def test_l0l1_fw_variants_golden(acc, dopt, golden_traj):
         acc.FW_alg_L0_L1_shortest_step(f, h, -1.0, 1.0, x0, 5, 2.0, lmo, verbose=False)
 
 
-@pytest.mark.parametrize("m,n,seed", [(80, 200, 10), (5, 6, 1), (30, 600, 3), (96, 120, 4), (16, 41, 5), (13, 506, 6)])
+@pytest.mark.parametrize("m,n,seed", [(80, 200, 10), (5, 6, 1), (30, 600, 3), (96, 120, 4), (16, 41, 5), (13, 506, 6),
+                                      (2, 3, 7), (7, 9, 8), (64, 300, 9), (33, 400, 11), (8, 1100, 12), (70, 197, 13)])
 def test_bpg_fused_small_matches_operator_path(acc, m, n, seed):
     """config.fused_small (the whole BPG solve in one CTA, csrc/small.cu) against the operator-by-operator loop."""
     from accbpg_and_fw_b200 import config
@@ -347,3 +348,11 @@ def test_bpg_fused_small_raises_like_the_reference(acc):
     bad[3] = -0.5
     with pytest.raises((AssertionError, ValueError)):
         acc.BPG(f, h, L, bad, maxitrs=5, verbose=False)
+
+
+def test_bpg_fused_small_is_deterministic(acc):
+    """Fixed-order reductions everywhere: two solves of the same instance are bit-identical."""
+    f, h, L, x0 = acc.D_opt_design(80, 200, randseed=10)
+    a = acc.BPG(f, h, L, x0, maxitrs=200, verbose=False)
+    b = acc.BPG(f, h, L, x0, maxitrs=200, verbose=False)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(np.asarray(a[0]), np.asarray(b[0]))
