@@ -16,6 +16,8 @@
 //                                    refilled from global memory (L2) by cp.async under the prox   (functions.py:52-58)
 //   prox      Burg-simplex root-find (functions.py:341-356) with the CTA-wide sums of a Newton step in one barrier
 //   test      f(x+) > f(x) + <g, x+ - x> + L D(x+, x)  ->  L *= ls_ratio                      (algorithms.py:46-56)
+#include <cooperative_groups.h>
+
 #include "dmma.cuh"
 
 namespace accbpg {
@@ -27,19 +29,23 @@ constexpr int SM_SMEM_LIMIT = 220 * 1024;
 #define kInf (__longlong_as_double(0x7ff0000000000000LL))
 
 struct SmallPlan {
-    int MP, NP, ldn, lda;
-    size_t off_H, off_A, off_x, off_x1, off_g, off_d, off_rinv, off_cp, off_xd, off_red, bytes;
+    int MP, NP, NL, ldn, lda, nblk16;
+    size_t off_H, off_A, off_part, off_x, off_x1, off_g, off_d, off_rinv, off_cp, off_xd, off_red, bytes;
 };
 
-__host__ __device__ inline SmallPlan small_plan(int m, int n) {
+// C = CTAs of the cluster: CTA r holds columns [r NL, (r + 1) NL) of H (NL a multiple of 8); vectors are replicated
+__host__ __device__ inline SmallPlan small_plan(int m, int n, int C) {
     SmallPlan p;
     p.MP = (m + 15) / 16 * 16;
-    p.NP = (n + 7) / 8 * 8;
-    p.ldn = p.NP + 4;                 // = 4 mod 8: DMMA fragment reads (8 rows x 4 consecutive doubles) hit every bank pair once
+    p.NL = ((n + C - 1) / C + 7) / 8 * 8;
+    p.NP = p.NL * C;                  // vectors are padded to the cluster's column range (>= n)
+    p.ldn = p.NL + 4;                 // = 4 mod 8: DMMA fragment reads (8 rows x 4 consecutive doubles) hit every bank pair once
     p.lda = p.MP + 4;
+    p.nblk16 = (p.MP / 16) * (p.MP / 16 + 1) / 2;
     size_t o = 0;
     p.off_H = o;    o += (size_t)p.MP * p.ldn * 8;
     p.off_A = o;    o += (size_t)p.MP * p.lda * 8;
+    p.off_part = o; o += (C > 1) ? (size_t)2 * p.nblk16 * 256 * 8 : 0;   // this CTA's partial Gram blocks, double buffered
     p.off_x = o;    o += (size_t)p.NP * 8;
     p.off_x1 = o;   o += (size_t)p.NP * 8;
     p.off_g = o;    o += (size_t)p.NP * 8;
@@ -63,8 +69,9 @@ struct SmallParams {
 };
 
 struct SmallCtx {
-    double *Hs, *A, *xs, *x1s, *gs, *dv, *rinv, *Cp, *Xd, *red;
+    double *Hs, *A, *part, *xs, *x1s, *gs, *dv, *rinv, *Cp, *Xd, *red;
     int m, n, MP, NP, ldn, lda;
+    int C, rank, NL, col0, nloc, nblk16, gcount;     // cluster size / rank, local column slice [col0, col0 + nloc), Gram calls so far
     int tid, lane, warp, g, t;
     int flip;
     long long tf0, tf1, tf2, tf3;        // clocks inside the factorisation: diagonal tile, its inverse, panel, trailing update
@@ -98,29 +105,38 @@ __device__ __forceinline__ double cta_min(SmallCtx& c, double a) {
     return r;
 }
 
-// ---- H (global, L2 resident after the first pass) -> shared-memory copy; rows >= m and columns >= n stay zero
+// ---- this CTA's columns of H (global, L2 resident after the first pass) -> shared-memory copy; rows >= m and columns
+//      beyond the slice stay zero
 __device__ __forceinline__ void small_fill_H(const SmallCtx& c, const SmallParams& p, bool vec) {
+    if (c.nloc <= 0) return;
     if (vec) {
-        const int per_row = c.n >> 1;                   // 16-byte chunks per row
+        const int per_row = c.nloc >> 1;                // 16-byte chunks per row (col0 and nloc are even here)
         const int total = c.m * per_row;
         for (int e = c.tid; e < total; e += SM_THREADS) {
             const int i = e / per_row, q = e - i * per_row;
-            cp_async16(c.Hs + (size_t)i * c.ldn + 2 * q, p.H + (int64_t)i * p.ldh + 2 * q, 16);
+            cp_async16(c.Hs + (size_t)i * c.ldn + 2 * q, p.H + (int64_t)i * p.ldh + c.col0 + 2 * q, 16);
         }
         cp_async_commit();
     } else {
-        const int total = c.m * c.n;
+        const int total = c.m * c.nloc;
         for (int e = c.tid; e < total; e += SM_THREADS) {
-            const int i = e / c.n, j = e - i * c.n;
-            c.Hs[(size_t)i * c.ldn + j] = p.H[(int64_t)i * p.ldh + j];
+            const int i = e / c.nloc, j = e - i * c.nloc;
+            c.Hs[(size_t)i * c.ldn + j] = p.H[(int64_t)i * p.ldh + c.col0 + j];
         }
     }
 }
 
-// ---- A <- H diag(v) H^T (lower 16 x 16 blocks; diagonal blocks are written in full)
-__device__ __forceinline__ void small_gram(const SmallCtx& c, const double* v) {
+// ---- A <- H diag(v) H^T (lower 16 x 16 blocks; diagonal blocks are written in full).  In a cluster every CTA forms the
+//      blocks over ITS columns, leaves them (packed, 256 doubles per block) in its partial buffer, and after one cluster
+//      barrier every CTA adds the C partial buffers in rank order through distributed shared memory: all CTAs hold the
+//      same A, bit for bit.  The partial buffers alternate between calls, so the barrier of the next call also covers
+//      the reads of this one.
+template <int C>
+__device__ __forceinline__ void small_gram(SmallCtx& c, const double* v) {
     const int nb = c.MP >> 4;
-    const int nblocks = nb * (nb + 1) / 2;
+    const int nblocks = c.nblk16;
+    double* part = (C > 1) ? c.part + (size_t)(c.gcount & 1) * nblocks * 256 : nullptr;
+    const double* vl = v + c.col0;
     for (int b = c.warp; b < nblocks; b += SM_WARPS) {
         int bi = (int)((sqrtf(8.0f * b + 1.0f) - 1.0f) * 0.5f);
         while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
@@ -135,8 +151,8 @@ __device__ __forceinline__ void small_gram(const SmallCtx& c, const double* v) {
         const double* bp = c.Hs + (size_t)(bj * 16 + c.g) * c.ldn + c.t;
         const size_t r8 = (size_t)8 * c.ldn;
 #pragma unroll 2
-        for (int k0 = 0; k0 < c.NP; k0 += 4) {
-            const double xv = v[k0 + c.t];
+        for (int k0 = 0; k0 < c.NL; k0 += 4) {
+            const double xv = vl[k0 + c.t];
             const double a0 = ap[k0] * xv, a1 = ap[r8 + k0] * xv;
             const double b0 = bp[k0], b1 = bp[r8 + k0];
             dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
@@ -148,21 +164,41 @@ __device__ __forceinline__ void small_gram(const SmallCtx& c, const double* v) {
         for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                double* o = c.A + (size_t)(bi * 16 + i * 8 + c.g) * c.lda + bj * 16 + j * 8 + 2 * c.t;
+                double* o = (C > 1) ? part + (size_t)b * 256 + (i * 8 + c.g) * 16 + j * 8 + 2 * c.t
+                                    : c.A + (size_t)(bi * 16 + i * 8 + c.g) * c.lda + bj * 16 + j * 8 + 2 * c.t;
                 o[0] = acc[i][j][0];
                 o[1] = acc[i][j][1];
             }
     }
+    if (C > 1) {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cl = cg::this_cluster();
+        cl.sync();
+        const double* src[C];
+#pragma unroll
+        for (int r = 0; r < C; ++r) src[r] = cl.map_shared_rank(part, r);
+        for (int e = c.tid; e < nblocks * 128; e += SM_THREADS) {          // a pair of doubles per thread and step
+            const int b = e >> 7, w = (e & 127) * 2;
+            int bi = (int)((sqrtf(8.0f * b + 1.0f) - 1.0f) * 0.5f);
+            while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+            while (bi * (bi + 1) / 2 > b) --bi;
+            const int bj = b - bi * (bi + 1) / 2;
+            double2 sacc = *reinterpret_cast<const double2*>(src[0] + (size_t)b * 256 + w);
+#pragma unroll
+            for (int r = 1; r < C; ++r) {
+                const double2 q = *reinterpret_cast<const double2*>(src[r] + (size_t)b * 256 + w);
+                sacc.x += q.x;
+                sacc.y += q.y;
+            }
+            double* o = c.A + (size_t)(bi * 16 + (w >> 4)) * c.lda + bj * 16 + (w & 15);
+            o[0] = sacc.x;
+            o[1] = sacc.y;
+        }
+    }
+    ++c.gcount;
+    (void)nb;
 }
 
-// ---- in place: A (lower, symmetric positive definite; diagonal 8 x 8 tiles held in full) -> unit lower factor Lt below the
-//      diagonal, pivots d in dv, 1/d in rinv, inverses of the unit lower diagonal tiles in Xd.  Returns -sum log d (the
-//      objective); `bad` is set when a pivot is not positive.  Blocked right-looking, 8 columns per panel:
-//        diagonal  ONE thread eliminates the 8 x 8 diagonal tile in registers (the eight pivots are a chain of dependent
-//                  reciprocal -> multiply -> FMA; more threads would only add shuffle latency to it), then eight lanes
-//                  invert the unit lower tile, a column each
-//        panel     rows below: C[I] = A[I, panel] X^T (= Lt D, two DMMAs per 8 x 8 tile), Lt[I] = C[I] D^-1
-//        trailing  8 x 8 tiles of the lower triangle: A[I,K] -= Lt[I] C[K]^T, two DMMAs each
 // reciprocal for the pivot chain: 20-bit seed and two Newton steps (4 dependent FMAs, no special-case branches; pivots of a
 // positive definite matrix are normal numbers); within 1 ulp of 1/d
 __device__ __forceinline__ double pivot_rcp(double d) {
@@ -377,16 +413,29 @@ __device__ __forceinline__ void small_gradient_blocks(const SmallCtx& c, int cb0
             n1[b] += __shfl_xor_sync(0xffffffffu, n1[b], o);
         }
         if (c.g == 0) {
-            c.gs[(cb0 + b * SM_WARPS) * 8 + 2 * c.t] = -n0[b];
-            c.gs[(cb0 + b * SM_WARPS) * 8 + 2 * c.t + 1] = -n1[b];
+            c.gs[c.col0 + (cb0 + b * SM_WARPS) * 8 + 2 * c.t] = -n0[b];
+            c.gs[c.col0 + (cb0 + b * SM_WARPS) * 8 + 2 * c.t + 1] = -n1[b];
         }
     }
 }
+template <int C>
 __device__ __forceinline__ void small_gradient(const SmallCtx& c) {
-    const int ncb = c.NP >> 3;
+    const int ncb = c.NL >> 3;
     for (int cb = c.warp; cb < ncb; cb += 2 * SM_WARPS) {
         if (cb + SM_WARPS < ncb) small_gradient_blocks<2>(c, cb);
         else small_gradient_blocks<1>(c, cb);
+    }
+    if (C > 1) {
+        // every CTA needs the whole gradient for the (replicated) prox: each one stores its slice into the other CTAs'
+        // vectors through distributed shared memory; the cluster barrier that publishes it follows in the caller
+        namespace cg = cooperative_groups;
+        cg::cluster_group cl = cg::this_cluster();
+        __syncthreads();
+#pragma unroll
+        for (int r = 1; r < C; ++r) {
+            double* dst = cl.map_shared_rank(c.gs, (c.rank + r) % C);
+            for (int i = c.tid; i < c.NL; i += SM_THREADS) dst[c.col0 + i] = c.gs[c.col0 + i];
+        }
     }
 }
 
@@ -463,24 +512,32 @@ __device__ __forceinline__ int small_prox(SmallCtx& c, double L, double eps, uin
     return nnewton;
 }
 
+template <int C>
 __global__ void __launch_bounds__(SM_THREADS, 1) dopt_bpg_small_kernel(SmallParams p) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    const SmallPlan pl = small_plan(p.m, p.n);
+    namespace cg = cooperative_groups;
+    const SmallPlan pl = small_plan(p.m, p.n, C);
     SmallCtx c;
     c.Hs = (double*)(sm_raw + pl.off_H);   c.A = (double*)(sm_raw + pl.off_A);
+    c.part = (double*)(sm_raw + pl.off_part);
     c.xs = (double*)(sm_raw + pl.off_x);   c.x1s = (double*)(sm_raw + pl.off_x1);
     c.gs = (double*)(sm_raw + pl.off_g);   c.dv = (double*)(sm_raw + pl.off_d);
     c.rinv = (double*)(sm_raw + pl.off_rinv); c.Cp = (double*)(sm_raw + pl.off_cp);
     c.Xd = (double*)(sm_raw + pl.off_xd);  c.red = (double*)(sm_raw + pl.off_red);
     c.m = p.m; c.n = p.n; c.MP = pl.MP; c.NP = pl.NP; c.ldn = pl.ldn; c.lda = pl.lda;
+    c.C = C; c.rank = (C > 1) ? (int)cg::this_cluster().block_rank() : 0;
+    c.NL = pl.NL; c.col0 = c.rank * pl.NL; c.nloc = min(pl.NL, p.n - c.col0); c.nblk16 = pl.nblk16; c.gcount = 0;
+    if (c.nloc < 0) c.nloc = 0;
     c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5; c.g = c.lane >> 2; c.t = c.lane & 3;
     c.flip = 0;
     c.tf0 = c.tf1 = c.tf2 = c.tf3 = 0;
     const bool vec = ((reinterpret_cast<uintptr_t>(p.H) & 15u) == 0) && (p.ldh % 2 == 0) && (p.n % 2 == 0);
+    const bool writer = c.rank == 0;
     uint32_t st = 0;
 
     for (size_t e = c.tid; e < pl.bytes / 8; e += SM_THREADS) ((double*)sm_raw)[e] = 0.0;
     __syncthreads();
+    if (C > 1) cg::this_cluster().sync();               // no CTA's shared memory is written remotely before it is cleared
     small_fill_H(c, p, vec);
     for (int i = c.tid; i < p.n; i += SM_THREADS) {
         const double v = p.x[i];
@@ -494,7 +551,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) dopt_bpg_small_kernel(SmallPara
     long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tp5 = 0;   // clocks per phase: diag inverses, gradient, prox, div/dot, Gram, factor
     long long tc = clock64();
 #define SM_LAP(v) { const long long now_ = clock64(); v += now_ - tc; tc = now_; }
-    small_gram(c, c.xs);
+    small_gram<C>(c, c.xs);
     __syncthreads();
     double fx = small_factor(c, bad);
     double L = p.L;
@@ -502,11 +559,12 @@ __global__ void __launch_bounds__(SM_THREADS, 1) dopt_bpg_small_kernel(SmallPara
     double fprev = 0.0;
     if (bad) st |= ACCBPG_ST_NOT_PD;
     for (; k < p.maxitrs && !bad; ++k) {
-        if (c.tid == 0) p.F[k] = fx;
+        if (writer && c.tid == 0) p.F[k] = fx;
         // gradient at x from the factor in A
         tc = clock64();
-        small_gradient(c);
-        __syncthreads();
+        small_gradient<C>(c);
+        if (C > 1) cg::this_cluster().sync();           // the other CTAs' slices of the gradient have arrived
+        else __syncthreads();
         small_fill_H(c, p, vec);                        // refill the copy of H under the prox
         SM_LAP(tp1);
         if (p.linesearch) L = L / p.ls_ratio;
@@ -527,7 +585,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) dopt_bpg_small_kernel(SmallPara
             if (vec) cp_async_wait<0>();
             cta_sum2(c, dsum, dot);                     // (its barrier also publishes the refilled H)
             SM_LAP(tp3);
-            small_gram(c, c.x1s);
+            small_gram<C>(c, c.x1s);
             __syncthreads();
             SM_LAP(tp4);
             f1 = small_factor(c, bad);
@@ -539,21 +597,62 @@ __global__ void __launch_bounds__(SM_THREADS, 1) dopt_bpg_small_kernel(SmallPara
         }
         if (bad) { ++k; break; }
         for (int i = c.tid; i < p.n; i += SM_THREADS) c.xs[i] = c.x1s[i];
-        if (c.tid == 0) p.Ls[k] = L;
+        if (writer && c.tid == 0) p.Ls[k] = L;
         const double fk = fx;
         fx = f1;
         __syncthreads();
         if (k > 0 && fabs(fk - fprev) < p.epsilon) { ++k; break; }       // algorithms.py:70
         fprev = fk;
     }
-    for (int i = c.tid; i < p.n; i += SM_THREADS) p.x[i] = c.xs[i];
+    if (C > 1) cg::this_cluster().sync();               // nobody leaves while its shared memory may still be read
+    if (writer)
+        for (int i = c.tid; i < p.n; i += SM_THREADS) p.x[i] = c.xs[i];
     if (st) atomicOr(p.status, st);
-    if (c.tid == 0) {
+    if (writer && c.tid == 0) {
         p.info[0] = (double)k; p.info[1] = (double)trials; p.info[2] = L; p.info[3] = (double)newton;
         p.info[4] = (double)tp0; p.info[5] = (double)tp1; p.info[6] = (double)tp2; p.info[7] = (double)tp3;
         p.info[8] = (double)tp4; p.info[9] = (double)tp5;
         p.info[10] = (double)c.tf0; p.info[11] = (double)c.tf1; p.info[12] = (double)c.tf2; p.info[13] = (double)c.tf3;
     }
+}
+
+// cluster size for a shape: the largest of {preferred, 2, 1} whose plan fits one SM's shared memory (a cluster also
+// admits shapes whose H does not fit a single CTA).  ACCBPG_SMALL_CLUSTER = 1 / 2 / 4 overrides the preference.
+static int small_pick_cluster(int m, int64_t n, size_t* bytes) {
+    if (m < 1 || m > SM_MAX_M || n < 2 || n > 65536 || n <= m) return 0;
+    static int pref = 0;
+    if (pref == 0) { const char* e = getenv("ACCBPG_SMALL_CLUSTER"); pref = e ? atoi(e) : 4; if (pref != 1 && pref != 2 && pref != 4) pref = 4; }
+    const int cand[3] = {pref, pref > 2 ? 2 : 1, 1};
+    for (int q = 0; q < 3; ++q) {
+        const int C = cand[q];
+        if (C > 1 && n < 32 * C) continue;              // too few columns to be worth splitting
+        const SmallPlan pl = small_plan(m, (int)n, C);
+        if (pl.bytes <= (size_t)SM_SMEM_LIMIT) { if (bytes) *bytes = pl.bytes; return C; }
+    }
+    return 0;
+}
+
+template <int C>
+static int small_launch(Ctx* c, cudaStream_t s, const SmallParams& p, size_t smem) {
+    static bool attr_done[kMaxDevices] = {};
+    if (!(c->device >= 0 && c->device < kMaxDevices && attr_done[c->device])) {
+        ACCBPG_CUDA(cudaFuncSetAttribute(dopt_bpg_small_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_LIMIT));
+        if (c->device >= 0 && c->device < kMaxDevices) attr_done[c->device] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C, 1, 1);
+    cfg.blockDim = dim3(SM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = C > 1 ? 1 : 0;
+    ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, dopt_bpg_small_kernel<C>, p));
+    return ACCBPG_OK;
 }
 
 }  // namespace accbpg
@@ -563,9 +662,8 @@ using namespace accbpg;
 extern "C" {
 
 size_t accbpg_dopt_bpg_small_smem_bytes(int m, int64_t n) {
-    if (m < 1 || m > SM_MAX_M || n < 2 || n > 65536 || n <= m) return 0;
-    const SmallPlan pl = small_plan(m, (int)n);
-    return pl.bytes <= (size_t)SM_SMEM_LIMIT ? pl.bytes : 0;
+    size_t bytes = 0;
+    return small_pick_cluster(m, n, &bytes) ? bytes : 0;
 }
 
 int accbpg_dopt_bpg_small(void* ctx, void* stream, const double* H, int m, int64_t n, int64_t ldh, double* x, double L,
@@ -575,19 +673,16 @@ int accbpg_dopt_bpg_small(void* ctx, void* stream, const double* H, int m, int64
     cudaStream_t s = (cudaStream_t)stream;
     if (!c || !H || !x || !F_out || !Ls_out || !info_out) return arg_err("dopt_bpg_small: NULL pointer");
     ACCBPG_ON_DEVICE(c);
-    const size_t smem = accbpg_dopt_bpg_small_smem_bytes(m, n);
-    if (smem == 0 || ldh < n) return arg_err("dopt_bpg_small: shape does not fit one CTA (accbpg_dopt_bpg_small_smem_bytes)");
+    size_t smem = 0;
+    const int C = small_pick_cluster(m, n, &smem);
+    if (C == 0 || ldh < n) return arg_err("dopt_bpg_small: shape does not fit one SM (accbpg_dopt_bpg_small_smem_bytes)");
     if (!(L > 0.0) || !(ls_ratio > 1.0) || maxitrs < 1 || !(eps_prox > 0.0)) return arg_err("dopt_bpg_small: L, ls_ratio, maxitrs, eps");
-    static bool attr_done[kMaxDevices] = {};
-    if (!(c->device >= 0 && c->device < kMaxDevices && attr_done[c->device])) {
-        ACCBPG_CUDA(cudaFuncSetAttribute(dopt_bpg_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_LIMIT));
-        if (c->device >= 0 && c->device < kMaxDevices) attr_done[c->device] = true;
-    }
     SmallParams p;
     p.H = H; p.m = m; p.n = (int)n; p.ldh = ldh; p.x = x; p.L = L; p.ls_ratio = ls_ratio; p.epsilon = epsilon;
     p.eps_prox = eps_prox; p.linesearch = linesearch; p.maxitrs = maxitrs; p.F = F_out; p.Ls = Ls_out; p.info = info_out;
     p.status = c->d_status;
-    dopt_bpg_small_kernel<<<1, SM_THREADS, smem, s>>>(p);
+    int rc = C == 4 ? small_launch<4>(c, s, p, smem) : C == 2 ? small_launch<2>(c, s, p, smem) : small_launch<1>(c, s, p, smem);
+    if (rc) return rc;
     ACCBPG_LAUNCHED("dopt_bpg_small_kernel");
     return ACCBPG_OK;
 }

@@ -294,7 +294,8 @@ int accbpg_dopt_sparse_grad(void* ctx, void* stream, const int64_t* d_colptr, co
 
 /* ---- small shapes: the WHOLE BPG solve in one launch (accbpg/algorithms.py:11-72 with DOptimalObj, functions.py:27-59,
  *      and BurgEntropySimplex, functions.py:326-356).  When H and the m x m factor fit in the shared memory of one SM
- *      (accbpg_dopt_bpg_small_smem_bytes(m, n) != 0; BASELINE configs[0], 80 x 200, does) one persistent CTA runs every
+ *      (accbpg_dopt_bpg_small_smem_bytes(m, n) != 0; BASELINE configs[0], 80 x 200, does) one persistent CTA - or a
+ *      cluster of 2 / 4 CTAs that share the columns of H and exchange through distributed shared memory - runs every
  *      iteration - Gram matrix, factorisation, gradient, Burg-simplex prox, divergence, line-search test, stopping test -
  *      with the control flow of the reference's loop.  d_x: x0 in, last iterate out.  d_F / d_Ls: maxitrs entries each;
  *      d_info[0] = entries written (k + 1), [1] = line-search trials, [2] = last L, [3] = Newton steps of all prox calls,

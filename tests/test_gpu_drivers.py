@@ -356,3 +356,25 @@ def test_bpg_fused_small_is_deterministic(acc):
     a = acc.BPG(f, h, L, x0, maxitrs=200, verbose=False)
     b = acc.BPG(f, h, L, x0, maxitrs=200, verbose=False)
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(np.asarray(a[0]), np.asarray(b[0]))
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+def test_bpg_fused_small_other_cluster_sizes(cluster, golden_traj):
+    """The default splits the columns of H over a 4-CTA cluster; the 1- and 2-CTA forms (ACCBPG_SMALL_CLUSTER, read once
+    per process) run the golden 80 x 200 trajectory in a subprocess."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    from conftest import ROOT
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import accbpg_and_fw_b200 as acc; "
+            "f, h, L, x0 = acc.D_opt_design(80, 200, randseed=10); "
+            "x, F, Ls, T = acc.BPG(f, h, L, x0, maxitrs=1000, linesearch=True, ls_ratio=1.2, verbose=False); "
+            "np.savez(sys.argv[1], F=F, Ls=Ls)" % ROOT)
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "r.npz")
+        env = dict(os.environ, ACCBPG_SMALL_CLUSTER=str(cluster))
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=300)
+        r = np.load(out)
+        assert ferr(r["F"], golden_traj["bpg_ls_F"]) <= FTOL
+        assert np.array_equal(r["Ls"], golden_traj["bpg_ls_Ls"])
