@@ -234,8 +234,13 @@ __device__ __forceinline__ void small_diag_tile(SmallCtx& c, int j0) {
         if (c.lane == cc && live) { c.dv[j0 + cc] = d; c.rinv[j0 + cc] = r; }
         if (c.lane < 8 && i > cc) { t[cc] = l; T[(size_t)i * lda + cc] = l; }
     }
-    __syncwarp();
-    if (c.lane < 8) {                                   // X = Lt_diag^-1, column `lane`
+}
+
+// inverse X of the unit lower 8 x 8 tile at (j0, j0) -> Xd (lanes 0..7 of the calling warp, a column each).  Only the
+// gradient's forward substitution needs it, so it runs off the factorisation's critical path.
+__device__ __forceinline__ void small_tile_inverse(const SmallCtx& c, int j0) {
+    const double* T = c.A + (size_t)j0 * c.lda + j0;
+    if (c.lane < 8) {
         const int cc = c.lane;
         double xcol[8];
 #pragma unroll
@@ -244,11 +249,34 @@ __device__ __forceinline__ void small_diag_tile(SmallCtx& c, int j0) {
         for (int r = 1; r < 8; ++r) {
             double sacc = 0.0;
 #pragma unroll
-            for (int k = 0; k < r; ++k) sacc += T[(size_t)r * lda + k] * xcol[k];
+            for (int k = 0; k < r; ++k) sacc += T[(size_t)r * c.lda + k] * xcol[k];
             if (r > cc) xcol[r] = -sacc;
         }
 #pragma unroll
         for (int r = 0; r < 8; ++r) c.Xd[(size_t)(j0 + r) * 12 + cc] = xcol[r];
+    }
+}
+
+// rows below the diagonal tile of panel p, a lane per row: C[i, :] Lt_diag^T = A[i, panel] by substitution over the eight
+// columns (C = Lt D, the unscaled panel -> Cp), Lt[i, :] = C[i, :] D^-1 -> A.  Needs the eliminated tile, not its inverse.
+__device__ __forceinline__ void small_panel_rows(const SmallCtx& c, int j0, int row) {
+    const double* T = c.A + (size_t)j0 * c.lda + j0;
+    double* ar = c.A + (size_t)row * c.lda + j0;
+    double t[8];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(ar + k);
+        t[k] = v.x; t[k + 1] = v.y;
+    }
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+#pragma unroll
+        for (int q = 0; q < k; ++q) t[k] -= t[q] * T[(size_t)k * c.lda + q];
+    double* cq = c.Cp + (size_t)row * 12;
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        *reinterpret_cast<double2*>(cq + k) = make_double2(t[k], t[k + 1]);
+        *reinterpret_cast<double2*>(ar + k) = make_double2(t[k] * c.rinv[j0 + k], t[k + 1] * c.rinv[j0 + k + 1]);
     }
 }
 
@@ -277,21 +305,16 @@ __device__ __forceinline__ double small_factor(SmallCtx& c, bool& bad) {
     { const long long now = clock64(); c.tf0 += now - tq; tq = now; }
     for (int p = 0; p < npan; ++p) {
         const int j0 = 8 * p;
-        // panel: row tiles I > p
-        for (int I = p + 1 + c.warp; I < ntl; I += SM_WARPS) {
-            const double* ap = A + (size_t)(I * 8 + c.g) * lda + j0 + c.t;
-            const double* xp = c.Xd + (size_t)(j0 + c.g) * 12 + c.t;          // B[k][n] = X[n][k]
-            double c0 = 0.0, c1 = 0.0;
-            const double a0 = ap[0], a1 = ap[4];
-            dmma884(c0, c1, a0, xp[0]);
-            dmma884(c0, c1, a1, xp[4]);
-            __syncwarp();                               // every lane has read its fragment of A[I, panel]
-            double* cq = Cp + (size_t)(I * 8 + c.g) * 12 + 2 * c.t;
-            cq[0] = c0;
-            cq[1] = c1;
-            double* lq = A + (size_t)(I * 8 + c.g) * lda + j0 + 2 * c.t;
-            lq[0] = c0 * c.rinv[j0 + 2 * c.t];
-            lq[1] = c1 * c.rinv[j0 + 2 * c.t + 1];
+        // panel: the rows below the diagonal tile, a lane per row (warps 0..); one more warp inverts the tile meanwhile
+        {
+            const int rows = MP - (j0 + 8);
+            const int pw = (rows + 31) >> 5;            // warps that hold rows
+            if (c.warp < pw) {
+                const int row = j0 + 8 + c.tid;
+                if (row < MP) small_panel_rows(c, j0, row);
+            } else if (c.warp == pw) {
+                small_tile_inverse(c, j0);
+            }
         }
         const int nt = ntl - (p + 1);
         if (nt <= 0) break;

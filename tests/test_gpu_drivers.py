@@ -321,9 +321,12 @@ def test_bpg_fused_small_matches_operator_path(acc, m, n, seed):
             config.fused_small = False
             x2, F2, L2, T2 = acc.BPG(f, h, L, x0, maxitrs=300, verbose=False, **kw)
             assert T1.shape == F1.shape and np.all(np.diff(T1) >= 0)
-            # the default stopping test |F_k - F_k-1| < 1e-14 fires at rounding level: the two runs may stop an iteration apart
+            # the default stopping test |F_k - F_k-1| < 1e-14 fires at rounding level: once F has converged to the last
+            # bits the two runs stop at different (noise-determined) iterations; before that they have the same length
             k = min(len(F1), len(F2))
-            assert abs(len(F1) - len(F2)) <= 2 and k >= 10, (len(F1), len(F2))
+            assert k >= 10, (len(F1), len(F2))
+            if len(F1) != len(F2):
+                assert abs(F1[k - 1] - F1[k - 2]) <= 1e-12 * abs(F1[k - 1]), (len(F1), len(F2))
             assert ferr(F1[:k], F2[:k]) <= 1e-10, (kw, ferr(F1[:k], F2[:k]))
             # once F moves by less than 1e-10 |F| per iteration the line-search test compares rounding noise: L_k is
             # compared up to there
