@@ -88,6 +88,11 @@ struct ProfScope {
 
 // defined in dopt.cu: byte offset of Linv (mp x mp, zero padded) inside the dopt workspace
 size_t dopt_linv_offset(int m, int64_t n, int sm_count, int* mp_out);
+// defined in dopt.cu: 2-D FP64 tensor map (no swizzle) over a row-major matrix; `out` points to a CUtensorMap
+bool encode_tmap_f64_2d(void* out, const double* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols,
+                        uint32_t box_rows);
+bool encode_tmap_f64_3d(void* out, const double* base, uint64_t cols, uint64_t rows, uint64_t groups, uint64_t ld,
+                        uint32_t box_cols, uint32_t box_rows, uint32_t box_groups);
 
 inline int grid_for(const Ctx* c, int64_t n, int threads, int items_per_thread, int blocks_per_sm) {
     int64_t per_block = (int64_t)threads * items_per_thread;

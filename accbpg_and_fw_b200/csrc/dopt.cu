@@ -1052,6 +1052,37 @@ static bool syrk_tma_enabled() {
     return v == 1;
 }
 
+// 2-D FP64 tensor map (no swizzle, zero fill outside) over a row-major matrix with `cols` columns, `rows` rows and leading
+// dimension `ld`, box = box_cols x box_rows; for the other translation units (fw.cu).  `out` points to a CUtensorMap.
+bool encode_tmap_f64_2d(void* out, const double* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols,
+                        uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || !aligned16(base) || (ld % 2) != 0 || (box_cols % 2) != 0 || box_cols > 256 || box_rows > 256) return false;
+    cuuint64_t dim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t str[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t one[2] = {1, 1};
+    return fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dim, str, box, one,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// the same matrix seen as `groups` row groups of `rows` rows each (row g * rows + r of the matrix): one 3-D box moves
+// box_rows rows of every group.  Only valid when groups * rows rows exist.
+bool encode_tmap_f64_3d(void* out, const double* base, uint64_t cols, uint64_t rows, uint64_t groups, uint64_t ld,
+                        uint32_t box_cols, uint32_t box_rows, uint32_t box_groups) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || !aligned16(base) || (ld % 2) != 0 || (box_cols % 2) != 0 || box_cols > 256 || box_rows > 256 || box_groups > 256)
+        return false;
+    cuuint64_t dim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)groups};
+    cuuint64_t str[2] = {(cuuint64_t)ld * 8, (cuuint64_t)rows * ld * 8};
+    cuuint32_t box[3] = {box_cols, box_rows, box_groups};
+    cuuint32_t one[3] = {1, 1, 1};
+    return fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dim, str, box, one,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 size_t dopt_linv_offset(int m, int64_t n, int sm_count, int* mp_out) {
     DoptPlan pl = make_plan(m, n, sm_count);
     if (mp_out) *mp_out = pl.mp;

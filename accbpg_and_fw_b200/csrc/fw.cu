@@ -11,6 +11,7 @@
 // thousands of iterations (tests/test_fw_*.py).
 // Compiled with -fmad=false: the step-size formulas round as in NumPy.
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include "common.cuh"
 
 namespace accbpg {
@@ -149,6 +150,11 @@ struct FwParams {
     int64_t col_offset;       // global index of local column 0
     int sharded;              // decide: the chosen column may live on another rank (then v <- 0 here)
     int reverse;              // pass kernel: walk the column blocks from the end
+    int dbg;                  // fw_pass_ring_kernel: write timing stamps (experiment)
+    int ring_3d;              // fw_pass_ring_kernel: the tensor map is 3-D (columns, rows of a group, row groups)
+    int ring_stages;          // fw_pass_ring_kernel: stages of the shared-memory ring (0: that kernel is not used)
+    int early;                // pass kernel: rows of V fetched before the dependency wait (registers: the first batch; L2:
+                              // `early - FWP_UNROLL` more rows); 0 = nothing is touched before the wait
 };
 
 // The decision of iteration p.k from the merged candidates (thread 0 of the last CTA), then the gather of the chosen
@@ -345,12 +351,16 @@ __global__ void __launch_bounds__(FW_THREADS) fw_select_kernel(FwParams p) {
     fw_select_tail(p, cd, blockIdx.x, gridDim.x, sh_c, &sh_last, &sh_go, &sh_idx);
 }
 
+__device__ unsigned long long g_fwr_dbg[512 * 8];   // timing experiment (ACCBPG_FW_DBG=4)
+
 // u = Hinv v (warp per row)            D_opt_alg.py:78 / :165 / :174
 __global__ void __launch_bounds__(256) fw_hv_kernel(const double* __restrict__ Hinv, int m, const double* __restrict__ v,
                                                     double* __restrict__ u, const double* ctrl,
                                                     const unsigned long long* col_flag, unsigned long long epoch) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // the dependent pass may become resident while the previous pass drains: it fetches rows of V (which never change)
+    // before its own wait, and that wait returns only when this grid - hence everything before it - has completed
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (ld_cg(&ctrl[C_STOP]) != 0.0) return;
     if (col_flag) {                          // peer memory: v arrives from the rank that owns the chosen column
         if (threadIdx.x == 0) peer_flag_wait(col_flag, epoch);
@@ -384,11 +394,35 @@ __global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(FwParams p) {
     __shared__ bool sh_last;
     __shared__ int sh_go;
     __shared__ long long sh_idx;
+    // ---- before the dependency wait: only V (constant for the whole solve) and the launch parameters are touched.
+    // Launched programmatically behind u = Hinv v, this CTA can be resident while the previous pass drains and takes its
+    // decision; the first rows of its columns go to registers and the next ones are pulled into L2 meanwhile.
+    const int m = p.m;
+    const int blk = (int)blockIdx.x - p.nr1;
+    const int cb = p.reverse ? (p.nblk - 1 - blk) : blk;
+    const int rg = threadIdx.x >> 6, ct = threadIdx.x & 63;
+    const int rows_per = (m + 3) / 4;
+    const int r0 = rg * rows_per, r1 = min(m, r0 + rows_per);
+    const int64_t j = (int64_t)cb * p.width + ct * 2;
+    const bool owns = blk >= 0 && (ct * 2 < p.width) && (j < p.n);
+    const bool pre = VEC2 && p.early > 0 && owns && (j + 1 < p.n) && (r0 + FWP_UNROLL <= r1);
+    double2 a0[FWP_UNROLL];
+    if (pre) {
+        const double* col = p.V + j;
+#pragma unroll
+        for (int q = 0; q < FWP_UNROLL; ++q)
+            asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                         : "=d"(a0[q].x), "=d"(a0[q].y) : "l"(col + (int64_t)(r0 + q) * p.ldv));
+        if ((ct & 3) == 0) {                                 // one request per 64 bytes of a row
+            const int rl = min(r1, r0 + p.early);
+            for (int r = r0 + FWP_UNROLL; r < rl; ++r)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(col + (int64_t)r * p.ldv));
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (ld_cg(&p.ctrl[C_STOP]) != 0.0) return;               // uniform over the whole grid
     const double cs = ld_cg(&p.ctrl[C_CS]), den = ld_cg(&p.ctrl[C_DEN]);
-    const int m = p.m;
     if ((int)blockIdx.x < p.nr1) {                           // Hinv <- (Hinv - cs u u^T)/den     D_opt_alg.py:79 / :166 / :175
         const int64_t total = (int64_t)m * m;
         const int64_t stride = (int64_t)p.nr1 * blockDim.x;
@@ -401,18 +435,20 @@ __global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(FwParams p) {
     }
     for (int r = threadIdx.x; r < m; r += blockDim.x) us[r] = __ldcg(p.u + r);
     __syncthreads();
-    const int blk = (int)blockIdx.x - p.nr1;
-    const int cb = p.reverse ? (p.nblk - 1 - blk) : blk;
-    const int rg = threadIdx.x >> 6, ct = threadIdx.x & 63;
-    const int rows_per = (m + 3) / 4;
-    const int r0 = rg * rows_per, r1 = min(m, r0 + rows_per);
-    const int64_t j = (int64_t)cb * p.width + ct * 2;
-    const bool owns = (ct * 2 < p.width) && (j < p.n);
     double s0 = 0.0, s1 = 0.0;
     if (owns) {
         const double* col = p.V + j;
         int r = r0;
         if (VEC2 && j + 1 < p.n) {
+            if (pre) {                                       // the batch fetched before the wait: same rows, same order
+#pragma unroll
+                for (int q = 0; q < FWP_UNROLL; ++q) {
+                    double uq = us[r + q];
+                    s0 += uq * a0[q].x;
+                    s1 += uq * a0[q].y;
+                }
+                r += FWP_UNROLL;
+            }
             for (; r + FWP_UNROLL <= r1; r += FWP_UNROLL) {
                 double2 a[FWP_UNROLL];
 #pragma unroll
@@ -478,6 +514,222 @@ __global__ void __launch_bounds__(FWP_THREADS) fw_pass_kernel(FwParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// The pass as one CTA per SM fed by a bulk-copy ring (the default when V is 16-byte aligned with even n and ldv).
+// A CTA owns the column blocks b = blockIdx.x, blockIdx.x + G, ...; a producer warp streams their rows into a shared
+// memory ring (one 2-D tensor copy per row group: a stage holds FWR_ROWS rows of each of the four row groups; single
+// row copies issued per lane serialise in the TMA unit and reach 3 TB/s only),
+// eight consuming warps form p_j = u^T v_j from the ring with the summation order of fw_pass_kernel (four row groups,
+// rows in order, groups merged ((0+1)+2)+3), so w, x and the vertex sequence are bit-identical.  Bytes in flight are
+// bounded by shared memory (6 x 32 KB per SM) instead of registers, which keeps HBM busy through the tail of the pass,
+// and the ring is filled BEFORE the dependency wait: launched programmatically behind u = Hinv v (which releases its
+// dependents before its own wait), a CTA becomes resident as soon as the previous pass leaves its SM and pulls the
+// first 192 KB of its columns while that pass drains, takes its decision and u = Hinv v is formed (V never changes).
+// The rank-one update of Hinv is shared by all CTAs (a grid-stride slice each, before the first stage is consumed).
+constexpr int FWR_ROWS = 8;                                  // rows per row group and stage (one tensor box)
+constexpr int FWR_BOX_BYTES = FWR_ROWS * FWP_COLS * 8;       // bytes reserved per box (rows packed at width * 8 bytes)
+constexpr int FWR_STAGE_BYTES = 4 * FWR_BOX_BYTES;           // 32 KB
+constexpr int FWR_MAX_STAGES = 6;
+constexpr int FWR_THREADS = FWP_THREADS + 64;                // eight consuming warps, the producer warp, the Hinv warp
+constexpr int FWR_STATIC_SMEM = 12 * 1024;                   // part, records, barriers (upper bound used by the host)
+
+__device__ __forceinline__ void fwr_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fwr_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fwr_mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fwr_mbar_wait(uint32_t bar, uint32_t parity) {      // bounded: a protocol error traps
+    uint32_t ok = 0;
+    for (int spin = 0; spin < (1 << 24); ++spin) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void fwr_tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fwr_tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+// timing experiment (ACCBPG_FW_DBG=4, tools/exp_s2.py stamps): globaltimer stamps of the last pass, per CTA
+__device__ __forceinline__ void fwr_stamp(int on, int slot) {      // on: 1 = first stamped pass, 2 = the one after it
+    if (on) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        g_fwr_dbg[((on - 1) * 256 + blockIdx.x) * 8 + slot] = ns;
+    }
+}
+
+__global__ void __launch_bounds__(FWR_THREADS, 1) fw_pass_ring_kernel(FwParams p, const __grid_constant__ CUtensorMap tmV) {
+    extern __shared__ __align__(128) unsigned char fwr_raw[];      // ring [S][4][FWR_BOX_BYTES], then u (m doubles)
+    __shared__ double part[2][4][FWP_COLS];
+    __shared__ FwCand sh_c[32];
+    __shared__ __align__(8) unsigned long long bar_mem[2 * FWR_MAX_STAGES];
+    __shared__ bool sh_last;
+    __shared__ int sh_go;
+    __shared__ long long sh_idx;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = p.m, S = p.ring_stages, G = (int)gridDim.x;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(fwr_raw);
+    double* us = reinterpret_cast<double*>(fwr_raw + (size_t)S * FWR_STAGE_BYTES);
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(bar_mem);
+    const int rows_per = (m + 3) / 4;
+    const int chunks = (rows_per + FWR_ROWS - 1) / FWR_ROWS;          // stages per column block
+    const int nmine = ((int)blockIdx.x < p.nblk) ? (p.nblk - 1 - (int)blockIdx.x) / G + 1 : 0;
+    const int total = nmine * chunks;
+    const int dbg = (p.dbg && tid == 0 && (p.k == 101 || p.k == 102)) ? p.k - 100 : 0;
+    fwr_stamp(dbg, 0);
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            fwr_mbar_init(bars + 8 * s, 1);                            // full: the producer's arrive.expect_tx
+            fwr_mbar_init(bars + 8 * (FWR_MAX_STAGES + s), FWP_THREADS / 32);   // empty: one arrival per consuming warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    FwCand cd;
+    fw_cand_init(cd);
+    if (warp == FWP_THREADS / 32) {
+        // ---- producer warp: lane 0 issues the four boxes of a stage (rows beyond a row group's end - the last box of a
+        // group when rows_per is not a multiple of FWR_ROWS - and columns beyond n are loaded or zero-filled and ignored)
+        const uint32_t stage_tx = 4u * FWR_ROWS * (uint32_t)p.width * 8u;
+        const uint32_t box_pitch = FWR_ROWS * (uint32_t)p.width * 8u;      // boxes packed as the 3-D copy lays them out
+        auto issue = [&](int c) {
+            if (lane != 0) return;
+            const int st = c % S;
+            const int bi = c / chunks, ch = c - bi * chunks;
+            const int b = (int)blockIdx.x + bi * G;
+            const int cb = p.reverse ? (p.nblk - 1 - b) : b;
+            const int j0 = cb * p.width;
+            if (c >= S) fwr_mbar_wait(bars + 8 * (FWR_MAX_STAGES + st), ((c / S) + 1) & 1);
+            fwr_mbar_expect(bars + 8 * st, stage_tx);
+            if (p.ring_3d) {                                 // m = 4 rows_per: one box over (columns, rows, row groups)
+                fwr_tma_load_3d(ring + st * FWR_STAGE_BYTES, &tmV, j0, ch * FWR_ROWS, 0, bars + 8 * st);
+            } else {
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4)
+                    fwr_tma_load_2d(ring + st * FWR_STAGE_BYTES + g4 * box_pitch, &tmV, j0, g4 * rows_per + ch * FWR_ROWS,
+                                    bars + 8 * st);
+            }
+        };
+        int c = 0;
+        if (p.early > 0) {                                   // V only: nothing here depends on the kernels in front
+            const int pre = total < S ? total : S;
+            for (; c < pre; ++c) issue(c);
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (ld_cg(&p.ctrl[C_STOP]) != 0.0) {                 // uniform over the grid: let the copies in flight land, then leave
+            if (lane == 0)
+                for (int q = 0; q < c; ++q) fwr_mbar_wait(bars + 8 * q, 0);
+            return;
+        }
+        for (; c < total; ++c) issue(c);
+    } else if (warp == FWP_THREADS / 32 + 1) {
+        // ---- Hinv <- (Hinv - cs u u^T)/den  (D_opt_alg.py:79 / :166 / :175): a grid-stride slice per CTA, off the
+        // consumers' path; eight independent elements in flight per lane
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (ld_cg(&p.ctrl[C_STOP]) != 0.0) return;
+        const double cs = ld_cg(&p.ctrl[C_CS]), den = ld_cg(&p.ctrl[C_DEN]);
+        const unsigned tot = (unsigned)m * (unsigned)m, um = (unsigned)m;      // m <= 20480 here (u fits shared memory)
+        const unsigned stride = (unsigned)G * 32u;
+        for (unsigned e0 = blockIdx.x * 32u + lane; e0 < tot; e0 += 8u * stride) {
+            double h[8], o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned e = e0 + q * stride;
+                if (e < tot) {
+                    const unsigned r = e / um, cc = e - r * um;
+                    h[q] = __ldcg(p.Hinv + e);
+                    o[q] = __ldcg(p.u + r) * __ldcg(p.u + cc);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned e = e0 + q * stride;
+                if (e < tot) p.Hinv[e] = (h[q] - cs * o[q]) / den;
+            }
+        }
+    } else {
+        // ---- consuming warps
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        fwr_stamp(dbg, 1);
+        if (ld_cg(&p.ctrl[C_STOP]) != 0.0) return;
+        const double cs = ld_cg(&p.ctrl[C_CS]), den = ld_cg(&p.ctrl[C_DEN]);
+        for (int r = tid; r < m; r += FWP_THREADS) us[r] = __ldcg(p.u + r);
+        asm volatile("bar.sync 1, %0;" ::"n"(FWP_THREADS) : "memory");
+        const int rg = tid >> 6, ct = tid & 63;
+        const int r0 = rg * rows_per, r1 = min(m, r0 + rows_per);
+        const double thr = p.away ? 1.0e-8 : 0.0;
+        const int64_t idx = (int64_t)ld_cg(&p.ctrl[C_IDX]);
+        const double tsign = ld_cg(&p.ctrl[C_TSIGN]);
+        const uint32_t seg = (uint32_t)p.width * 8u;         // row pitch inside a box
+        int c = 0;
+        for (int bi = 0; bi < nmine; ++bi) {
+            const int b = (int)blockIdx.x + bi * G;
+            const int cb = p.reverse ? (p.nblk - 1 - b) : b;
+            const int64_t j = (int64_t)cb * p.width + ct * 2;
+            const bool owns = (ct * 2 < p.width) && (j < p.n);
+            double s0 = 0.0, s1 = 0.0;
+            for (int ch = 0; ch < chunks; ++ch, ++c) {
+                const int st = c % S;
+                fwr_mbar_wait(bars + 8 * st, (c / S) & 1);
+                if (c == 0) fwr_stamp(dbg, 2);
+                if (owns) {
+                    const uint32_t base = ring + st * FWR_STAGE_BYTES + rg * (FWR_ROWS * seg) + ct * 16;
+                    const int rb = r0 + ch * FWR_ROWS;
+#pragma unroll
+                    for (int q = 0; q < FWR_ROWS; ++q) {
+                        if (rb + q < r1) {
+                            double ax, ay;
+                            asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(ax), "=d"(ay) : "r"(base + q * seg));
+                            const double uq = us[rb + q];
+                            s0 += uq * ax;
+                            s1 += uq * ay;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) fwr_mbar_arrive(bars + 8 * (FWR_MAX_STAGES + st));
+            }
+            const int buf = bi & 1;
+            part[buf][rg][2 * ct] = s0;
+            part[buf][rg][2 * ct + 1] = s1;
+            asm volatile("bar.sync 1, %0;" ::"n"(FWP_THREADS) : "memory");
+            if (rg == 0 && owns) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (j + e < p.n) {
+                        const double pj = ((part[buf][0][2 * ct + e] + part[buf][1][2 * ct + e]) + part[buf][2][2 * ct + e]) +
+                                          part[buf][3][2 * ct + e];
+                        const double wn = (p.w[j + e] - cs * (pj * pj)) / den;
+                        double xn = p.x[j + e] * den;
+                        if (j + e + p.col_offset == idx) xn = xn + tsign;
+                        p.w[j + e] = wn;
+                        p.x[j + e] = xn;
+                        fw_cand_add(cd, wn, xn, j + e + p.col_offset, thr);
+                    }
+                }
+            }
+        }
+    }
+    fwr_stamp(dbg, 3);
+    if (!p.decide) return;
+    fw_select_tail(p, cd, (int)blockIdx.x, G, sh_c, &sh_last, &sh_go, &sh_idx);
+    fwr_stamp(dbg, 4);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // The same loop as ONE persistent launch per batch of iterations (one GPU): one CTA per SM owns a fixed block of columns
 // of V for the whole batch and keeps part of it in shared memory, so an iteration reads less than all of V from HBM and
 // costs no kernel launches.  Per iteration k (the leader is CTA 0):
@@ -525,6 +777,11 @@ __device__ __forceinline__ void fwq_wait(const unsigned long long* p, unsigned l
             else if (now - t0 > 4000000000ULL) __trap();
         }
     }
+}
+__device__ __forceinline__ unsigned long long fwq_ld_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void fwq_post(unsigned long long* p, unsigned long long token) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(token) : "memory");
@@ -881,6 +1138,350 @@ __global__ void __launch_bounds__(FWQ_THREADS, 1) fw_persistent_kernel(FwParams 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The persistent loop with the pass fed by the tensor-copy ring of fw_pass_ring_kernel (the default on one GPU when the
+// operands allow it).  Measured on the two-launch chain at 500 x 50000 (globaltimer stamps, tools/exp_s2.py stamps): the
+// ring streams the 200 MB of V in 29.6 us (6.8 TB/s, the copy roof), but an iteration takes 53 us because the decision
+// tail (13.5 us after the last CTA has finished streaming) and the u = Hinv v launch (8.6 us between the decision and the
+// next pass) are serial.  Here nothing is launched between iterations:
+//   records   every CTA reads all G selection records itself (one store -> poll hop), merges them and takes the
+//             decision of iteration k on its own copy of the log-det accumulator (CTA 0 writes the history entry and the
+//             control block), then gathers the chosen column
+//   u         rows cta + i G of Hinv times the column (warp per row), delivered as (value, token) words every CTA collects
+//   pass      a CTA owns q column blocks of W columns; warps 0-7 consume the ring (row groups and summation order of
+//             fw_pass_kernel: bit-identical w, x, vertex sequence), lane 0 of warp 8 feeds it and, towards the end of
+//             the pass, already issues the first stages of the NEXT iteration (V never changes), which land during the
+//             exchanges; warps 9-15 apply the rank-one update to the own rows of Hinv meanwhile
+//   record    of the updated columns, for the next decision
+constexpr int FWS_THREADS = 512;
+constexpr int FWS_CONS = 256;                           // consuming threads (warps 0-7)
+
+__device__ __forceinline__ void fwq_read_record(const double* src, unsigned long long token, int sleep_ns, FwCand& o) {
+    double f8[8];
+    unsigned done = 0;
+    unsigned long long t0 = 0;
+    unsigned spin = 0;
+    while (done != 0xffu) {                              // eight loads in flight; a word counts once it carries the token
+        unsigned long long v[8], tk[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (!(done & (1u << e)))
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v[e]), "=l"(tk[e]) : "l"(src + 2 * e) : "memory");
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (!(done & (1u << e)) && tk[e] == token) { f8[e] = __longlong_as_double((long long)v[e]); done |= 1u << e; }
+        if (done != 0xffu) {
+            __nanosleep(sleep_ns);
+            if ((++spin & 0x3ffu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ULL) __trap();
+            }
+        }
+    }
+    o.amax = f8[0]; o.imax = __double_as_longlong(f8[1]);
+    o.smin = f8[2]; o.imin = __double_as_longlong(f8[3]); o.xmin = f8[4];
+    o.fmask = __double_as_longlong(f8[5]); o.wmask = f8[6]; o.xmask = f8[7];
+}
+
+__global__ void __launch_bounds__(FWS_THREADS, 1)
+fw_persist_ring_kernel(FwParams p, FwPersist q, const __grid_constant__ CUtensorMap tmV) {
+    extern __shared__ __align__(128) unsigned char fws_raw[];      // ring [S][32 KB], then u, v, second v (mpad each)
+    __shared__ double part[2][4][FWP_COLS];
+    __shared__ FwCand sh_c[32];
+    __shared__ FwCand sh_merged;
+    __shared__ FwDec sh_dec;
+    __shared__ double sh_logdet[2];
+    __shared__ __align__(8) unsigned long long bar_mem[2 * FWR_MAX_STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int m = p.m, S = p.ring_stages, G = q.G, cta = blockIdx.x;
+    const int mpad = (m + 1) / 2 * 2;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(fws_raw);
+    double* us = reinterpret_cast<double*>(fws_raw + (size_t)S * FWR_STAGE_BYTES);
+    double* vs = us + mpad;                             // the chosen column
+    double* vs2 = vs + mpad;                            // the other candidate (both are fetched while thread 0 decides)
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(bar_mem);
+    if (ld_cg(&p.ctrl[C_STOP]) != 0.0) return;          // stopped in an earlier batch: uniform over the grid
+    if (tid == 0) {
+        sh_logdet[0] = ld_cg(&p.ctrl[C_LOGDET_HI]); sh_logdet[1] = ld_cg(&p.ctrl[C_LOGDET_LO]);
+        for (int s = 0; s < S; ++s) {
+            fwr_mbar_init(bars + 8 * s, 1);
+            fwr_mbar_init(bars + 8 * (FWR_MAX_STAGES + s), FWS_CONS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // column blocks cta, cta + G, ... of W columns each: at any moment the CTAs read neighbouring segments of the same rows
+    // (contiguous strips per CTA scatter the requests over DRAM pages: 43 us per pass against 30)
+    const int W = p.width;
+    const int nsub = (cta < p.nblk) ? (p.nblk - 1 - cta) / G + 1 : 0;
+    const int rows_per = (m + 3) / 4;
+    const int chunks = (rows_per + FWR_ROWS - 1) / FWR_ROWS;
+    const int per_it = nsub * chunks;                    // stages per iteration
+    const double thr = p.away ? 1.0e-8 : 0.0;
+    const int rg = (tid & 255) >> 6, ct = tid & 63;
+    const int r0 = rg * rows_per, r1 = min(m, r0 + rows_per);
+    const int nown = cta < m ? (m - cta + G - 1) / G : 0;      // rows of Hinv / entries of u this CTA owns: cta + i G
+    const uint32_t seg = (uint32_t)W * 8u;
+    const bool producer = (tid == FWS_CONS);
+    // ---- producer state (one thread): stages issued over the whole launch, kept as (slot, use count of the slot, position
+    //      inside the iteration) so that no division sits on the issue path
+    // Odd iterations walk the column blocks in the opposite order: what the previous pass read last - still in the
+    // 126 MB L2 - is read first (a pass in the same order every time finds nothing of a 200 MB V left).
+    int pc = 0, p_st = 0, p_use = 0, p_sb = 0, p_ch = 0, p_rev = q.k_start & 1;
+    const uint32_t stage_tx = 4u * FWR_ROWS * seg;
+    auto issue = [&]() {
+        const int j0 = (cta + (p_rev ? nsub - 1 - p_sb : p_sb) * G) * W;
+        if (p_use > 0) fwr_mbar_wait(bars + 8 * (FWR_MAX_STAGES + p_st), (uint32_t)((p_use + 1) & 1));
+        fwr_mbar_expect(bars + 8 * p_st, stage_tx);
+        if (p.ring_3d) {
+            fwr_tma_load_3d(ring + p_st * FWR_STAGE_BYTES, &tmV, j0, p_ch * FWR_ROWS, 0, bars + 8 * p_st);
+        } else {
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4)
+                fwr_tma_load_2d(ring + p_st * FWR_STAGE_BYTES + g4 * (FWR_ROWS * seg), &tmV, j0, g4 * rows_per + p_ch * FWR_ROWS,
+                                bars + 8 * p_st);
+        }
+        ++pc;
+        if (++p_st == S) { p_st = 0; ++p_use; }
+        if (++p_ch == chunks) { p_ch = 0; if (++p_sb == nsub) { p_sb = 0; p_rev ^= 1; } }
+    };
+    if (producer && per_it > 0) {                        // the first stages of the first pass
+        const int lim = per_it < S ? per_it : S;
+        while (pc < lim) issue();
+    }
+    int cc_done = 0, c_st = 0, c_ph = 0;                 // stages consumed so far; the consumers' slot and its phase parity
+    // ---- the record of the first decision: candidates of the own columns from (w, x) as they are
+    FwCand cd;
+    fw_cand_init(cd);
+    for (int sb = 0; sb < nsub; ++sb) {
+        const int64_t b0 = (int64_t)(cta + sb * G) * W;
+        const int64_t b1 = b0 + W < p.n ? b0 + W : p.n;
+        for (int64_t j = b0 + tid; j < b1; j += FWS_THREADS) fw_cand_add(cd, p.w[j], p.x[j], j, thr);
+    }
+    // Exchanges.  Records: plain words, then ONE flag word per CTA (compact array, sixteen flags per line) released after
+    // them; a waiting CTA polls the G flags with one warp and a 100 ns back-off, then reads the records once.  Polling the
+    // records themselves - (value, token) words, a line per CTA - costs a hop less but disturbs the CTAs that are still
+    // streaming: their pass ran at 27 GB/s per SM instead of 43 with every thread polling, and still did with one polling
+    // warp and a 300 ns back-off.  u: (value, token) words; everybody waits for u together, nothing streams meanwhile.
+    unsigned long long* frec = q.tok;                    // [2][256]
+    auto wait_flags = [&](const unsigned long long* f, unsigned long long token) {      // warp 0; all G <= 256 flags == token
+        unsigned long long t0 = 0;
+        unsigned spin = 0, done = 0;
+        for (;;) {
+            unsigned long long v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {                // all of a lane's flags in flight at once
+                v[e] = token;
+                if (!(done & (1u << e)) && lane + 32 * e < G)
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[e]) : "l"(f + lane + 32 * e) : "memory");
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (v[e] == token) done |= 1u << e;
+            if (__all_sync(0xffffffffu, done == 0xffu)) break;
+            __nanosleep(100);
+            if ((++spin & 0x3ffu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ULL) __trap();
+            }
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");      // acquire: the records behind the flags
+    };
+    auto deliver_record = [&](int it) {                 // record for the decision of batch iteration `it`
+        fw_cand_block(cd, sh_c);
+        if (tid == 0) {                                  // warp 0 holds the merged record in every lane
+            double* dst = q.recs + ((size_t)(it & 1) * G + cta) * FWQ_REC_DOUBLES;
+            __stcg(dst + 0, cd.amax); __stcg(dst + 1, __longlong_as_double(cd.imax));
+            __stcg(dst + 2, cd.smin); __stcg(dst + 3, __longlong_as_double(cd.imin)); __stcg(dst + 4, cd.xmin);
+            __stcg(dst + 5, __longlong_as_double(cd.fmask)); __stcg(dst + 6, cd.wmask); __stcg(dst + 7, cd.xmask);
+            fwq_post(frec + (size_t)(it & 1) * 256 + cta, q.base + 4ULL * (unsigned long long)it);
+        }
+    };
+    deliver_record(0);
+    unsigned long long ts[8];
+#define FWS_STAMP(i) do { if (q.dbg && tid == 0 && (cta < 2 || q.dbg == 3) && it == 5) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[i])); } while (0)
+    for (int it = 0; it < q.k_count; ++it) {
+        const int par = it & 1;
+        const unsigned long long tokD = q.base + 4ULL * it, tokB = tokD + 2;
+        FWS_STAMP(0);
+        // ---- every CTA gathers the G records itself and merges them (any order: the combines are total orders on
+        //      (value, index)), then takes the decision of iteration k
+        if (wid == 0) wait_flags(frec + (size_t)par * 256, tokD);
+        __syncthreads();
+        fw_cand_init(cd);
+        for (int b = tid; b < G; b += FWS_THREADS) {
+            const double* src = q.recs + ((size_t)par * G + b) * FWQ_REC_DOUBLES;
+            FwCand o;
+            o.amax = __ldcg(src + 0); o.imax = __double_as_longlong(__ldcg(src + 1));
+            o.smin = __ldcg(src + 2); o.imin = __double_as_longlong(__ldcg(src + 3)); o.xmin = __ldcg(src + 4);
+            o.fmask = __double_as_longlong(__ldcg(src + 5)); o.wmask = __ldcg(src + 6); o.xmask = __ldcg(src + 7);
+            fw_cand_merge(cd, o);
+        }
+        fw_cand_block(cd, sh_c);                          // merged record in every lane of warp 0
+        if (wid == 0 && lane == 0) sh_merged = cd;
+        __syncthreads();
+        FWS_STAMP(1);
+        // Thread 0 takes the decision (a few hundred dependent FP64 instructions) while the other warps fetch BOTH columns
+        // the step rule can choose (argmax w, or the away vertex).  (Forming the own rows of u for both candidates under
+        // the decision as well was measured slower: 17.7 k against 19.9 k iterations per second.)
+        {
+            const FwCand mc = sh_merged;
+            long long jm = mc.imin;
+            if (p.away && !(mc.imin != FW_NOIDX && mc.smin < -mc.amax) && mc.fmask < mc.imin) jm = mc.fmask;
+            if (jm == FW_NOIDX) jm = 0;
+            const long long im = mc.imax;
+            if (tid == 0) {
+                FwDec d;
+                d.cs = d.den = d.tsign = 0.0; d.idx = 0; d.go = 0;
+                fwq_decide(p, mc, q.k_start + it, sh_logdet[0], sh_logdet[1], cta == 0, d);
+                sh_dec = d;
+            } else if (tid >= 32) {
+                for (int r = tid - 32; r < 2 * m; r += FWS_THREADS - 32) {
+                    const int rr = r < m ? r : r - m;
+                    const long long col = r < m ? im : jm;
+                    const double val = (col >= 0 && col < p.n) ? __ldg(p.V + (int64_t)rr * p.ldv + col) : 0.0;
+                    if (r < m) vs[rr] = val; else vs2[rr] = val;
+                }
+            }
+        }
+        __syncthreads();
+        if (!sh_dec.go) {                                // the optimality test fired at this iteration: uniform over the grid
+            if (producer) {                              // let the copies in flight land before the CTA gives up its shared memory
+                int st = c_st, ph = c_ph;
+                for (int c = cc_done; c < pc; ++c) {
+                    fwr_mbar_wait(bars + 8 * st, (uint32_t)ph);
+                    if (++st == S) { st = 0; ph ^= 1; }
+                }
+            }
+            return;
+        }
+        const double cs = sh_dec.cs, den = sh_dec.den, tsign = sh_dec.tsign;
+        const int64_t idx = sh_dec.idx;
+        const double* vc = (idx == sh_merged.imax) ? vs : vs2;      // (when both candidates coincide the columns are equal)
+        FWS_STAMP(2);
+        // ---- u_r = Hinv[r,:] v for the own rows (warp per row, summation order of fw_hv_kernel), delivered to every CTA
+        for (int i = wid; i < nown; i += FWS_THREADS / 32) {
+            const int r = cta + i * G;
+            const double* hr = p.Hinv + (size_t)r * m;
+            double sacc = 0.0;
+            for (int cb = 0; cb < m; cb += 256) {         // eight loads in flight per lane
+                double hv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = cb + lane + 32 * e;
+                    hv[e] = c < m ? __ldcg(hr + c) : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = cb + lane + 32 * e;
+                    if (c < m) sacc += hv[e] * vc[c];
+                }
+            }
+            sacc = warp_sum(sacc);
+            if (lane == 0) fwq_st_pair(q.ux + ((size_t)par * m + r) * 2, sacc, tokB);
+        }
+        FWS_STAMP(3);
+        // (value, token) words: one hop; everybody waits here together, so the polling does not disturb a pass
+        for (int r = tid; r < m; r += FWS_THREADS) us[r] = fwq_wait_pair(q.ux + ((size_t)par * m + r) * 2, tokB);
+        __syncthreads();
+        FWS_STAMP(4);
+        fw_cand_init(cd);
+        if (tid < FWS_CONS) {
+            // ---- the pass over the own column blocks
+            int st = c_st, ph = c_ph;
+            const int rev = (q.k_start + it) & 1;
+            for (int sq = 0; sq < nsub; ++sq) {
+                const int sb = rev ? nsub - 1 - sq : sq;
+                const int64_t j = (int64_t)(cta + sb * G) * W + ct * 2;
+                const bool owns = (ct * 2 < W) && (j < p.n);
+                double s0 = 0.0, s1 = 0.0;
+                for (int ch = 0; ch < chunks; ++ch) {
+                    fwr_mbar_wait(bars + 8 * st, (uint32_t)ph);
+                    if (owns) {
+                        const uint32_t base = ring + st * FWR_STAGE_BYTES + rg * (FWR_ROWS * seg) + ct * 16;
+                        const int rb = r0 + ch * FWR_ROWS;
+#pragma unroll
+                        for (int e = 0; e < FWR_ROWS; ++e) {
+                            if (rb + e < r1) {
+                                double ax, ay;
+                                asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(ax), "=d"(ay) : "r"(base + e * seg));
+                                const double uq = us[rb + e];
+                                s0 += uq * ax;
+                                s1 += uq * ay;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) fwr_mbar_arrive(bars + 8 * (FWR_MAX_STAGES + st));
+                    if (++st == S) { st = 0; ph ^= 1; }
+                }
+                const int buf = sq & 1;
+                part[buf][rg][2 * ct] = s0;
+                part[buf][rg][2 * ct + 1] = s1;
+                asm volatile("bar.sync 1, %0;" ::"n"(FWS_CONS) : "memory");
+                if (rg == 0 && owns) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (j + e < p.n) {
+                            const double pj = ((part[buf][0][2 * ct + e] + part[buf][1][2 * ct + e]) + part[buf][2][2 * ct + e]) +
+                                              part[buf][3][2 * ct + e];
+                            const double wn = (p.w[j + e] - cs * (pj * pj)) / den;
+                            double xn = p.x[j + e] * den;
+                            if (j + e == idx) xn = xn + tsign;
+                            p.w[j + e] = wn;
+                            p.x[j + e] = xn;
+                            fw_cand_add(cd, wn, xn, j + e, thr);
+                        }
+                    }
+                }
+            }
+        } else if (producer) {
+            // ---- the rest of this pass, then the first stages of the next one (they land during the exchanges)
+            const int end_it = cc_done + per_it;
+            const int lim = (it + 1 < q.k_count) ? end_it + (per_it < S ? per_it : S) : end_it;
+            while (pc < lim) issue();
+        } else if (wid > FWS_CONS / 32) {
+            // ---- Hinv <- (Hinv - cs u u^T)/den on the own rows (warps 9-15)      D_opt_alg.py:79 / :166 / :175
+            const int ht = tid - (FWS_CONS + 32), hn = FWS_THREADS - FWS_CONS - 32;
+            for (int e0 = ht; e0 < nown * m; e0 += hn * 4) {
+                double hv[4];
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int e = e0 + u4 * hn;
+                    if (e < nown * m) { const int i = e / m, c = e - i * m; hv[u4] = __ldcg(p.Hinv + (size_t)(cta + i * G) * m + c); }
+                }
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int e = e0 + u4 * hn;
+                    if (e < nown * m) {
+                        const int i = e / m, c = e - i * m, r = cta + i * G;
+                        const double o = us[r] * us[c];
+                        p.Hinv[(size_t)r * m + c] = (hv[u4] - cs * o) / den;
+                    }
+                }
+            }
+        }
+        cc_done += per_it;
+        {   // every thread advances its copy of the consumers' ring position by per_it stages
+            const int adv = c_st + per_it;
+            c_ph ^= (adv / S) & 1;
+            c_st = adv % S;
+        }
+        __syncthreads();
+        FWS_STAMP(5);
+        deliver_record(it + 1);
+        FWS_STAMP(6);
+        if (q.dbg == 3 && tid == 0 && it == 5 && q.dbg_buf)
+            for (int i = 0; i < 7; ++i) q.dbg_buf[cta * 8 + i] = ts[i];
+        if (q.dbg == 1 && tid == 0 && cta < 2 && it == 5)
+            printf("fw persistent ring cta %d: records %llu ns, decide + column %llu, u rows %llu, u gather %llu, pass %llu, record %llu | iteration %llu ns\n",
+                   cta, ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], ts[6] - ts[5], ts[6] - ts[0]);
+    }
+}
+
 // Hinv = Linv^T Linv  (setup only; Linv lower triangular, zero padded, leading dimension mp)
 __global__ void __launch_bounds__(256) fw_hinv_kernel(const double* __restrict__ Linv, int m, int mp,
                                                       double* __restrict__ Hinv) {
@@ -935,7 +1536,8 @@ size_t accbpg_fw_workspace_bytes(int m, int64_t n_local) {
     size_t base = accbpg_dopt_workspace_bytes(m, n_local);
     const size_t nparts = (size_t)((n_local + 127) / 128) + 4096;        // selection candidates, one per selecting CTA
     // + the exchange tables of the persistent loop: u parts (2 x m pairs), u (2 x m), records (2 x 256 CTAs x 128 B), tokens
-    return base + 2 * (((size_t)m + 31) / 32 * 32 * 8) + nparts * 64 + 256 + (size_t)6 * m * 8 + 2 * 256 * 128 + 2 * 16 * 128 + 512;
+    return base + 2 * (((size_t)m + 31) / 32 * 32 * 8) + nparts * 64 + 256 + (size_t)6 * m * 8 + 2 * 256 * 128 + 2 * 16 * 128 + 512 +
+           4 * 256 * 8 /* flag words of the ring-fed persistent loop */ + 128;
 }
 
 // D_opt_alg.py:39-45 / :123-129:  M = V diag(x0) V^T, Hinv = M^{-1}, w_j = v_j^T Hinv v_j, log det M
@@ -969,6 +1571,11 @@ struct FwLaunch {
     int sel_grid, hv_grid, nblk, r1_ctas;
     size_t pass_smem;
     bool pass_vec;
+    bool ring_ok;              // the ring-fed kernels can run on this instance (tensor map encoded, shared memory fits)
+    bool use_ring;             // launch chain: fw_pass_ring_kernel (one CTA per SM, tensor-copy ring) instead of fw_pass_kernel
+    CUtensorMap tmV;           // V as a 2-D tensor, box = width columns x FWR_ROWS rows
+    int ring_grid;
+    size_t ring_smem;
     double* persist_mem;       // exchange tables of the persistent loop (inside the workspace)
 };
 
@@ -1015,6 +1622,60 @@ static int fw_prepare(Ctx* c, const double* V, int m, int64_t n, int64_t ldv, in
     p.parts = parts; p.counter = c->d_counter; p.away = away; p.eps = eps; p.nblk = L->nblk; p.nr1 = L->r1_ctas;
     p.k = 0; p.decide = 0; p.reverse = 0; p.cand_out = nullptr; p.col_offset = 0; p.sharded = 0;
     p.peer.world = 0; p.peer.rank = 0;
+    {
+        static int early = -1;                                // ACCBPG_FW_EARLY: rows per row group fetched before the wait
+        if (early < 0) { const char* e = getenv("ACCBPG_FW_EARLY"); early = e ? atoi(e) : 48; if (early < 0) early = 0; }
+        p.early = early;
+        static int ring = -1;                                 // ACCBPG_FW_RING=0: the register-fed pass kernel
+        if (ring < 0) {                                       // the launch chain keeps the register-fed pass unless asked:
+            const char* e = getenv("ACCBPG_FW_RING");         // 19.2 k against 17.7 k iterations per second at 500 x 50000
+            ring = (e && e[0] == '1') ? 1 : 0;
+        }
+        int max_optin = 0;
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+        const long long room = (long long)max_optin - FWR_STATIC_SMEM - (long long)m * 8;
+        int stages = room > 0 ? (int)(room / FWR_STAGE_BYTES) : 0;
+        if (stages > FWR_MAX_STAGES) stages = FWR_MAX_STAGES;
+        static int ring_w = -1;                               // ACCBPG_FW_RING_W: columns per block of the ring kernel
+        if (ring_w < 0) { const char* e = getenv("ACCBPG_FW_RING_W"); ring_w = e ? atoi(e) : 0; }
+        int64_t rw = width;
+        if (ring_w >= 16 && ring_w <= FWP_COLS && ring_w % 2 == 0) rw = ring_w;
+        L->ring_ok = L->pass_vec && (n % 2 == 0) && stages >= 3 && n < (1LL << 31) && !getenv("ACCBPG_FW_L2_MB");
+        p.ring_3d = 0;
+        if (L->ring_ok) {
+            static int no3d = -1;
+            if (no3d < 0) { const char* e = getenv("ACCBPG_FW_RING_3D"); no3d = (e && e[0] == '0') ? 1 : 0; }
+            // a box of FWR_ROWS x rw doubles must keep the 128-byte alignment of the next box when they are packed
+            if (m % 4 == 0 && !no3d && ((FWR_ROWS * rw * 8) % 128 == 0) &&
+                encode_tmap_f64_3d(&L->tmV, V, (uint64_t)n, (uint64_t)(m / 4), 4, (uint64_t)ldv, (uint32_t)rw, FWR_ROWS, 4))
+                p.ring_3d = 1;
+            else if (((FWR_ROWS * rw * 8) % 128 != 0) ||
+                     !encode_tmap_f64_2d(&L->tmV, V, (uint64_t)n, (uint64_t)m, (uint64_t)ldv, (uint32_t)rw, FWR_ROWS))
+                L->ring_ok = false;
+        }
+        L->use_ring = L->ring_ok && ring;
+        if (L->ring_ok && rw != width) {                       // (experiment) block width of the ring kernels
+            L->nblk = (int)((n + rw - 1) / rw);
+            p.nblk = L->nblk;
+            p.width = (int)rw;
+        }
+        p.ring_stages = L->use_ring ? stages : 0;
+        {
+            static int fdbg = -1;
+            if (fdbg < 0) { const char* e = getenv("ACCBPG_FW_DBG"); fdbg = e ? atoi(e) : 0; }
+            p.dbg = fdbg == 4;
+        }
+        L->ring_grid = L->nblk < c->sm_count ? L->nblk : c->sm_count;
+        L->ring_smem = (size_t)stages * FWR_STAGE_BYTES + (size_t)m * 8;
+        if (L->use_ring) {
+            static bool attr_done[kMaxDevices] = {};
+            if (c->device >= 0 && c->device < kMaxDevices && !attr_done[c->device]) {
+                ACCBPG_CUDA(cudaFuncSetAttribute(fw_pass_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 FWR_MAX_STAGES * FWR_STAGE_BYTES + 24 * 1024));
+                attr_done[c->device] = true;
+            }
+        }
+    }
     return ACCBPG_OK;
 }
 
@@ -1064,6 +1725,16 @@ static FwL2 fw_l2_window(const double* V, int m, int64_t ldv) {
     return r;
 }
 
+// one pass launch (either kernel) on the configuration the caller prepared (stream, launch attributes)
+static cudaError_t fw_launch_pass(const FwLaunch& L, cudaLaunchConfig_t cfg, const FwParams& p) {
+    if (L.use_ring) {
+        cfg.gridDim = dim3(L.ring_grid); cfg.blockDim = dim3(FWR_THREADS); cfg.dynamicSmemBytes = L.ring_smem;
+        return cudaLaunchKernelEx(&cfg, fw_pass_ring_kernel, p, L.tmV);
+    }
+    cfg.gridDim = dim3(L.nblk + L.r1_ctas); cfg.blockDim = dim3(FWP_THREADS); cfg.dynamicSmemBytes = L.pass_smem;
+    return cudaLaunchKernelEx(&cfg, L.pass_vec ? fw_pass_kernel<true> : fw_pass_kernel<false>, p);
+}
+
 // run iterations k_start .. k_start+k_count-1 (no-ops after the stop flag is raised):
 //   select+decide(k_start);  then per iteration  u = Hinv v;  pass (+ rank-one update of Hinv, + decision of k+1)
 // Launches are chained with programmatic dependent launch.
@@ -1081,7 +1752,6 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
     int rc = fw_prepare(c, V, m, n, ldv, away, eps, ws, Hinv, x, w, ctrl, hist_F, hist_SP, hist_SN, hist_T, &L);
     if (rc) return rc;
     FwParams& p = L.p;
-    auto pass_fn = L.pass_vec ? fw_pass_kernel<true> : fw_pass_kernel<false>;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1105,15 +1775,78 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
     //      against 19.2 k: its exchanges (records -> merge -> replicas, u all-gather) cost 13 us per iteration and a
     //      statically partitioned CTA streams its strip of V at 3.0-4.9 TB/s only (tried and dropped)
     {
-        static int persist = -1;
-        if (persist < 0) { const char* e = getenv("ACCBPG_FW_PERSIST"); persist = (e && e[0] == '1') ? 1 : 0; }
+        static int persist = -1;                              // unset: ring-fed persistent loop when it can run; 0: launch chain;
+        if (persist < 0) {                                    // 1: a persistent loop in any case (register-fed without the ring)
+            const char* e = getenv("ACCBPG_FW_PERSIST");
+            persist = !e ? 2 : (e[0] == '1' ? 1 : 0);
+        }
         const int G = c->sm_count < 256 ? c->sm_count : 256;
         int64_t per = (n + G - 1) / G;
         per = (per + 1) / 2 * 2;
         const int mpad = (m + 1) / 2 * 2;
+        if (persist && L.ring_ok && !l2.on && m <= 4096) {
+            // the ring-fed form: q column blocks of W = p.width columns per CTA
+            int max_optin = 0;
+            cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+            const long long room = (long long)max_optin - FWR_STATIC_SMEM - 3LL * mpad * 8;
+            int stages = room > 0 ? (int)(room / FWR_STAGE_BYTES) : 0;
+            if (stages > FWR_MAX_STAGES) stages = FWR_MAX_STAGES;
+            if (stages >= 3) {
+                static bool attr_done[kMaxDevices] = {};
+                if (c->device >= 0 && c->device < kMaxDevices && !attr_done[c->device]) {
+                    ACCBPG_CUDA(cudaFuncSetAttribute(fw_persist_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     max_optin - FWR_STATIC_SMEM));
+                    attr_done[c->device] = true;
+                }
+                FwPersist q;
+                q.ux = L.persist_mem;
+                q.recs = q.ux + (size_t)4 * m;
+                q.recs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(q.recs) + 127) / 128 * 128);
+                q.bcast = q.recs + (size_t)2 * 256 * FWQ_REC_DOUBLES;
+                q.tok = reinterpret_cast<unsigned long long*>(
+                    (reinterpret_cast<uintptr_t>(q.bcast + (size_t)2 * FWQ_REPL * FWQ_REC_DOUBLES) + 127) / 128 * 128);
+                static unsigned long long calls_r = 0;
+                q.base = ((++calls_r) << 24) | (1ULL << 62);  // never a token of the other persistent kernel
+                q.G = G; q.k_start = k_start; q.k_count = k_count; q.per = 0; q.rc4 = 0;
+                static int fdbg = -1;
+                if (fdbg < 0) { const char* e = getenv("ACCBPG_FW_DBG"); fdbg = e ? atoi(e) : 0; }
+                q.dbg = (fdbg == 1 || fdbg == 3) ? fdbg : 0;
+                q.dbg_buf = nullptr;
+                static unsigned long long* dbg_dev = nullptr;
+                if (fdbg == 3) {
+                    if (!dbg_dev) cudaMalloc(&dbg_dev, 256 * 8 * 8);
+                    cudaMemsetAsync(dbg_dev, 0, 256 * 8 * 8, s);
+                    q.dbg_buf = dbg_dev;
+                }
+                p.k = k_start; p.decide = 1; p.reverse = 0; p.ring_stages = stages;
+                const size_t smem = (size_t)stages * FWR_STAGE_BYTES + (size_t)3 * mpad * 8;
+                ProfScope ps(P_FW_BATCH, s);
+                fw_persist_ring_kernel<<<G, FWS_THREADS, smem, s>>>(p, q, L.tmV);
+                ACCBPG_LAUNCHED("fw_persist_ring_kernel");
+                if (fdbg == 3 && k_count > 6) {              // timing experiment only: per-CTA stamps of batch iteration 5
+                    static unsigned long long h[256 * 8];
+                    cudaStreamSynchronize(s);
+                    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+                    unsigned long long t0 = ~0ULL;
+                    for (int b = 0; b < G; ++b) if (h[b * 8] && h[b * 8] < t0) t0 = h[b * 8];
+                    const char* nm[7] = {"loop top", "records merged", "decided + column", "own u rows sent", "u gathered", "pass done",
+                                         "record posted"};
+                    for (int i = 0; i < 7; ++i) {
+                        unsigned long long lo = ~0ULL, hi = 0; int amax = 0, amin = 0;
+                        for (int b = 0; b < G; ++b) {
+                            unsigned long long v = h[b * 8 + i] - t0;
+                            if (v < lo) { lo = v; amin = b; }
+                            if (v > hi) { hi = v; amax = b; }
+                        }
+                        fprintf(stderr, "[fw ring dbg] %-18s min %7llu ns (cta %d)  max %7llu ns (cta %d)\n", nm[i], lo, amin, hi, amax);
+                    }
+                }
+                return ACCBPG_OK;
+            }
+        }
         const size_t fixed = ((size_t)2 * mpad + 2 * 4 * FWP_COLS) * sizeof(double);
         const size_t budget = 200 * 1024;
-        if (persist && L.pass_vec && !l2.on && m <= 4096 && per >= 2 && per < (1 << 28) && fixed + 1024 < budget) {
+        if (persist == 1 && L.pass_vec && !l2.on && m <= 4096 && per >= 2 && per < (1 << 28) && fixed + 1024 < budget) {
             const int rows_per = (m + 3) / 4;
             int64_t rc4 = (int64_t)((budget - fixed) / ((size_t)32 * per));
             if (rc4 > rows_per) rc4 = rows_per;
@@ -1178,11 +1911,10 @@ int accbpg_fw_run(void* ctx, void* stream, const double* V, int m, int64_t n, in
         p.k = k + 1;                                        // the tail decides the next iteration ...
         p.decide = (k + 1 < k_start + k_count) ? 1 : 0;     // ... except after the last pass of the batch
         p.reverse = k & 1;
-        cfg.gridDim = dim3(L.nblk + L.r1_ctas); cfg.blockDim = dim3(FWP_THREADS); cfg.dynamicSmemBytes = L.pass_smem;
         cfg.numAttrs = pass_attrs;
         {
             ProfScope ps(P_FW_PASS, s);
-            ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, pass_fn, p));
+            ACCBPG_CUDA(fw_launch_pass(L, cfg, p));
         }
         ACCBPG_LAUNCHED("fw_pass_kernel");
     }
@@ -1243,10 +1975,11 @@ int accbpg_fw_step(void* ctx, void* stream, const double* V, int m, int64_t n_lo
     fw_hv_kernel<<<L.hv_grid, 256, 0, s>>>(Hinv, m, d_vcol, p.u, ctrl, nullptr, 0ULL);
     ACCBPG_LAUNCHED("fw_hv_kernel");
     p.k = k + 1; p.decide = 2; p.reverse = k & 1; p.cand_out = (FwCand*)d_record_out; p.col_offset = col_offset;
-    auto pass_fn = L.pass_vec ? fw_pass_kernel<true> : fw_pass_kernel<false>;
     {
+        cudaLaunchConfig_t cfg = {};
+        cfg.stream = s;
         ProfScope ps(P_FW_PASS, s);
-        pass_fn<<<L.nblk + L.r1_ctas, FWP_THREADS, L.pass_smem, s>>>(p);
+        ACCBPG_CUDA(fw_launch_pass(L, cfg, p));
     }
     ACCBPG_LAUNCHED("fw_pass_kernel");
     return ACCBPG_OK;
@@ -1284,7 +2017,6 @@ int accbpg_fw_run_peer(void* ctx, void* stream, const double* V, int m, int64_t 
     }
     p.peer.rank = rank; p.peer.world = world;
     p.col_offset = col_offset; p.sharded = 1;
-    auto pass_fn = L.pass_vec ? fw_pass_kernel<true> : fw_pass_kernel<false>;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1314,10 +2046,9 @@ int accbpg_fw_run_peer(void* ctx, void* stream, const double* V, int m, int64_t 
         ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, fw_hv_kernel, (const double*)Hinv, m, vcol, p.u, (const double*)ctrl, col_flag, epoch));
         ACCBPG_LAUNCHED("fw_hv_kernel");
         p.k = k + 1; p.decide = 2; p.reverse = k & 1;
-        cfg.gridDim = dim3(L.nblk + L.r1_ctas); cfg.blockDim = dim3(FWP_THREADS); cfg.dynamicSmemBytes = L.pass_smem;
         {
             ProfScope ps(P_FW_PASS, s);
-            ACCBPG_CUDA(cudaLaunchKernelEx(&cfg, pass_fn, p));
+            ACCBPG_CUDA(fw_launch_pass(L, cfg, p));
         }
         ACCBPG_LAUNCHED("fw_pass_kernel");
     }
@@ -1349,6 +2080,11 @@ int accbpg_fw_setup_from_gram(void* ctx, void* stream, const double* V, int m, i
     fw_hinv_kernel<<<grid, 256, 0, s>>>(Linv, m, mp, Hinv);
     ACCBPG_LAUNCHED("fw_hinv_kernel");
     return ACCBPG_OK;
+}
+
+// timing experiment: the stamps of two consecutive fw_pass_ring_kernel launches (8 per CTA, 2 x 256 CTAs at most)
+int accbpg_fw_debug_stamps(unsigned long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_fwr_dbg, sizeof(unsigned long long) * 512 * 8) == cudaSuccess ? 0 : -1;
 }
 
 }  // extern "C"

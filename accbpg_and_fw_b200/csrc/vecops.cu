@@ -363,6 +363,7 @@ constexpr int kBurgMaxG = kMaxBlocks / 4;              // 296 blocks per rank at
 struct BurgX {
     double* tab[kMaxPeerRanks];                        // every rank's table (layout at burgx_round)
     int rank, world;
+    int onehop;                                        // world == 1: every block gathers the block partials itself
     unsigned long long base;                           // token of round r is base + r (unique per call on these tables)
 };
 
@@ -494,27 +495,33 @@ __device__ __forceinline__ void burgx_round(const BurgX& X, int round, double a,
             st_pair(dst + 2, bb, token);
         }
         double ta, tb;
-        if (blockIdx.x == 0) {                         // the leader adds its rank's block partials and tells every rank
+        if (X.world == 1 && X.onehop) {
+            // one rank: every block gathers all block partials itself, in the order the leader would (same lanes, same
+            // shuffle tree, and 0 + t = t in the rank sum: same bits), so a round costs one store -> poll hop, not two
             gather_slots<IS_MIN>(tab + (size_t)par * kBurgMaxG * kBurgSlot, G, token, false, ta, tb);
-            if (lane < X.world) {
-                double* dst = X.tab[lane] + ((size_t)kBurgOffB + par * kMaxPeerRanks + X.rank) * kBurgSlot;
-                st_pair(dst, ta, token);
-                st_pair(dst + 2, tb, token);
+        } else {
+            if (blockIdx.x == 0) {                     // the leader adds its rank's block partials and tells every rank
+                gather_slots<IS_MIN>(tab + (size_t)par * kBurgMaxG * kBurgSlot, G, token, false, ta, tb);
+                if (lane < X.world) {
+                    double* dst = X.tab[lane] + ((size_t)kBurgOffB + par * kMaxPeerRanks + X.rank) * kBurgSlot;
+                    st_pair(dst, ta, token);
+                    st_pair(dst + 2, tb, token);
+                }
             }
-        }
-        // every block (the leader included) waits for the `world` rank sums in its own table and adds them in rank order
-        double va = 0.0, vb = 0.0;
-        if (lane < X.world) {
-            const double* src = tab + ((size_t)kBurgOffB + par * kMaxPeerRanks + lane) * kBurgSlot;
-            va = wait_pair(src, token, sys);
-            vb = wait_pair(src + 2, token, sys);
-        }
-        ta = IS_MIN ? kInf : 0.0;
-        tb = 0.0;
-        for (int r = 0; r < X.world; ++r) {
-            const double ar = __shfl_sync(0xffffffffu, va, r), br = __shfl_sync(0xffffffffu, vb, r);
-            if (IS_MIN) ta = fmin(ta, ar);
-            else { ta += ar; tb += br; }
+            // every block (the leader included) waits for the `world` rank sums in its own table, adds them in rank order
+            double va = 0.0, vb = 0.0;
+            if (lane < X.world) {
+                const double* src = tab + ((size_t)kBurgOffB + par * kMaxPeerRanks + lane) * kBurgSlot;
+                va = wait_pair(src, token, sys);
+                vb = wait_pair(src + 2, token, sys);
+            }
+            ta = IS_MIN ? kInf : 0.0;
+            tb = 0.0;
+            for (int r = 0; r < X.world; ++r) {
+                const double ar = __shfl_sync(0xffffffffu, va, r), br = __shfl_sync(0xffffffffu, vb, r);
+                if (IS_MIN) ta = fmin(ta, ar);
+                else { ta += ar; tb += br; }
+            }
         }
         double* o = sh + flip * 64;                    // the other buffer: nobody reads it before the barrier below
         if (lane == 0) { o[0] = ta; o[1] = tb; }
@@ -984,7 +991,11 @@ int accbpg_burg_prox(void* ctx, void* stream, int64_t n, int kind, double lamda,
     return launch_map(c, s, n, BurgProxF{kind, lamda, L, 4 * lamL, 2 * lamL, y, g, out}, "burg_prox");
 }
 static int burgx_launch(Ctx* c, cudaStream_t s, int64_t n, int64_t width, const double* y, const double* g, double L, double eps,
-                        double* out, double* info, const BurgX& X, const double* gg_in = nullptr) {
+                        double* out, double* info, const BurgX& X0, const double* gg_in = nullptr) {
+    BurgX X = X0;
+    static int onehop = -1;                            // ACCBPG_BURG_ONEHOP=0: the two-level exchange on one rank too
+    if (onehop < 0) { const char* e = getenv("ACCBPG_BURG_ONEHOP"); onehop = (e && e[0] == '0') ? 0 : 1; }
+    X.onehop = onehop;
     // the grid depends on `width` only (the widest slice), so every rank uses the same slot layout
     int64_t want = (width + kBurgThreads - 1) / kBurgThreads;
     static int per_sm_x = 0;                           // co-resident blocks per SM of the exchange-form kernel (all variants)
