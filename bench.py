@@ -475,8 +475,10 @@ def extra_c2(B):
         gbs = 8.0 * m * n / (ms_it * 1e-3) / 1e9
         out["fw_pass_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": B.hbm, "unit": "GB/s", "frac": gbs / B.hbm,
                                    "ms_avg": ms_it, "bytes_per_launch": 8 * m * n, "peak_source": B.hbm_source,
-                                   "kernel": "fw_persistent_kernel (whole iterations, one launch per batch of 64; algorithmic "
-                                             "bytes 8mn per iteration, part of V stays in shared memory)",
+                                   "kernel": "fw_persist_ring_kernel: WHOLE iterations (decision, column gather, u = Hinv v and its "
+                                             "all-gather, rank-one update, pass over V, selection record), one launch per batch "
+                                             "of 64; algorithmic bytes 8mn per iteration.  The pass alone streams V in 31 us = "
+                                             "6.4 TB/s (globaltimer stamps inside the kernel, ACCBPG_FW_DBG=3: DESIGN.md section 11)",
                                    "launches": pb["launches"], "iterations": len(res300[1])}
         out["fw_iteration_ms_avg"] = ms_it
     p = kfw.get("fw_pass_kernel")

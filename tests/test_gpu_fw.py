@@ -172,3 +172,47 @@ def test_sharded_fw_building_blocks_on_one_gpu(acc, away, world):
     assert np.max(np.abs(xfull - xo)) <= 1e-9
     for r in range(1, world):                               # replicated state stays identical
         assert torch.equal(ctrl[r][:15], ctrl[0][:15]) and torch.equal(Hinv[r], Hinv[0])
+
+
+_FW_PATHS_SCRIPT = r"""
+import hashlib, sys, numpy as np
+sys.path.insert(0, {root!r})
+import accbpg_and_fw_b200 as acc
+out = []
+for (m, n, seed, eps, its, batch) in [(200, 5000, 2, 1e-8, 200, 64), (64, 3000, 5, 1e-2, 4000, 32), (10, 40, 4, 1e-3, 5000, 16)]:
+    np.random.seed(seed)
+    V = np.random.randn(m, n)
+    x0 = np.ones(n) / n
+    for fn in (acc.D_opt_FW_away, acc.D_opt_FW):
+        x, F, SP, SN, T = fn(V, x0, eps, its, verbose=False, batch=batch)
+        h = hashlib.sha256()
+        for a in (x, F, SP, SN):
+            h.update(np.ascontiguousarray(a).tobytes())
+        out.append(f"{{len(F)}}:{{h.hexdigest()[:16]}}")
+print("FWHASH " + " ".join(out))
+"""
+
+
+def test_fw_paths_bit_identical():
+    """The three forms of the loop - ring-fed persistent launch (default on one GPU), launch chain with the register-fed
+    pass, launch chain with the ring-fed pass - give the same bits (iterates, histories, stopping iteration).  The
+    switches are read once per process, hence the subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for name, env in (("persistent ring", {}), ("chain", {"ACCBPG_FW_PERSIST": "0"}),
+                      ("chain + ring pass", {"ACCBPG_FW_PERSIST": "0", "ACCBPG_FW_RING": "1"}),
+                      ("chain, nothing before the wait", {"ACCBPG_FW_PERSIST": "0", "ACCBPG_FW_EARLY": "0"})):
+        e = dict(os.environ)
+        for k in ("ACCBPG_FW_PERSIST", "ACCBPG_FW_RING", "ACCBPG_FW_EARLY"):
+            e.pop(k, None)
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", _FW_PATHS_SCRIPT.format(root=root)], env=e, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("FWHASH ")]
+        assert line, (name, r.stdout[-500:])
+        res[name] = line[-1]
+    assert len(set(res.values())) == 1, res
