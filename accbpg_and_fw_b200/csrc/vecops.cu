@@ -995,7 +995,6 @@ static int burgx_launch(Ctx* c, cudaStream_t s, int64_t n, int64_t width, const 
     BurgX X = X0;
     static int onehop = -1;                            // ACCBPG_BURG_ONEHOP=0: the two-level exchange on one rank too
     if (onehop < 0) { const char* e = getenv("ACCBPG_BURG_ONEHOP"); onehop = (e && e[0] == '0') ? 0 : 1; }
-    X.onehop = onehop;
     // the grid depends on `width` only (the widest slice), so every rank uses the same slot layout
     int64_t want = (width + kBurgThreads - 1) / kBurgThreads;
     static int per_sm_x = 0;                           // co-resident blocks per SM of the exchange-form kernel (all variants)
@@ -1013,6 +1012,8 @@ static int burgx_launch(Ctx* c, cudaStream_t s, int64_t n, int64_t width, const 
     if (grid < 1) grid = 1;
     if (width <= 8 * kBurgThreads && X.world == 1) grid = 1;      // small vectors: one block, no exchange (shared memory only)
     const int64_t per = (width + (int64_t)grid * kBurgThreads - 1) / ((int64_t)grid * kBurgThreads);
+    // one hop costs G polls per block and round (G^2 in all): measured 2 us faster per call at 98 blocks, slower at 196
+    X.onehop = onehop && grid <= 128;
     ProfScope ps(P_BURG_SIMPLEX, s);
     if (per <= 1) burg_simplex_x_kernel<1><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
     else if (per <= 2) burg_simplex_x_kernel<2><<<grid, kBurgThreads, 0, s>>>(n, y, g, L, eps, out, info, c->d_status, X, gg_in);
