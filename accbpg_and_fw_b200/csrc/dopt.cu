@@ -492,6 +492,10 @@ struct TrmmParams {
     const int* gate_fX = nullptr;
     const int* gate_fLi = nullptr;
     int gate_nb = 0, gate_epoch = 0, ascending = 0;
+    // tail filler (persistent kernel only): the ascending list leaves out the last `hold0` panels of row block 0, the
+    // descending list ends with them (`ext_cnt` = hold0 there).  A tile of the heaviest row blocks takes 50-67 us at
+    // m = 500 against 17 us for row block 0, so the last wave of the gradient ends on short tiles instead of long ones.
+    int hold0 = 0, ext_cnt = 0;
 };
 
 template <bool ALIGNED16>
@@ -788,8 +792,17 @@ trmm_persistent_kernel(TrmmParams p, const __grid_constant__ CUtensorMap tmL, in
                 ++issued;
                 return;
             }
-            pr_ib = p.ascending ? (int)(tile / npanels) : p.nib - 1 - (int)(tile / npanels);   // default: heaviest first
-            pr_panel = (int)(tile % npanels);
+            if (p.ascending) {
+                const int first0 = (int)npanels - p.hold0;                 // tiles of row block 0 in this list
+                if (tile < first0) { pr_ib = 0; pr_panel = tile; }
+                else { const int t2 = tile - first0; pr_ib = 1 + (int)(t2 / npanels); pr_panel = (int)(t2 % npanels); }
+            } else if (p.ext_cnt > 0 && tile >= tile_limit - p.ext_cnt) {   // the held-back panels of row block 0, last
+                pr_ib = 0;
+                pr_panel = (int)npanels - (tile_limit - tile);
+            } else {
+                pr_ib = p.nib - 1 - (int)(tile / npanels);                 // default: heaviest first
+                pr_panel = (int)(tile % npanels);
+            }
             if (p.gate_fX != nullptr && pr_ib > pr_ready) {   // rows of this row block of L^-1 final?  (64-row block rows 2ib, 2ib+1)
                 for (int J = 2 * pr_ib; J <= 2 * pr_ib + 1 && J < p.gate_nb; ++J) {
                     gate_wait(p.gate_fX + J);
@@ -1362,12 +1375,21 @@ static int dopt_factor_grad(Ctx* c, cudaStream_t s, const double* H, int m, int6
         if (rc) return rc;
         TrmmParams pe = p;
         pe.gate_fX = gate.fX; pe.gate_fLi = gate.fLi; pe.gate_nb = gate.nb; pe.gate_epoch = gate.epoch; pe.ascending = 1;
-        trmm_persistent_kernel<<<early_grid, TRP_THREADS, TRP_SMEM, c->side2>>>(pe, tmL, counters + 1, 0, (int)(n_early * npanels));
+        // panels of row block 0 kept for the end of the late launch (ACCBPG_TRMM_HOLD, per cent of the panels; only when the
+        // tiles are long against the whole gradient, i.e. few tiles per SM: at m = 2000 a tile is 0.2 % of an SM's share)
+        static int hold_pct = -1;
+        if (hold_pct < 0) { const char* e = getenv("ACCBPG_TRMM_HOLD"); hold_pct = e ? atoi(e) : 35; if (hold_pct < 0 || hold_pct > 90) hold_pct = 0; }
+        int hold0 = 0;
+        if (n_early >= 2 && ntiles < 64LL * c->sm_count) hold0 = (int)(npanels * hold_pct / 100);
+        pe.hold0 = hold0;
+        trmm_persistent_kernel<<<early_grid, TRP_THREADS, TRP_SMEM, c->side2>>>(pe, tmL, counters + 1, 0, (int)(n_early * npanels) - hold0);
         ACCBPG_LAUNCHED("trmm_persistent_kernel");
         ACCBPG_CUDA(cudaEventRecord(c->ev_early_done, c->side2));
-        const int limit = (int)((pl.nib - n_early) * npanels);
+        const int limit = (int)((pl.nib - n_early) * npanels) + hold0;
         const int pgrid = (int)((int64_t)c->sm_count < (int64_t)limit ? c->sm_count : limit);
-        trmm_persistent_kernel<<<pgrid, TRP_THREADS, TRP_SMEM, s>>>(p, tmL, counters, 0, limit);
+        TrmmParams pl2 = p;
+        pl2.ext_cnt = hold0;
+        trmm_persistent_kernel<<<pgrid, TRP_THREADS, TRP_SMEM, s>>>(pl2, tmL, counters, 0, limit);
         ACCBPG_LAUNCHED("trmm_persistent_kernel");
         ACCBPG_CUDA(cudaStreamWaitEvent(s, c->ev_early_done, 0));
         int fgd = grid_for(c, n, 256, 2, 8);
