@@ -331,11 +331,14 @@ size_t accbpg_fw_workspace_bytes(int m, int64_t n);   /* zero-filled once by the
  * ctrl <- {log det M, not stopped}.  Sets the ST_X_NEGATIVE / ST_NOT_PD status bits like func_grad. */
 int accbpg_fw_setup(void* ctx, void* stream, const double* d_V, int m, int64_t n, int64_t ldv,
                     const double* d_x0, void* d_ws, double* d_Hinv, double* d_w, double* d_ctrl);
-/* enqueue iterations k_start .. k_start+k_count-1 of the loop (:51-82 / :135-179), five kernels each:
- * argmax w; masked argmin + step rule + history entry + gather of the chosen column; u = Hinv v;
- * Hinv <- (Hinv -/+ c u u^T)/(1 -/+ t); the single pass over V that forms u^T V and updates w and x.
+/* enqueue iterations k_start .. k_start+k_count-1 of the loop (:51-82 / :135-179): argmax w; masked argmin + step
+ * rule + history entry + gather of the chosen column; u = Hinv v; Hinv <- (Hinv -/+ c u u^T)/(1 -/+ t); the single
+ * pass over V that forms u^T V and updates w and x.  When V is 16-byte aligned with even n and ldv this is ONE
+ * persistent launch for the whole batch (one CTA per SM; the pass is fed by tensor copies into a shared-memory
+ * ring, decisions and u are exchanged between the CTAs); otherwise two launches per iteration chained by
+ * programmatic dependent launch.  Same bits either way (ACCBPG_FW_PERSIST=0 forces the launch chain).
  * away = 0: D_opt_FW, 1: D_opt_FW_away.  Once the optimality test fires (ctrl[0] = 1, ctrl[1] = k) the
- * remaining launches are no-ops; ctrl[14] counts the history entries written. */
+ * remaining iterations are not executed; ctrl[14] counts the history entries written. */
 int accbpg_fw_run(void* ctx, void* stream, const double* d_V, int m, int64_t n, int64_t ldv, int away, double eps,
                   int k_start, int k_count, void* d_ws, double* d_Hinv, double* d_x, double* d_w, double* d_ctrl,
                   double* d_hist_F, double* d_hist_SP, double* d_hist_SN, double* d_hist_T);
