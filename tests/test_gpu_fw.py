@@ -42,7 +42,7 @@ def test_fw_away_golden(acc, golden_traj):
 
 
 @pytest.mark.parametrize("away", [0, 1])
-@pytest.mark.parametrize("m,n,seed,its", [(80, 200, 10, 400), (30, 1000, 3, 500), (13, 506, 0, 300)])
+@pytest.mark.parametrize("m,n,seed,its", [(80, 200, 10, 400), (30, 1000, 3, 500), (13, 506, 0, 300), (24, 1001, 6, 300)])
 def test_fw_vertex_indices_bit_exact(acc, golden_ops, away, m, n, seed, its):
     if seed == 0:
         V = golden_ops["housing_H"]
