@@ -43,6 +43,31 @@ def test_library_is_sm100a_with_dmma():
     assert tma.count("DMMA.8x8x4") >= 64 and "UTMALDG" in tma and "SYNCS" in tma
 
 
+def test_frank_wolfe_ring_kernels_are_tma_fed():
+    """The ring-fed Frank-Wolfe kernels stream V with tensor copies signalled on mbarriers (UTMALDG + SYNCS), the
+    persistent one also releases / acquires its flag words at GPU scope."""
+    from accbpg_and_fw_b200 import _native as nat
+    sass = subprocess.run(["cuobjdump", "-sass", nat.LIB_PATH], capture_output=True, text=True).stdout
+    funcs, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            funcs[cur] = []
+        elif cur is not None:
+            funcs[cur].append(line)
+
+    def body(substr):
+        hits = [k for k in funcs if substr in k]
+        assert hits, substr
+        return "\n".join(funcs[hits[0]])
+
+    for k in ("fw_persist_ring_kernel", "fw_pass_ring_kernel"):
+        b = body(k)
+        assert "UTMALDG.3D" in b and "UTMALDG.2D" in b and "SYNCS" in b, k
+    b = body("fw_persist_ring_kernel")
+    assert re.search(r"ST\w*\.E\.64\.STRONG\.GPU", b) and re.search(r"LD\w*\.E\.64\.STRONG\.GPU", b)
+
+
 def test_peer_memory_kernels_use_system_scope_release_acquire():
     """The NVLink peer-memory exchanges rest on: payload stores, a system-scope fence, a release store of the flag word;
     an acquire load of the flag (which also drops stale L1 lines) before the payload is read.  Check that this is what
